@@ -1,0 +1,107 @@
+"""ctypes binding of libgdrn_b200.so (the C ABI declared in include/gdrn_b200.h).
+
+The product path has no CPU fallback: if the shared library is missing or a call fails, we raise.
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgdrn_b200.so")
+
+_lib = None
+
+
+class GdrnError(RuntimeError):
+    pass
+
+
+class GdrnMaps(ctypes.Structure):
+    _fields_ = [
+        ("mask", c_void_p),
+        ("full_mask", c_void_p),
+        ("coor_x", c_void_p),
+        ("coor_y", c_void_p),
+        ("coor_z", c_void_p),
+        ("region", c_void_p),
+    ]
+
+
+_SIGNATURES = {
+    "gdrn_last_error": (c_char_p, []),
+    "gdrn_version": (c_int, []),
+    "gdrn_model_create": (c_int, [POINTER(c_void_p), c_char_p, c_int, c_int]),
+    "gdrn_model_destroy": (None, [c_void_p]),
+    "gdrn_model_load_tensor": (c_int, [c_void_p, c_char_p, c_void_p, c_int64, c_void_p]),
+    "gdrn_model_missing": (c_int, [c_void_p]),
+    "gdrn_model_workspace_bytes": (c_size_t, [c_void_p, c_int]),
+    "gdrn_model_forward": (
+        c_int,
+        [c_void_p] + [c_void_p] * 8 + [c_int] + [c_void_p] * 3 + [POINTER(GdrnMaps), c_void_p, c_size_t, c_void_p],
+    ),
+    "gdrn_model_debug_read": (c_int64, [c_void_p, c_char_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "gdrn_gemm_bf16": (c_int, [c_void_p] * 6 + [c_int] * 6 + [c_void_p]),
+    "farthest_point_sampling": (None, [c_void_p, c_void_p, c_int, c_int]),
+    "farthest_point_sampling_init_center": (None, [c_void_p, c_void_p, c_int, c_int]),
+    "gdrn_fps_set_seed": (None, [c_uint]),
+    "gdrn_fps_cuda": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "rv_generate_hypothesis": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
+    "rv_voting_for_hypothesis": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_float, c_void_p]),
+    "rv_generate_hypothesis_vanishing_point": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
+    "rv_voting_for_hypothesis_vanishing_point": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_float, c_void_p]),
+    "rv_vote_count": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_float, c_int, c_void_p]),
+    "nnd_forward_cuda": (c_int, [c_void_p] * 6 + [c_int] * 3 + [c_void_p]),
+    "nnd_backward_cuda": (c_int, [c_void_p] * 8 + [c_int] * 3 + [c_void_p]),
+    "flow_forward_cuda": (c_int, [c_void_p] * 6 + [c_int] * 3 + [c_void_p]),
+    "uncertainty_pnp": (None, [c_void_p] * 6 + [c_int]),
+    "upnp_batched": (c_int, [c_void_p] * 6 + [c_int, c_int, c_void_p]),
+    "rast_render_depth": (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_float, c_int]
+        + [c_void_p] * 4,
+    ),
+    "rast_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "gdrn_depth_refine_step": (c_int, [c_void_p] * 6 + [c_int, c_int, c_float, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES.keys())
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises GdrnError when the extension is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GdrnError(
+                f"{LIB_PATH} not found: build it with `python -m gdrnpp_bop2022_b200.build` "
+                "(there is no CPU fallback for the product path)"
+            )
+        h = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(h, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def last_error():
+    return lib().gdrn_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what):
+    if rc != 0:
+        raise GdrnError(f"{what} failed (code {rc}): {last_error()}")
+
+
+def ptr(t):
+    """data pointer of a torch tensor (or None)."""
+    if t is None:
+        return None
+    return c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+
+    return c_void_p(torch.cuda.current_stream().cuda_stream)

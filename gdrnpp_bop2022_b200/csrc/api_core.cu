@@ -1,0 +1,50 @@
+// Error channel, version, and the exported plain-GEMM entry (tests + roofline measurement).
+#include <string.h>
+
+#include "common.cuh"
+#include "gemm_tc.h"
+
+static thread_local char g_last_error[512] = "";
+
+void gdrn_set_last_error(const char* file, int line, const char* msg) {
+  const char* base = strrchr(file, '/');
+  snprintf(g_last_error, sizeof(g_last_error), "%s:%d: %s", base ? base + 1 : file, line, msg);
+}
+
+extern "C" const char* gdrn_last_error(void) { return g_last_error; }
+extern "C" int gdrn_version(void) { return 100; }
+
+extern "C" int gdrn_gemm_bf16(const void* A, const void* W, const float* bias, const float* gamma, const float* resid,
+                              void* out, int M, int N, int K, int epi, int out_f32, int block_n, void* stream) {
+  GDRN_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem");
+  GDRN_REQUIRE(K % 8 == 0, "gemm: K must be a multiple of 8 (16-byte TMA row pitch)");
+  GDRN_REQUIRE(epi >= 0 && epi <= 2, "gemm: epi must be 0 (store), 1 (gelu) or 2 (resid)");
+  GemmPlan p;
+  memset(&p, 0, sizeof(p));
+  uint64_t dims_a[2] = {(uint64_t)K, (uint64_t)M};
+  uint64_t str_a[1] = {(uint64_t)K * 2};
+  uint32_t box_a[2] = {64, 128};
+  int rc = make_tmap_bf16(&p.tmap_a, A, 2, dims_a, str_a, box_a);
+  if (rc) return rc;
+  uint64_t dims_b[2] = {(uint64_t)K, (uint64_t)N};
+  uint64_t str_b[1] = {(uint64_t)K * 2};
+  uint32_t box_b[2] = {64, (uint32_t)block_n};
+  rc = make_tmap_bf16(&p.tmap_b, W, 2, dims_b, str_b, box_b);
+  if (rc) return rc;
+  p.a_rank = 2;
+  p.num_taps = 1;
+  p.k_chunks = (K + 63) / 64;
+  p.b_tap_stride = 0;
+  p.m_tiles = (M + 127) / 128;
+  p.n_tiles = (N + block_n - 1) / block_n;
+  p.M = M;
+  p.N = N;
+  p.epi = epi;
+  p.out_f32 = (epi == 2) ? 1 : (epi == 1 ? 0 : out_f32);
+  p.out = out;
+  p.ldo = N;
+  p.bias = bias;
+  p.gamma = gamma;
+  p.resid = resid;
+  return gemm_tc_launch(p, block_n, (cudaStream_t)stream);
+}

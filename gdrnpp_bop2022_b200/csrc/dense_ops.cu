@@ -1,0 +1,485 @@
+// CUDA-core kernels around the tcgen05 GEMMs of the dense path: weight repacking, stem patchify,
+// ConvNeXt depthwise-7x7 + LayerNorm, LayerNorm + 2x2 patchify, GroupNorm/GELU/bilinear, pose lift.
+// Reference semantics: timm 0.6.7 ConvNeXtBlock (third-party), heads/top_down_doublemask_xyz_region_head.py,
+// heads/conv_pnp_net.py, core/utils/rot_reps.py:34-55, models/pose_from_pred_centroid_z.py:56-154,
+// core/utils/utils.py:31-88.
+#include "common.cuh"
+#include "dense_ops.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_kernel(const float* __restrict__ src, void* __restrict__ dst, int dst_is_bf16, PackDesc d) {
+  const long long total = d.dims[0] * d.dims[1] * d.dims[2] * d.dims[3];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    long long i3 = r % d.dims[3]; r /= d.dims[3];
+    long long i2 = r % d.dims[2]; r /= d.dims[2];
+    long long i1 = r % d.dims[1]; r /= d.dims[1];
+    long long i0 = r;
+    float v = src[d.soff + i0 * d.ss[0] + i1 * d.ss[1] + i2 * d.ss[2] + i3 * d.ss[3]];
+    long long o = d.doff + i0 * d.ds[0] + i1 * d.ds[1] + i2 * d.ds[2] + i3 * d.ds[3];
+    if (dst_is_bf16) reinterpret_cast<__nv_bfloat16*>(dst)[o] = __float2bfloat16(v);
+    else reinterpret_cast<float*>(dst)[o] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stem patchify: one thread per output pixel writes one 128-byte row.
+__global__ void stem_patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int H,
+                                     int W) {
+  const int OW = W / 4, OH = H / 4;
+  const long long total = (long long)B * OH * OW;
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= total) return;
+  const int ox = (int)(m % OW);
+  const int oy = (int)((m / OW) % OH);
+  const int b = (int)(m / ((long long)OW * OH));
+  uint4* row = reinterpret_cast<uint4*>(out + m * 64);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v[16];
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      float4 t = *reinterpret_cast<const float4*>(img + (((long long)b * 3 + c) * H + (oy * 4 + ky)) * W + ox * 4);
+      v[ky * 4] = t.x; v[ky * 4 + 1] = t.y; v[ky * 4 + 2] = t.z; v[ky * 4 + 3] = t.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j * 8], v[j * 8 + 1]);
+      __nv_bfloat162 p1 = __floats2bfloat162_rn(v[j * 8 + 2], v[j * 8 + 3]);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j * 8 + 4], v[j * 8 + 5]);
+      __nv_bfloat162 p3 = __floats2bfloat162_rn(v[j * 8 + 6], v[j * 8 + 7]);
+      uint4 u;
+      u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+      u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+      row[c * 2 + j] = u;
+    }
+  }
+  row[6] = make_uint4(0, 0, 0, 0);
+  row[7] = make_uint4(0, 0, 0, 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// depthwise 7x7 + bias + LayerNorm(C).  Block = 256 threads = S strips x (C/4) channel-quads; a strip is TW
+// consecutive output pixels of one image row; a thread owns 4 channels of its strip's TW pixels.
+template <int TW>
+__global__ void __launch_bounds__(256)
+dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ w49c, const float* __restrict__ bias,
+                 const float* __restrict__ ln_w, const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out,
+                 int B, int H, int W, int C, float eps) {
+  __shared__ float red[8][TW];  // [warp][pixel]
+  const int cq = C >> 2;                 // threads per strip
+  const int S = 256 / cq;                // strips per block
+  const int strip = threadIdx.x / cq;
+  const int c4 = (threadIdx.x % cq) * 4;
+  const int strips_per_row = W / TW;
+  const long long strip_id = (long long)blockIdx.x * S + strip;  // over B*H*strips_per_row
+  const long long n_strips = (long long)B * H * strips_per_row;
+  const bool live = strip_id < n_strips;
+  const int sx = live ? (int)(strip_id % strips_per_row) : 0;
+  const int y = live ? (int)((strip_id / strips_per_row) % H) : 0;
+  const int b = live ? (int)(strip_id / ((long long)strips_per_row * H)) : 0;
+  const int x0 = sx * TW;
+
+  float4 acc[TW];
+  {
+    const float4 bv = *reinterpret_cast<const float4*>(bias + c4);
+#pragma unroll
+    for (int i = 0; i < TW; ++i) acc[i] = bv;
+  }
+  if (live) {
+    for (int ky = 0; ky < 7; ++ky) {
+      const int iy = y + ky - 3;
+      if (iy < 0 || iy >= H) continue;
+      float4 wr[7];
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) wr[kx] = __ldg(reinterpret_cast<const float4*>(w49c + (ky * 7 + kx) * C + c4));
+      const float* rowp = x + (((long long)b * H + iy) * W) * C + c4;
+#pragma unroll
+      for (int j = 0; j < TW + 6; ++j) {
+        const int ix = x0 + j - 3;
+        if (ix < 0 || ix >= W) continue;
+        const float4 v = *reinterpret_cast<const float4*>(rowp + (long long)ix * C);
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) {
+          const int o = j - kx;  // output pixel index in the strip: ix = x0 + o + kx - 3
+          if (o >= 0 && o < TW) {
+            acc[o].x = fmaf(v.x, wr[kx].x, acc[o].x);
+            acc[o].y = fmaf(v.y, wr[kx].y, acc[o].y);
+            acc[o].z = fmaf(v.z, wr[kx].z, acc[o].z);
+            acc[o].w = fmaf(v.w, wr[kx].w, acc[o].w);
+          }
+        }
+      }
+    }
+  }
+  // LayerNorm over C: two-pass (mean, then centred variance), reductions over the strip's cq threads.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wps = cq >> 5;               // warps per strip (1, 2, 4, 8)
+  const int w0 = strip * wps;            // first warp of this strip
+  float mean[TW];
+#pragma unroll
+  for (int i = 0; i < TW; ++i) {
+    float s = (acc[i].x + acc[i].y) + (acc[i].z + acc[i].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    mean[i] = s;
+  }
+  if (wps > 1) {
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < TW; ++i) red[warp][i] = mean[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < TW; ++i) {
+      float s = 0.f;
+      for (int k = 0; k < wps; ++k) s += red[w0 + k][i];
+      mean[i] = s;
+    }
+    __syncthreads();
+  }
+  const float invC = 1.0f / (float)C;
+  float rstd[TW];
+#pragma unroll
+  for (int i = 0; i < TW; ++i) {
+    mean[i] *= invC;
+    float dx = acc[i].x - mean[i], dy = acc[i].y - mean[i], dz = acc[i].z - mean[i], dw = acc[i].w - mean[i];
+    float s = (dx * dx + dy * dy) + (dz * dz + dw * dw);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    rstd[i] = s;
+  }
+  if (wps > 1) {
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < TW; ++i) red[warp][i] = rstd[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < TW; ++i) {
+      float s = 0.f;
+      for (int k = 0; k < wps; ++k) s += red[w0 + k][i];
+      rstd[i] = s;
+    }
+  }
+  if (!live) return;
+  const float4 gw = *reinterpret_cast<const float4*>(ln_w + c4);
+  const float4 gb = *reinterpret_cast<const float4*>(ln_b + c4);
+  __nv_bfloat16* orow = out + ((((long long)b * H + y) * W) + x0) * C + c4;
+#pragma unroll
+  for (int i = 0; i < TW; ++i) {
+    const float r = rsqrtf(rstd[i] * invC + eps);
+    float o0 = fmaf((acc[i].x - mean[i]) * r, gw.x, gb.x);
+    float o1 = fmaf((acc[i].y - mean[i]) * r, gw.y, gb.y);
+    float o2 = fmaf((acc[i].z - mean[i]) * r, gw.z, gb.z);
+    float o3 = fmaf((acc[i].w - mean[i]) * r, gw.w, gb.w);
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&p0);
+    u.y = *reinterpret_cast<uint32_t*>(&p1);
+    *reinterpret_cast<uint2*>(orow + (long long)i * C) = u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm2d + 2x2 stride-2 patchify: one warp per source pixel.
+__global__ void __launch_bounds__(256)
+ln_patchify2_kernel(const float* __restrict__ x, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                    __nv_bfloat16* __restrict__ out, int B, int H, int W, int C, float eps) {
+  const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long total = (long long)B * H * W;
+  if (pix >= total) return;
+  const int lane = threadIdx.x & 31;
+  const int px = (int)(pix % W);
+  const int py = (int)((pix / W) % H);
+  const int b = (int)(pix / ((long long)W * H));
+  const float* src = x + pix * C;
+  const int nv = C >> 7;  // float4 per lane: C/128 (1, 2, 4)
+  float4 v[4];
+  float s = 0.f;
+  for (int k = 0; k < nv; ++k) {
+    v[k] = *reinterpret_cast<const float4*>(src + (k * 32 + lane) * 4);
+    s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float q = 0.f;
+  for (int k = 0; k < nv; ++k) {
+    float dx = v[k].x - mean, dy = v[k].y - mean, dz = v[k].z - mean, dw = v[k].w - mean;
+    q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float r = rsqrtf(q / (float)C + eps);
+  const long long m2 = ((long long)b * (H / 2) + (py >> 1)) * (W / 2) + (px >> 1);
+  __nv_bfloat16* dst = out + m2 * (4LL * C) + ((py & 1) * 2 + (px & 1)) * C;
+  for (int k = 0; k < nv; ++k) {
+    const int c = (k * 32 + lane) * 4;
+    const float4 gw = *reinterpret_cast<const float4*>(ln_w + c);
+    const float4 gb = *reinterpret_cast<const float4*>(ln_b + c);
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaf((v[k].x - mean) * r, gw.x, gb.x), fmaf((v[k].y - mean) * r, gw.y, gb.y));
+    __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaf((v[k].z - mean) * r, gw.z, gb.z), fmaf((v[k].w - mean) * r, gw.w, gb.w));
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&p0);
+    u.y = *reinterpret_cast<uint32_t*>(&p1);
+    *reinterpret_cast<uint2*>(dst + c) = u;
+  }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n;
+       i += (long long)gridDim.x * blockDim.x * 4) {
+    if (i + 3 < n) {
+      float4 v = *reinterpret_cast<const float4*>(src + i);
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&p0);
+      u.y = *reinterpret_cast<uint32_t*>(&p1);
+      *reinterpret_cast<uint2*>(dst + i) = u;
+    } else {
+      for (long long j = i; j < n; ++j) dst[j] = __float2bfloat16(src[j]);
+    }
+  }
+}
+
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = __bfloat162float(src[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm apply + exact-erf GELU (+ bilinear x2, align_corners=True).  One thread per (output pixel, 8 channels).
+__device__ __forceinline__ void load8(const void* raw, int is_f32, long long off, float (&v)[8]) {
+  if (is_f32) {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(raw) + off);
+    float4 a = p[0], b = p[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(raw) + off);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 f = __bfloat1622float2(h[k]);
+      v[2 * k] = f.x; v[2 * k + 1] = f.y;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gn_gelu_kernel(const void* __restrict__ raw, int raw_is_f32, const double* __restrict__ stats,
+               const float* __restrict__ gn_w, const float* __restrict__ gn_b, __nv_bfloat16* __restrict__ out, int B,
+               int h, int w, int C, int groups, float eps, int up) {
+  const int cv = C >> 3;
+  const int oh = h * up, ow = w * up;
+  const long long total = (long long)B * oh * ow * cv;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % cv) * 8;
+  const long long p = idx / cv;
+  const int ox = (int)(p % ow);
+  const int oy = (int)((p / ow) % oh);
+  const int b = (int)(p / ((long long)ow * oh));
+  const int cpg = C / groups;
+  // per-channel scale/shift: y = v * a + s
+  float a[8], s[8];
+  {
+    const double n = (double)h * w * cpg;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int g = (c8 + k) / cpg;
+      const double su = stats[((long long)b * groups + g) * 2], sq = stats[((long long)b * groups + g) * 2 + 1];
+      const double mean = su / n;
+      double var = sq / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float r = (float)(1.0 / sqrt(var + (double)eps));
+      const float gw = __ldg(gn_w + c8 + k), gb = __ldg(gn_b + c8 + k);
+      a[k] = r * gw;
+      s[k] = fmaf(-(float)mean, a[k], gb);
+    }
+  }
+  float o[8];
+  if (up == 1) {
+    float v[8];
+    load8(raw, raw_is_f32, (((long long)b * h + oy) * w + ox) * C + c8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = gelu_erf(fmaf(v[k], a[k], s[k]));
+  } else {
+    // nn.UpsamplingBilinear2d(scale_factor=2): align_corners=True, src = dst * (in-1)/(out-1)
+    const float fy = (oh > 1) ? (float)oy * ((float)(h - 1) / (float)(oh - 1)) : 0.f;
+    const float fx = (ow > 1) ? (float)ox * ((float)(w - 1) / (float)(ow - 1)) : 0.f;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    float v00[8], v01[8], v10[8], v11[8];
+    load8(raw, raw_is_f32, (((long long)b * h + y0) * w + x0) * C + c8, v00);
+    load8(raw, raw_is_f32, (((long long)b * h + y0) * w + x1) * C + c8, v01);
+    load8(raw, raw_is_f32, (((long long)b * h + y1) * w + x0) * C + c8, v10);
+    load8(raw, raw_is_f32, (((long long)b * h + y1) * w + x1) * C + c8, v11);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float g00 = gelu_erf(fmaf(v00[k], a[k], s[k])), g01 = gelu_erf(fmaf(v01[k], a[k], s[k]));
+      float g10 = gelu_erf(fmaf(v10[k], a[k], s[k])), g11 = gelu_erf(fmaf(v11[k], a[k], s[k]));
+      o[k] = w00 * g00 + w01 * g01 + w10 * g10 + w11 * g11;
+    }
+  }
+  uint4 u;
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
+  __nv_bfloat162 p2 = __floats2bfloat162_rn(o[4], o[5]), p3 = __floats2bfloat162_rn(o[6], o[7]);
+  u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+  u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+  *reinterpret_cast<uint4*>(out + (((long long)b * oh + oy) * ow + ox) * C + c8) = u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pose lift, one thread per ROI.  fp32 steps mirror the torch ops one rounding at a time
+// (rot_reps.py:34-55, pose_from_pred_centroid_z.py:74-113); allo->ego in fp64 like the numpy path
+// (utils.py:31-88 + transforms3d.axangles.axangle2mat).
+__global__ void pose_lift_kernel(const float* __restrict__ raw, int ld, const float* __restrict__ cams,
+                                 const float* __restrict__ centers, const float* __restrict__ whs,
+                                 const float* __restrict__ ratios, float* __restrict__ out_rot,
+                                 float* __restrict__ out_trans, float* __restrict__ out_raw9, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const float* r = raw + (long long)i * ld;
+  if (out_raw9) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) out_raw9[i * 9 + k] = r[k];
+  }
+  // --- rot6d -> matrix (columns x, y, z) ---
+  float a0 = r[0], a1 = r[1], a2 = r[2], b0 = r[3], b1 = r[4], b2 = r[5];
+  float na = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)), __fmul_rn(a2, a2)));
+  na = fmaxf(na, 1e-12f);
+  float x0 = __fdiv_rn(a0, na), x1 = __fdiv_rn(a1, na), x2 = __fdiv_rn(a2, na);
+  // z = cross(x, y_raw)
+  float z0 = __fsub_rn(__fmul_rn(x1, b2), __fmul_rn(x2, b1));
+  float z1 = __fsub_rn(__fmul_rn(x2, b0), __fmul_rn(x0, b2));
+  float z2 = __fsub_rn(__fmul_rn(x0, b1), __fmul_rn(x1, b0));
+  float nz = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(z0, z0), __fmul_rn(z1, z1)), __fmul_rn(z2, z2)));
+  nz = fmaxf(nz, 1e-12f);
+  z0 = __fdiv_rn(z0, nz); z1 = __fdiv_rn(z1, nz); z2 = __fdiv_rn(z2, nz);
+  // y = cross(z, x)
+  float y0 = __fsub_rn(__fmul_rn(z1, x2), __fmul_rn(z2, x1));
+  float y1 = __fsub_rn(__fmul_rn(z2, x0), __fmul_rn(z0, x2));
+  float y2 = __fsub_rn(__fmul_rn(z0, x1), __fmul_rn(z1, x0));
+  float Ra[9] = {x0, y0, z0, x1, y1, z1, x2, y2, z2};  // row-major, columns (x,y,z)
+  // --- translation ---
+  const float* K = cams + i * 9;
+  float cx = __fadd_rn(__fmul_rn(r[6], whs[i * 2]), centers[i * 2]);
+  float cy = __fadd_rn(__fmul_rn(r[7], whs[i * 2 + 1]), centers[i * 2 + 1]);
+  float z = __fmul_rn(r[8], ratios[i]);
+  float tx = __fdiv_rn(__fmul_rn(z, __fsub_rn(cx, K[2])), K[0]);
+  float ty = __fdiv_rn(__fmul_rn(z, __fsub_rn(cy, K[5])), K[4]);
+  out_trans[i * 3] = tx; out_trans[i * 3 + 1] = ty; out_trans[i * 3 + 2] = z;
+  // --- allocentric -> egocentric ---
+  float nt = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(tx, tx), __fmul_rn(ty, ty)), __fmul_rn(z, z)));
+  float ox = __fdiv_rn(tx, nt), oy = __fdiv_rn(ty, nt), oz = __fdiv_rn(z, nt);  // obj_ray (float32)
+  double dotv = (double)oz;  // cam_ray (0,0,1) . obj_ray
+  double angle = acos(dotv);
+  float* Ro = out_rot + i * 9;
+  if (angle > 0.0) {
+    // axis = cross((0,0,1), obj_ray) = (-oy, ox, 0)
+    double ax = -(double)oy, ay = (double)ox, az = 0.0;
+    double n = sqrt(ax * ax + ay * ay + az * az);
+    ax /= n; ay /= n; az /= n;
+    double c = cos(angle), s = sin(angle), Cc = 1.0 - c;
+    double xs = ax * s, ys = ay * s, zs = az * s;
+    double xC = ax * Cc, yC = ay * Cc, zC = az * Cc;
+    double xyC = ax * yC, yzC = ay * zC, zxC = az * xC;
+    double M[9] = {ax * xC + c, xyC - zs, zxC + ys, xyC + zs, ay * yC + c, yzC - xs, zxC - ys, yzC + xs, az * zC + c};
+#pragma unroll
+    for (int rr = 0; rr < 3; ++rr)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        double acc = M[rr * 3] * (double)Ra[cc] + M[rr * 3 + 1] * (double)Ra[3 + cc] + M[rr * 3 + 2] * (double)Ra[6 + cc];
+        Ro[rr * 3 + cc] = (float)acc;
+      }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Ro[k] = Ra[k];
+  }
+}
+
+}  // namespace
+
+// ================================================================================================
+int launch_pack(const float* src, void* dst, int dst_is_bf16, const PackDesc& d, cudaStream_t st) {
+  long long total = d.dims[0] * d.dims[1] * d.dims[2] * d.dims[3];
+  if (total <= 0) return GDRN_OK;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 4096) blocks = 4096;
+  pack_kernel<<<(int)blocks, 256, 0, st>>>(src, dst, dst_is_bf16, d);
+  GDRN_CHECK_CUDA(cudaGetLastError());
+  return GDRN_OK;
+}
+
+int launch_stem_patchify(const float* img, __nv_bfloat16* out, int B, int H, int W, cudaStream_t st) {
+  GDRN_REQUIRE(H % 4 == 0 && W % 4 == 0, "stem: H, W must be multiples of 4");
+  long long total = (long long)B * (H / 4) * (W / 4);
+  stem_patchify_kernel<<<(int)((total + 127) / 128), 128, 0, st>>>(img, out, B, H, W);
+  GDRN_CHECK_CUDA(cudaGetLastError());
+  return GDRN_OK;
+}
+
+int launch_dwconv_ln(const float* x, const float* w49c, const float* bias, const float* ln_w, const float* ln_b,
+                     __nv_bfloat16* out, int B, int H, int W, int C, float eps, cudaStream_t st) {
+  GDRN_REQUIRE(C % 128 == 0 && C <= 1024, "dwconv: C must be a multiple of 128 and <= 1024");
+  const int S = 256 / (C / 4);
+  if (W % 16 == 0) {
+    long long strips = (long long)B * H * (W / 16);
+    dwconv_ln_kernel<16><<<(int)((strips + S - 1) / S), 256, 0, st>>>(x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps);
+  } else {
+    GDRN_REQUIRE(W % 8 == 0, "dwconv: W must be a multiple of 8");
+    long long strips = (long long)B * H * (W / 8);
+    dwconv_ln_kernel<8><<<(int)((strips + S - 1) / S), 256, 0, st>>>(x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps);
+  }
+  GDRN_CHECK_CUDA(cudaGetLastError());
+  return GDRN_OK;
+}
+
+int launch_ln_patchify2(const float* x, const float* ln_w, const float* ln_b, __nv_bfloat16* out, int B, int H, int W,
+                        int C, float eps, cudaStream_t st) {
+  GDRN_REQUIRE(C % 128 == 0 && C <= 512 && H % 2 == 0 && W % 2 == 0, "ln_patchify2: unsupported shape");
+  long long total = (long long)B * H * W;
+  ln_patchify2_kernel<<<(int)((total + 7) / 8), 256, 0, st>>>(x, ln_w, ln_b, out, B, H, W, C, eps);
+  GDRN_CHECK_CUDA(cudaGetLastError());
+  return GDRN_OK;
+}
+
+int launch_cast_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t st) {
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 8192) blocks = 8192;
+  cast_bf16_kernel<<<(int)blocks, 256, 0, st>>>(src, dst, n);
+  GDRN_CHECK_CUDA(cudaGetLastError());
+  return GDRN_OK;
+}
+
+int launch_bf16_to_f32(const __nv_bfloat16* src, float* dst, long long n, cudaStream_t st) {
+  long long blocks = (n + 255) / 256;
+  if (blocks > 8192) blocks = 8192;
+  bf16_to_f32_kernel<<<(int)blocks, 256, 0, st>>>(src, dst, n);
+  GDRN_CHECK_CUDA(cudaGetLastError());
+  return GDRN_OK;
+}
+
+int launch_gn_gelu(const void* raw, int raw_is_f32, const double* stats, const float* gn_w, const float* gn_b,
+                   __nv_bfloat16* out, int B, int h, int w, int C, int groups, float eps, int up, cudaStream_t st) {
+  GDRN_REQUIRE(C % 8 == 0 && (up == 1 || up == 2), "gn_gelu: unsupported shape");
+  long long total = (long long)B * h * up * w * up * (C / 8);
+  gn_gelu_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(raw, raw_is_f32, stats, gn_w, gn_b, out, B, h, w, C, groups,
+                                                            eps, up);
+  GDRN_CHECK_CUDA(cudaGetLastError());
+  return GDRN_OK;
+}
+
+int launch_pose_lift(const float* raw, int ld, const float* cams, const float* centers, const float* whs,
+                     const float* ratios, float* out_rot, float* out_trans, float* out_raw9, int B, cudaStream_t st) {
+  pose_lift_kernel<<<(B + 63) / 64, 64, 0, st>>>(raw, ld, cams, centers, whs, ratios, out_rot, out_trans, out_raw9, B);
+  GDRN_CHECK_CUDA(cudaGetLastError());
+  return GDRN_OK;
+}

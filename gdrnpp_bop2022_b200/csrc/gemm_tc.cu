@@ -1,0 +1,566 @@
+// tcgen05 + TMA implicit-GEMM kernel for the GDRNPP dense path (sm_100a).
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0 lane 0 : TMA producer  (A pixel boxes + W tiles -> 128B-swizzled smem ring)
+//   warp 1 lane 0 : tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16, bf16 -> fp32 accumulators in TMEM)
+//   warp 2        : TMEM allocate / free
+//   warps 4..7    : epilogue (tcgen05.ld -> registers -> fused math -> global), double-buffered
+//                   against the next tile's MMAs through two TMEM accumulator stages.
+//
+// It replaces, for the reference forward (core/gdrn_modeling/models/GDRN_double_mask.py:102-160), every
+// cuDNN/cuBLAS call made by timm ConvNeXt (Linear fc1/fc2, stem 4x4s4, 2x2s2 downsample), by the geometry
+// head (heads/top_down_doublemask_xyz_region_head.py:177-211: ConvTranspose2d, six 3x3 convs, 1x1 out
+// conv) and by ConvPnPNet (heads/conv_pnp_net.py:120-183: three 3x3 s2 convs and four Linear layers).
+#include "common.cuh"
+#include "gemm_tc.h"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr int NUM_THREADS = 256;
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
+  static constexpr int ACC_COLS = BLOCK_N <= 128 ? 128 : 256;  // TMEM columns per accumulator stage
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct RowInfo {
+  long long orow;  // output row index
+  int b;           // image index (rank 4/5) or row / rows_per_roi
+  bool valid;
+};
+
+__device__ __forceinline__ RowInfo map_row(const GemmPlan& p, int m_tile, int r) {
+  RowInfo ri;
+  if (p.a_rank == 2) {
+    long long grow = (long long)m_tile * BLOCK_M + r;
+    ri.orow = grow;
+    ri.valid = grow < p.M;
+    ri.b = p.rows_per_roi > 0 ? (int)(grow / p.rows_per_roi) : 0;
+  } else {
+    int tx = m_tile % p.tiles_x;
+    int t2 = m_tile / p.tiles_x;
+    int ty = t2 % p.tiles_y;
+    int tb = t2 / p.tiles_y;
+    int ix = r & ((1 << p.lg_bw) - 1);
+    int iy = (r >> p.lg_bw) & ((1 << p.lg_bh) - 1);
+    int ib = r >> (p.lg_bw + p.lg_bh);
+    int b = (tb << p.lg_bb) + ib;
+    int y = (ty << p.lg_bh) + iy;
+    int x = (tx << p.lg_bw) + ix;
+    ri.b = b;
+    ri.valid = b < p.M;
+    ri.orow = ((long long)b * p.OH + (y * p.osy + p.ooy)) * p.OW + (x * p.osx + p.oox);
+  }
+  return ri;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int CH>
+__device__ __forceinline__ void store_row_chunk(const GemmPlan& p, const RowInfo& ri, int col, const float (&v)[CH],
+                                                bool f32) {
+  // col is a multiple of CH; columns >= N are dropped
+  int nvalid = p.N - col;
+  if (nvalid <= 0) return;
+  if (f32) {
+    float* o = reinterpret_cast<float*>(p.out) + ri.orow * p.ldo + col;
+    if (nvalid >= CH) {
+#pragma unroll
+      for (int j = 0; j < CH; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+        if (j < nvalid) o[j] = v[j];
+    }
+  } else {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + ri.orow * p.ldo + col;
+    if (nvalid >= CH) {
+#pragma unroll
+      for (int j = 0; j < CH; j += 8) {
+        uint4 u;
+        u.x = pack_bf16(v[j], v[j + 1]);
+        u.y = pack_bf16(v[j + 2], v[j + 3]);
+        u.z = pack_bf16(v[j + 4], v[j + 5]);
+        u.w = pack_bf16(v[j + 6], v[j + 7]);
+        *reinterpret_cast<uint4*>(o + j) = u;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CH; ++j)
+        if (j < nvalid) o[j] = __float2bfloat16(v[j]);
+    }
+  }
+}
+
+template <int CH>
+__device__ __forceinline__ void load_vec(const float* __restrict__ src, int col, int N, float (&v)[CH]) {
+  if (src == nullptr) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) v[j] = 0.f;
+    return;
+  }
+  if (col + CH <= N) {
+#pragma unroll
+    for (int j = 0; j < CH; j += 4) {
+      float4 t = __ldg(reinterpret_cast<const float4*>(src + col + j));
+      v[j] = t.x; v[j + 1] = t.y; v[j + 2] = t.z; v[j + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) v[j] = (col + j < N) ? __ldg(src + col + j) : 0.f;
+  }
+}
+
+template <int CH>
+__device__ __forceinline__ void tmem_load_chunk(uint32_t taddr, float (&v)[CH]) {
+  if constexpr (CH == 32) {
+    uint32_t r[32];
+    ptx::tmem_ld32(taddr, r);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  } else {
+    uint32_t r[16];
+    ptx::tmem_ld16(taddr, r);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Epilogues.  Each of the 128 epilogue threads owns one accumulator row (TMEM lane).
+// ------------------------------------------------------------------------------------------------
+template <int BLOCK_N, int EPI>
+__device__ __forceinline__ void epilogue_tile(const GemmPlan& p, int m_tile, int n_tile, uint32_t tmem_row, int lane) {
+  constexpr int CH = BLOCK_N >= 32 ? 32 : 16;
+  const int r = ((threadIdx.x >> 5) & 3) * 32 + lane;
+  const RowInfo ri = map_row(p, m_tile, r);
+  const int n0 = n_tile * BLOCK_N;
+
+  if constexpr (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_RESID) {
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += CH) {
+      float v[CH];
+      tmem_load_chunk<CH>(tmem_row + c, v);
+      const int col = n0 + c;
+      if (!ri.valid || col >= p.N) continue;
+      float bias[CH];
+      load_vec<CH>(p.bias, col, p.N, bias);
+      if constexpr (EPI == EPI_STORE) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] += bias[j];
+        store_row_chunk<CH>(p, ri, col, v, p.out_f32 != 0);
+      } else if constexpr (EPI == EPI_GELU) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] = gelu_fast(v[j] + bias[j]);
+        store_row_chunk<CH>(p, ri, col, v, false);
+      } else {  // EPI_RESID
+        float g[CH], x[CH];
+        load_vec<CH>(p.gamma, col, p.N, g);
+        const float* rs = p.resid + ri.orow * p.ldo + col;
+#pragma unroll
+        for (int j = 0; j < CH; j += 4) {
+          float4 t = *reinterpret_cast<const float4*>(rs + j);
+          x[j] = t.x; x[j + 1] = t.y; x[j + 2] = t.z; x[j + 3] = t.w;
+        }
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] = fmaf(g[j], v[j] + bias[j], x[j]);
+        store_row_chunk<CH>(p, ri, col, v, true);
+      }
+    }
+  } else if constexpr (EPI == EPI_GNSTATS) {
+    const int cpg = p.gn_cpg;  // 4 or 8
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += CH) {
+      float v[CH];
+      tmem_load_chunk<CH>(tmem_row + c, v);
+      const int col = n0 + c;
+      if (col >= p.N) continue;
+      if (ri.valid) store_row_chunk<CH>(p, ri, col, v, p.out_f32 != 0);
+      // per-group partial sums over this thread's row (stats use the values as stored)
+      float s[8], ss[8];
+#pragma unroll
+      for (int g = 0; g < 8; ++g) { s[g] = 0.f; ss[g] = 0.f; }
+      if (!p.out_f32) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] = __bfloat162float(__float2bfloat16(v[j]));
+      }
+      if (cpg == 8) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) { s[j >> 3] += v[j]; ss[j >> 3] = fmaf(v[j], v[j], ss[j >> 3]); }
+      } else {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) { s[j >> 2] += v[j]; ss[j >> 2] = fmaf(v[j], v[j], ss[j >> 2]); }
+      }
+      const int ng = CH / cpg;  // groups in this chunk (4 or 8)
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        if (g < ng) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            s[g] += __shfl_xor_sync(0xffffffffu, s[g], o);
+            ss[g] += __shfl_xor_sync(0xffffffffu, ss[g], o);
+          }
+        }
+      }
+      if (ri.valid) {  // warp-uniform: a warp's 32 rows lie in one image
+        double* st = p.gn_stats + ((long long)ri.b * p.gn_groups + col / cpg) * 2;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          if (g < ng && lane == g) {
+            atomicAdd(st + 2 * g, (double)s[g]);
+            atomicAdd(st + 2 * g + 1, (double)ss[g]);
+          }
+        }
+      }
+    }
+  } else if constexpr (EPI == EPI_BIAS_LN) {
+    // N <= BLOCK_N (N % 32 == 0): the thread sees the whole channel vector of its pixel. Three TMEM passes.
+    float sum = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < p.N; c += CH) {
+      float v[CH], bias[CH];
+      tmem_load_chunk<CH>(tmem_row + c, v);
+      load_vec<CH>(p.bias, c, p.N, bias);
+#pragma unroll
+      for (int j = 0; j < CH; ++j) sum += v[j] + bias[j];
+    }
+    const float mean = sum / (float)p.N;
+    float sq = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < p.N; c += CH) {
+      float v[CH], bias[CH];
+      tmem_load_chunk<CH>(tmem_row + c, v);
+      load_vec<CH>(p.bias, c, p.N, bias);
+#pragma unroll
+      for (int j = 0; j < CH; ++j) { float d = v[j] + bias[j] - mean; sq = fmaf(d, d, sq); }
+    }
+    const float rstd = rsqrtf(sq / (float)p.N + p.ln_eps);
+#pragma unroll 1
+    for (int c = 0; c < p.N; c += CH) {
+      float v[CH], bias[CH], w[CH], bb[CH];
+      tmem_load_chunk<CH>(tmem_row + c, v);
+      load_vec<CH>(p.bias, c, p.N, bias);
+      load_vec<CH>(p.ln_w, c, p.N, w);
+      load_vec<CH>(p.ln_b, c, p.N, bb);
+#pragma unroll
+      for (int j = 0; j < CH; ++j) v[j] = fmaf((v[j] + bias[j] - mean) * rstd, w[j], bb[j]);
+      if (ri.valid) store_row_chunk<CH>(p, ri, c, v, true);
+    }
+  } else if constexpr (EPI == EPI_OUTCONV) {
+    // BLOCK_N == 80: [vis, full, x, y, z, region_0..64, pad x10] of the ROI's own class
+    // (GDRN_double_mask.py:107-126 gather + :131-148 feature assembly + conv_pnp_net.py:130-136).
+    float v[80];
+    {
+      float t[32];
+      tmem_load_chunk<32>(tmem_row, t);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = t[j];
+      tmem_load_chunk<32>(tmem_row + 32, t);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[32 + j] = t[j];
+      float t16[16];
+      tmem_load_chunk<16>(tmem_row + 64, t16);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[64 + j] = t16[j];
+    }
+    if (ri.valid) {
+      const int b = ri.b;
+      const int pix = (int)(ri.orow - (long long)b * p.rows_per_roi);
+      const int cls = (int)p.roi_classes[b];
+      const float* ob = p.oc_bias + cls * 80;
+#pragma unroll
+      for (int j = 0; j < 72; j += 4) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(ob + j));
+        v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+      }
+      const long long hw = p.rows_per_roi;
+      if (p.map_mask) {
+        p.map_mask[(long long)b * hw + pix] = v[0];
+        p.map_full[(long long)b * hw + pix] = v[1];
+        p.map_x[(long long)b * hw + pix] = v[2];
+        p.map_y[(long long)b * hw + pix] = v[3];
+        p.map_z[(long long)b * hw + pix] = v[4];
+#pragma unroll
+        for (int j = 0; j < 65; ++j) p.map_region[((long long)b * 65 + j) * hw + pix] = v[5 + j];
+      }
+      // softmax over region[1:65] = v[6..69]
+      float mx = v[6];
+#pragma unroll
+      for (int j = 7; j < 70; ++j) mx = fmaxf(mx, v[j]);
+      float den = 0.f;
+#pragma unroll
+      for (int j = 6; j < 70; ++j) { v[j] = __expf(v[j] - mx); den += v[j]; }
+      const float inv = 1.0f / den;
+      const float ex = __ldg(p.roi_extents + b * 3 + 0), ey = __ldg(p.roi_extents + b * 3 + 1),
+                  ez = __ldg(p.roi_extents + b * 3 + 2);
+      float f[72];
+      f[0] = (v[2] - 0.5f) * ex;
+      f[1] = (v[3] - 0.5f) * ey;
+      f[2] = (v[4] - 0.5f) * ez;
+      f[3] = __ldg(p.roi_coord_2d + ((long long)b * 2 + 0) * hw + pix);
+      f[4] = __ldg(p.roi_coord_2d + ((long long)b * 2 + 1) * hw + pix);
+#pragma unroll
+      for (int j = 0; j < 64; ++j) f[5 + j] = v[6 + j] * inv;
+      f[69] = 0.f; f[70] = 0.f; f[71] = 0.f;
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.pnp_in) + ri.orow * 128);
+#pragma unroll
+      for (int j = 0; j < 72; j += 8) {
+        uint4 u;
+        u.x = pack_bf16(f[j], f[j + 1]);
+        u.y = pack_bf16(f[j + 2], f[j + 3]);
+        u.z = pack_bf16(f[j + 4], f[j + 5]);
+        u.w = pack_bf16(f[j + 6], f[j + 7]);
+        dst[j >> 3] = u;
+      }
+#pragma unroll
+      for (int j = 9; j < 16; ++j) dst[j] = make_uint4(0, 0, 0, 0);
+    }
+  }
+}
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmPlan p) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment required by SWIZZLE_128B
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES +
+                                                                            8 * (2 * C::STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.tmap_a);
+    ptx::prefetch_tmap(&p.tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(tfull_bar(s), 1);
+      ptx::mbar_init(tempty_bar(s), 4);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int k_iters = p.num_taps * p.k_chunks;
+
+  if (warp == 0 && lane == 0) {
+    // ================= TMA producer =================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      int x0 = 0, y0 = 0, b0 = 0;
+      if (p.a_rank != 2) {
+        int tx = m_tile % p.tiles_x;
+        int t2 = m_tile / p.tiles_x;
+        x0 = tx << p.lg_bw;
+        y0 = (t2 % p.tiles_y) << p.lg_bh;
+        b0 = (t2 / p.tiles_y) << p.lg_bb;
+      }
+      int brow = n_tile * BLOCK_N;
+      if (EPI == EPI_OUTCONV) {
+        long long grow = (long long)m_tile * BLOCK_M;
+        int b = (int)(grow / p.rows_per_roi);
+        brow += (int)p.roi_classes[b] * p.b_rows_per_class;
+      }
+      for (int tap = 0; tap < p.num_taps; ++tap) {
+        const GemmTap tp = p.taps[tap];
+        for (int kc = 0; kc < p.k_chunks; ++kc) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t sb = sa + A_STAGE_BYTES;
+          ptx::mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          const int k0 = kc * BLOCK_K;
+          if (p.a_rank == 2) {
+            ptx::tma_load_2d(sa, &p.tmap_a, full_bar(stage), k0, m_tile * BLOCK_M);
+          } else if (p.a_rank == 4) {
+            ptx::tma_load_4d(sa, &p.tmap_a, full_bar(stage), k0 + tp.c0, x0 + tp.d1, y0 + tp.d2, b0);
+          } else {
+            ptx::tma_load_5d(sa, &p.tmap_a, full_bar(stage), k0 + tp.c0, x0 + tp.d1, tp.d2, y0 + tp.d3, b0);
+          }
+          ptx::tma_load_2d(sb, &p.tmap_b, full_bar(stage), tap * p.b_tap_stride + k0, brow);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = ptx::make_idesc_bf16(BLOCK_M, BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      ptx::mbar_wait(tempty_bar(as), aphase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * C::ACC_COLS;
+      for (int k = 0; k < k_iters; ++k) {
+        ptx::mbar_wait(full_bar(stage), phase);
+        ptx::tc_fence_after();
+        const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+        const uint32_t sb = sa + A_STAGE_BYTES;
+        const uint64_t adesc = ptx::make_sw128_kmajor_desc(sa);
+        const uint64_t bdesc = ptx::make_sw128_kmajor_desc(sb);
+#pragma unroll
+        for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+          // advance 16 bf16 = 32 B inside the 128B swizzle row: +2 in the (addr >> 4) field
+          ptx::tc_mma_bf16(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+        }
+        ptx::tc_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+      ptx::tc_commit(tfull_bar(as));  // accumulator complete
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue =================
+    const int q = warp & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      ptx::mbar_wait(tfull_bar(as), aphase);
+      ptx::tc_fence_after();
+      const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * C::ACC_COLS;
+      epilogue_tile<BLOCK_N, EPI>(p, m_tile, n_tile, tmem_row, lane);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BLOCK_N, int EPI>
+int launch_inst(const GemmPlan& plan, cudaStream_t stream) {
+  using C = Cfg<BLOCK_N>;
+  static bool configured = false;
+  auto kfn = gemm_tc_kernel<BLOCK_N, EPI>;
+  if (!configured) {
+    GDRN_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  int total = plan.m_tiles * plan.n_tiles;
+  if (total <= 0) return GDRN_OK;
+  int grid = total < gdrn_num_sms() ? total : gdrn_num_sms();
+  kfn<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(plan);
+  GDRN_CHECK_CUDA(cudaGetLastError());
+  return GDRN_OK;
+}
+
+}  // namespace
+
+int gemm_tc_launch(const GemmPlan& plan, int block_n, cudaStream_t stream) {
+  GDRN_REQUIRE(plan.a_rank == 2 || plan.a_rank == 4 || plan.a_rank == 5, "gemm: bad a_rank");
+  GDRN_REQUIRE(plan.num_taps >= 1 && plan.num_taps <= 9, "gemm: bad num_taps");
+#define GDRN_GEMM_CASE(BN, E) \
+  if (block_n == BN && plan.epi == E) return launch_inst<BN, E>(plan, stream);
+  GDRN_GEMM_CASE(256, EPI_GELU)
+  GDRN_GEMM_CASE(256, EPI_RESID)
+  GDRN_GEMM_CASE(256, EPI_STORE)
+  GDRN_GEMM_CASE(256, EPI_GNSTATS)
+  GDRN_GEMM_CASE(128, EPI_GELU)
+  GDRN_GEMM_CASE(128, EPI_RESID)
+  GDRN_GEMM_CASE(128, EPI_STORE)
+  GDRN_GEMM_CASE(128, EPI_GNSTATS)
+  GDRN_GEMM_CASE(128, EPI_BIAS_LN)
+  GDRN_GEMM_CASE(64, EPI_GELU)
+  GDRN_GEMM_CASE(64, EPI_STORE)
+  GDRN_GEMM_CASE(64, EPI_GNSTATS)
+  GDRN_GEMM_CASE(16, EPI_STORE)
+  GDRN_GEMM_CASE(80, EPI_OUTCONV)
+#undef GDRN_GEMM_CASE
+  gdrn_set_last_error(__FILE__, __LINE__, "gemm: unsupported (block_n, epilogue) combination");
+  return GDRN_ERR_INVALID;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tensor maps (driver entry point resolved at run time: the library does not link libcuda).
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  PFN_encodeTiled fn = get_encode_fn();
+  GDRN_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed: CUresult %d (rank %d dims %llu,%llu box %u,%u)", (int)r,
+             rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    gdrn_set_last_error(__FILE__, __LINE__, msg);
+    return GDRN_ERR_CUDA;
+  }
+  return GDRN_OK;
+}

@@ -1,0 +1,72 @@
+// Internal C++ interface of the tcgen05/TMA implicit-GEMM kernel (gemm_tc.cu).
+//
+//   D[m, n] = sum_{tap} sum_{k} A_tap[m, k] * W[n, tap*b_tap_stride + k]      (bf16 x bf16 -> fp32 in TMEM)
+//
+// A rows are pixels of an NHWC activation tensor: a 128-row tile is a (bw x bh x bb) box of pixels
+// fetched by one TMA box load per (tap, 64-channel chunk); conv padding = TMA out-of-bounds zero fill.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+enum GemmEpilogue : int {
+  EPI_STORE = 0,      // out = acc (+bias)                      -> bf16 or fp32
+  EPI_GELU = 1,       // out = gelu(acc + bias)                 -> bf16
+  EPI_RESID = 2,      // out = resid + gamma * (acc + bias)     -> fp32 (in place allowed)
+  EPI_GNSTATS = 3,    // out = acc; per-(image, group) sum / sumsq accumulated in double
+  EPI_BIAS_LN = 4,    // out = LayerNorm_C(acc + bias) * ln_w + ln_b  (N == BLOCK_N)  -> fp32
+  EPI_OUTCONV = 5,    // class-gathered geometry-head output + Patch-PnP input assembly
+};
+
+struct GemmTap {
+  int c0;  // added to coordinate 0 (channel offset; e.g. x-parity * C for the stride-2 view)
+  int d1;  // added to coordinate 1 (x)
+  int d2;  // rank 4: added to y.  rank 5: absolute coordinate 2 (y parity)
+  int d3;  // rank 5: added to y (coordinate 3)
+};
+
+struct GemmPlan {
+  // ---- A operand ----
+  CUtensorMap tmap_a;
+  int a_rank;           // 2: plain [M,K] rows; 4: (C,W,H,B); 5: (2C, W/2, 2, H/2, B) stride-2 view
+  int lg_bw, lg_bh, lg_bb;  // log2 of the pixel box (bw*bh*bb == 128); rank 2 ignores them
+  int tiles_x, tiles_y;     // tiles per image along x / y (rank 4/5)
+  int num_taps;
+  GemmTap taps[9];
+  int k_chunks;         // ceil(K_per_tap / 64)
+  // ---- B operand ----
+  CUtensorMap tmap_b;   // 2D [rows][K_total] bf16, K-major
+  int b_tap_stride;     // elements between taps along K in W
+  int b_rows_per_class; // EPI_OUTCONV: row offset multiplier for the ROI class (0 otherwise)
+  // ---- problem ----
+  int m_tiles, n_tiles;
+  int M;                // valid rows (rank 2) ; rank 4/5: number of images B
+  int N;                // valid output columns
+  // ---- epilogue ----
+  int epi;
+  int out_f32;          // EPI_STORE / EPI_GNSTATS: 1 -> fp32 output, 0 -> bf16
+  void* out;            // [rows, ldo]
+  long long ldo;        // output row stride (elements)
+  int OH, OW, osy, osx, ooy, oox;  // rank 4/5: out row = (b*OH + y*osy+ooy)*OW + x*osx+oox
+  const float* bias;    // [N] or null
+  const float* gamma;   // EPI_RESID [N]
+  const float* resid;   // EPI_RESID [rows, ldo] fp32
+  double* gn_stats;     // EPI_GNSTATS [B, groups, 2]
+  int gn_groups, gn_cpg;    // groups per image, channels per group
+  const float* ln_w; const float* ln_b; float ln_eps;  // EPI_BIAS_LN
+  // EPI_OUTCONV
+  const long long* roi_classes;  // [B]
+  int rows_per_roi;              // 4096
+  const float* oc_bias;          // [num_classes, 80]
+  const float* roi_extents;      // [B,3]
+  const float* roi_coord_2d;     // [B,2,64,64] fp32 NCHW
+  void* pnp_in;                  // bf16 [B*4096, 128]
+  float* map_mask; float* map_full; float* map_x; float* map_y; float* map_z; float* map_region;  // NCHW or null
+};
+
+// block_n in {16, 64, 80, 128, 256}
+int gemm_tc_launch(const GemmPlan& plan, int block_n, cudaStream_t stream);
+
+// tensor-map builders (bf16). dims/strides innermost first; strides in BYTES for dims 1..rank-1.
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box);

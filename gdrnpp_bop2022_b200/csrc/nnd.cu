@@ -1,0 +1,110 @@
+// Chamfer / nearest-neighbour distance, forward + backward.
+// Replaces core/csrc/torch_nndistance/src/nnd_cuda_kernel.cu:8-130 (NmDistanceKernel) and :164-183
+// (NmDistanceGradKernel); launch surface src/nnd_cuda.cpp:37-84.
+//
+// Result definition (what the reference computes): for every point of set A the minimum over set B of
+//   d = fma(dz,dz, fma(dx,dx, dy*dy))      (the contraction nvcc applies to x2*x2+y2*y2+z2*z2)
+// with dx = bx - ax etc., and the LOWEST index attaining it (strict '<' scan in index order).
+// This op is FP32-ALU bound (~8 instructions per point pair, no HBM traffic once tiles are in smem):
+// 256 query points per CTA in registers, set B streamed through shared memory in tiles of 1024 points
+// read as warp-wide broadcasts.
+#include "common.cuh"
+
+namespace {
+
+constexpr int NND_THREADS = 256;
+constexpr int NND_TILE = 1024;
+
+__global__ void __launch_bounds__(NND_THREADS)
+nnd_fwd_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ dist,
+               int* __restrict__ idx, int n, int m) {
+  __shared__ float sb[NND_TILE * 3];
+  const int b = blockIdx.y;
+  const float* a = A + (size_t)b * n * 3;
+  const float* bb = B + (size_t)b * m * 3;
+  const int j = blockIdx.x * NND_THREADS + threadIdx.x;
+  float ax = 0.f, ay = 0.f, az = 0.f;
+  if (j < n) { ax = a[j * 3]; ay = a[j * 3 + 1]; az = a[j * 3 + 2]; }
+  float best = 0.f;
+  int best_i = 0;
+  for (int k0 = 0; k0 < m; k0 += NND_TILE) {
+    const int cnt = min(NND_TILE, m - k0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt * 3; i += NND_THREADS) sb[i] = bb[(size_t)k0 * 3 + i];
+    __syncthreads();
+    if (j < n) {
+      int k = 0;
+      if (k0 == 0) {  // reference: `k==0 || d<best`
+        float dx = __fsub_rn(sb[0], ax), dy = __fsub_rn(sb[1], ay), dz = __fsub_rn(sb[2], az);
+        best = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+        best_i = 0;
+        k = 1;
+      }
+#pragma unroll 4
+      for (; k < cnt; ++k) {
+        float dx = __fsub_rn(sb[k * 3], ax), dy = __fsub_rn(sb[k * 3 + 1], ay), dz = __fsub_rn(sb[k * 3 + 2], az);
+        float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+        if (d < best) { best = d; best_i = k0 + k; }
+      }
+    }
+  }
+  if (j < n) {
+    dist[(size_t)b * n + j] = best;
+    idx[(size_t)b * n + j] = best_i;
+  }
+}
+
+__global__ void nnd_bwd_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                               const float* __restrict__ grad_dist, const int* __restrict__ idx,
+                               float* __restrict__ gradA, float* __restrict__ gradB, int n, int m) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const size_t ia = ((size_t)b * n + j) * 3;
+  const int j2 = idx[(size_t)b * n + j];
+  const size_t ib = ((size_t)b * m + j2) * 3;
+  const float g = __fmul_rn(grad_dist[(size_t)b * n + j], 2.f);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = __fmul_rn(g, __fsub_rn(A[ia + c], B[ib + c]));
+    atomicAdd(&gradA[ia + c], v);
+    atomicAdd(&gradB[ib + c], -v);
+  }
+}
+
+}  // namespace
+
+extern "C" int nnd_forward_cuda(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1,
+                                int* idx2, int b, int n, int m, void* stream) {
+  if (b <= 0 || n <= 0 || m <= 0) {
+    gdrn_set_last_error(__FILE__, __LINE__, "nnd: b, n, m must be positive");
+    return 0;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  nnd_fwd_kernel<<<dim3((n + NND_THREADS - 1) / NND_THREADS, b), NND_THREADS, 0, st>>>(xyz1, xyz2, dist1, idx1, n, m);
+  nnd_fwd_kernel<<<dim3((m + NND_THREADS - 1) / NND_THREADS, b), NND_THREADS, 0, st>>>(xyz2, xyz1, dist2, idx2, m, n);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    gdrn_set_last_error(__FILE__, __LINE__, cudaGetErrorString(e));
+    return 0;
+  }
+  return 1;
+}
+
+extern "C" int nnd_backward_cuda(const float* xyz1, const float* xyz2, float* gradxyz1, float* gradxyz2,
+                                 const float* graddist1, const float* graddist2, const int* idx1, const int* idx2,
+                                 int b, int n, int m, void* stream) {
+  if (b <= 0 || n <= 0 || m <= 0) {
+    gdrn_set_last_error(__FILE__, __LINE__, "nnd: b, n, m must be positive");
+    return 0;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  nnd_bwd_kernel<<<dim3((n + 255) / 256, b), 256, 0, st>>>(xyz1, xyz2, graddist1, idx1, gradxyz1, gradxyz2, n, m);
+  nnd_bwd_kernel<<<dim3((m + 255) / 256, b), 256, 0, st>>>(xyz2, xyz1, graddist2, idx2, gradxyz2, gradxyz1, m, n);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    gdrn_set_last_error(__FILE__, __LINE__, cudaGetErrorString(e));
+    return 0;
+  }
+  return 1;
+}

@@ -1,0 +1,176 @@
+/* libgdrn_b200.so -- C ABI of the B200-native GDRNPP per-ROI pose-inference hot path.
+ *
+ * Plain pointers and sizes only (no torch types).  Unless stated otherwise every pointer is a DEVICE
+ * pointer, every call is asynchronous on the given CUDA stream (passed as void* = cudaStream_t), never
+ * allocates, never synchronises, and returns 0 (GDRN_OK) or a negative error code; the message of the
+ * last error is available from gdrn_last_error().  One process per GPU; the caller owns all buffers.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference tree
+ * shanice-l/gdrnpp_bop2022 @ b80383bd).  The reference-side bindings are shown in INTEGRATION.md.
+ */
+#ifndef GDRN_B200_H_
+#define GDRN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GDRN_OK 0
+#define GDRN_ERR_INVALID (-1) /* bad argument / unsupported configuration */
+#define GDRN_ERR_CUDA (-2)    /* CUDA runtime or driver error */
+#define GDRN_ERR_STATE (-3)   /* model not fully loaded, workspace too small, ... */
+
+const char* gdrn_last_error(void);
+int gdrn_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense path: GDRN_DoubleMask.forward (eval, do_loss=False)
+ *   replaces core/gdrn_modeling/models/GDRN_double_mask.py:66-214 and everything it calls:
+ *   timm convnext features (core/utils/timm_utils.py:9-35), TopDownDoubleMaskXyzRegionHead.forward
+ *   (models/heads/top_down_doublemask_xyz_region_head.py:177-211), ConvPnPNet.forward
+ *   (models/heads/conv_pnp_net.py:120-183), rot6d_to_mat_batch (core/utils/rot_reps.py:34-55),
+ *   pose_from_predictions_test (models/pose_from_pred_centroid_z.py:56-154) and
+ *   allocentric_to_egocentric (core/utils/utils.py:31-88).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct GdrnModel GdrnModel;
+
+/* arch: "convnext_base" | "convnext_small" | "convnext_tiny"; num_classes: class-aware head size (21). */
+int gdrn_model_create(GdrnModel** out, const char* arch, int num_classes, int max_batch);
+void gdrn_model_destroy(GdrnModel* m);
+
+/* Feed one fp32 tensor of a reference checkpoint (state_dict key names, e.g.
+ * "backbone.stages_2.blocks.5.mlp.fc1.weight", "geo_head_net.features.0.weight", "pnp_net.fc_r.bias";
+ * loader: core/utils/my_checkpoint.py:35-83).  The tensor is re-packed into kernel-native layouts on
+ * `stream`; the source buffer may be freed after the stream reaches this point. Unknown keys return
+ * GDRN_ERR_INVALID. */
+int gdrn_model_load_tensor(GdrnModel* m, const char* key, const float* data, int64_t numel, void* stream);
+/* number of tensors still missing (0 = ready) */
+int gdrn_model_missing(const GdrnModel* m);
+
+size_t gdrn_model_workspace_bytes(const GdrnModel* m, int batch);
+
+typedef struct GdrnMaps { /* optional class-gathered maps (GDRN_double_mask.py:203-214), fp32 NCHW, or all NULL */
+  float* mask;      /* [B,1,64,64] */
+  float* full_mask; /* [B,1,64,64] */
+  float* coor_x;    /* [B,1,64,64] */
+  float* coor_y;    /* [B,1,64,64] */
+  float* coor_z;    /* [B,1,64,64] */
+  float* region;    /* [B,65,64,64] */
+} GdrnMaps;
+
+/* roi_img [B,3,256,256] fp32 NCHW in [0,1]; roi_classes [B] int64; roi_coord_2d [B,2,64,64]; roi_cams [B,3,3];
+ * roi_centers [B,2]; roi_whs [B,2]; resize_ratios [B]; roi_extents [B,3]  ->  out_rot [B,3,3] (egocentric,
+ * row-major), out_trans [B,3].  out_raw (optional, [B,9]) receives the Patch-PnP head output (rot6d, t_). */
+int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int64_t* roi_classes, const float* roi_coord_2d,
+                       const float* roi_cams, const float* roi_centers, const float* roi_whs,
+                       const float* resize_ratios, const float* roi_extents, int batch, float* out_rot,
+                       float* out_trans, float* out_raw, const GdrnMaps* maps, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* debugging / parity hooks: copy an internal activation (after the last forward on the same workspace)
+ * as fp32 into dst.  name: "conv_feat" ([B,8,8,C3] NHWC) | "stage0".."stage3" | "head16"|"head32"|"head64"
+ * ([B,h,w,256] NHWC, post GN+GELU) | "pnp_in" ([B,64,64,128]) . Returns element count or <0. */
+int64_t gdrn_model_debug_read(GdrnModel* m, const char* name, int batch, float* dst, void* workspace, void* stream);
+
+/* Plain GEMM through the same tcgen05 kernel, exported for tests and roofline measurement:
+ * out[M,N] = epi(A[M,K] @ W[N,K]^T + bias); A, W bf16 row-major (K contiguous, lda/ldw = K).
+ * epi: 0 = store (out bf16 or fp32 by out_f32), 1 = GELU -> bf16, 2 = resid + gamma*(.) -> fp32. */
+int gdrn_gemm_bf16(const void* A, const void* W, const float* bias, const float* gamma, const float* resid,
+                   void* out, int M, int N, int K, int epi, int out_f32, int block_n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Farthest point sampling -- replaces core/csrc/fps/src/farthest_point_sampling.cpp:166-204
+ * (cffi surface core/csrc/fps/src/ext.h:1-14, Python wrapper core/csrc/fps/fps_utils.py:6-21).
+ * The two host-pointer symbols keep the reference's exact signature (blocking; they stage through the
+ * GPU).  `farthest_point_sampling` (random start in the reference: srand(time(0)), :93-94) starts at
+ * index `gdrn_fps_set_seed`-derived rand()%pn here; `_init_center` is deterministic and bit-exact.
+ * ------------------------------------------------------------------------------------------- */
+void farthest_point_sampling(float* pts, int* idxs, int pn, int sn);
+void farthest_point_sampling_init_center(float* pts, int* idxs, int pn, int sn);
+void gdrn_fps_set_seed(unsigned seed);
+/* batched device version: pts [batch,pn,3] f32, idxs [batch,sn] i32.  start_idx: NULL -> bbox-centre
+ * initialisation (init_center), else [batch] i32 explicit first index. */
+int gdrn_fps_cuda(const float* pts, int* idxs, int pn, int sn, int batch, const int* start_idx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * PVNet RANSAC voting -- replaces core/csrc/ransac_voting/src/ransac_voting.cpp:30-109 (pybind module
+ * `ransac_voting`: generate_hypothesis, voting_for_hypothesis, *_vanishing_point) and the kernels
+ * src/ransac_voting_kernel.cu:11-49,88-126,170-229,268-310.
+ *   direct [tn,vn,2] f32, coords [tn,2] f32, idxs [hn,vn,2] i32, hypo [hn,vn,2|3] f32 (pre-zeroed by the
+ *   caller like at::zeros), inliers [hn,vn,tn] u8 (in/out, pre-zeroed by the caller).
+ * ------------------------------------------------------------------------------------------- */
+int rv_generate_hypothesis(const float* direct, const float* coords, const int* idxs, float* hypo, int tn, int vn,
+                           int hn, void* stream);
+int rv_voting_for_hypothesis(const float* direct, const float* coords, const float* hypo, unsigned char* inliers,
+                             int tn, int vn, int hn, float inlier_thresh, void* stream);
+int rv_generate_hypothesis_vanishing_point(const float* direct, const float* coords, const int* idxs, float* hypo,
+                                           int tn, int vn, int hn, void* stream);
+int rv_voting_for_hypothesis_vanishing_point(const float* direct, const float* coords, const float* hypo,
+                                             unsigned char* inliers, int tn, int vn, int hn, float inlier_thresh,
+                                             void* stream);
+/* fused round: votes without materialising the [hn,vn,tn] mask; counts [hn,vn] i32 (overwritten). */
+int rv_vote_count(const float* direct, const float* coords, const float* hypo, int* counts, int tn, int vn, int hn,
+                  float inlier_thresh, int vanishing_point, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Chamfer / NN distance -- replaces core/csrc/torch_nndistance/src/nnd_cuda.cpp:37-84
+ * (module torch_nndistance_aten: nnd_forward_cuda / nnd_backward_cuda; kernels nnd_cuda_kernel.cu:8-183).
+ *   xyz1 [b,n,3], xyz2 [b,m,3] f32 -> dist1 [b,n], dist2 [b,m] f32, idx1 [b,n], idx2 [b,m] i32.
+ *   backward: grad buffers are ACCUMULATED into (caller zeroes them, as torch_nndistance.py:52-53 does).
+ * Returns 1 on success / 0 on failure like the reference launchers.
+ * ------------------------------------------------------------------------------------------- */
+int nnd_forward_cuda(const float* xyz1, const float* xyz2, float* dist1, float* dist2, int* idx1, int* idx2, int b,
+                     int n, int m, void* stream);
+int nnd_backward_cuda(const float* xyz1, const float* xyz2, float* gradxyz1, float* gradxyz2, const float* graddist1,
+                      const float* graddist2, const int* idx1, const int* idx2, int b, int n, int m, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * DeepIM depth-reprojection flow -- replaces core/csrc/flow/src/flow_cuda.cpp:30-42 (module flow_cuda,
+ * kernel flow_cuda_kernel.cu:26-65). depth_src/tgt [B,1,H,W], KT [B,3,4], Kinv [B,3,3] ->
+ * flow [B,2,H,W] (ch0 = dh, ch1 = dw), valid [B,1,H,W]; fp32.
+ * ------------------------------------------------------------------------------------------- */
+int flow_forward_cuda(const float* depth_src, const float* depth_tgt, const float* KT, const float* Kinv, float* flow,
+                      float* valid, int batch, int height, int width, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Uncertainty PnP -- replaces core/csrc/uncertainty_pnp/src/uncertainty_pnp.cpp:61-92 (cffi surface
+ * src/ext.h; Ceres AutoDiff + DENSE_SCHUR LM).  Host f64 pointers, blocking, same signature.
+ * upnp_batched: device f64, `n_problems` independent problems of `pn` points each.
+ * ------------------------------------------------------------------------------------------- */
+void uncertainty_pnp(double* pts2d, double* pts3d, double* wgt2d, double* K, double* init_rt, double* result_rt,
+                     int pn);
+int upnp_batched(const double* pts2d, const double* pts3d, const double* wgt2d, const double* K,
+                 const double* init_rt, double* result_rt, int pn, int n_problems, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Depth rasteriser -- replaces the GL renderers used for depth: lib/render_vispy/renderer.py:126-182,
+ * 363-407 (Renderer.set_cam/draw_model/finish -> depth) and lib/egl_renderer/egl_renderer_v3.py:838-1228
+ * (EGLRenderer.render(..., pc_cam_tensor=) -> pc_cam[...,2]); C++ side lib/egl_renderer/cpp/
+ * egl_renderer.cpp:262-310.
+ *   verts [V,3] f32 (model space, metres), faces [F,3] i32; poses [n,3,4] f32 (R|t, OpenCV camera),
+ *   Ks [n,3,3] f32 -> depth [n,H,W] f32 (0 = background), optional xyz_cam [n,H,W,3].
+ *   quantize_bits: 0 = float depth of the interpolated camera-space z (EGL path), 24/16 = emulate the
+ *   fixed-point z-buffer decode of the vispy path (renderer.py:176-182) with znear/zfar.
+ * ------------------------------------------------------------------------------------------- */
+int rast_render_depth(const float* verts, const int* faces, int V, int F, const float* poses, const float* Ks,
+                      int n, int H, int W, float znear, float zfar, int quantize_bits, float* depth,
+                      float* xyz_cam, unsigned long long* zbuf_scratch, void* stream);
+size_t rast_scratch_bytes(int n, int H, int W);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fast depth refinement -- replaces GDRN_Evaluator.process_depth_refine
+ * (core/gdrn_modeling/engine/gdrn_evaluator.py:521-561) == GdrnPredictor.process_depth_refine
+ * (core/gdrn_modeling/demo/predictor_gdrn.py:239-286), one iteration after a render:
+ *   xyz [n,3,64,64], mask [n,64,64], depth_sensor [n,64,64], ren_depth [n,64,64], K_crop [n,3,3],
+ *   trans [n,3] in/out; thresh = DEPTH_REFINE_THRESHOLD (0.8).
+ * ------------------------------------------------------------------------------------------- */
+int gdrn_depth_refine_step(const float* xyz, const float* mask, const float* depth_sensor, const float* ren_depth,
+                           const float* K_crop, float* trans, int n, int hw, float thresh, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GDRN_B200_H_ */
