@@ -30,6 +30,9 @@ class GdrnMaps(ctypes.Structure):
 _SIGNATURES = {
     "gdrn_last_error": (c_char_p, []),
     "gdrn_version": (c_int, []),
+    "gdrn_launch_count": (ctypes.c_longlong, []),
+    "gdrn_model_set_profiling": (c_int, [c_void_p, c_int]),
+    "gdrn_model_get_profile": (c_int, [c_void_p, c_void_p, c_void_p]),
     "gdrn_model_create": (c_int, [POINTER(c_void_p), c_char_p, c_int, c_int]),
     "gdrn_model_destroy": (None, [c_void_p]),
     "gdrn_model_load_tensor": (c_int, [c_void_p, c_char_p, c_void_p, c_int64, c_void_p]),

@@ -1,5 +1,6 @@
 // Error channel, version, and the exported plain-GEMM entry (tests + roofline measurement).
 #include <string.h>
+#include <atomic>
 
 #include "common.cuh"
 #include "gemm_tc.h"
@@ -10,6 +11,10 @@ void gdrn_set_last_error(const char* file, int line, const char* msg) {
   const char* base = strrchr(file, '/');
   snprintf(g_last_error, sizeof(g_last_error), "%s:%d: %s", base ? base + 1 : file, line, msg);
 }
+
+static std::atomic<long long> g_launches{0};
+void gdrn_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" long long gdrn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" const char* gdrn_last_error(void) { return g_last_error; }
 extern "C" int gdrn_version(void) { return 100; }

@@ -12,6 +12,7 @@
   do {                                                                                          \
     cudaError_t _e = (expr);                                                                    \
     if (_e != cudaSuccess) {                                                                    \
+      (void)cudaGetLastError(); /* clear the non-sticky error state */                          \
       gdrn_set_last_error(__FILE__, __LINE__, cudaGetErrorString(_e));                          \
       return GDRN_ERR_CUDA;                                                                     \
     }                                                                                           \
@@ -26,6 +27,7 @@
   } while (0)
 
 void gdrn_set_last_error(const char* file, int line, const char* msg);
+void gdrn_count_launch(int n);  // bumps the counter behind gdrn_launch_count()
 
 static inline int gdrn_num_sms() {
   static int n = 0;

@@ -414,6 +414,7 @@ int launch_pack(const float* src, void* dst, int dst_is_bf16, const PackDesc& d,
   if (blocks > 4096) blocks = 4096;
   pack_kernel<<<(int)blocks, 256, 0, st>>>(src, dst, dst_is_bf16, d);
   GDRN_CHECK_CUDA(cudaGetLastError());
+  gdrn_count_launch(1);
   return GDRN_OK;
 }
 
@@ -422,6 +423,7 @@ int launch_stem_patchify(const float* img, __nv_bfloat16* out, int B, int H, int
   long long total = (long long)B * (H / 4) * (W / 4);
   stem_patchify_kernel<<<(int)((total + 127) / 128), 128, 0, st>>>(img, out, B, H, W);
   GDRN_CHECK_CUDA(cudaGetLastError());
+  gdrn_count_launch(1);
   return GDRN_OK;
 }
 
@@ -438,6 +440,7 @@ int launch_dwconv_ln(const float* x, const float* w49c, const float* bias, const
     dwconv_ln_kernel<8><<<(int)((strips + S - 1) / S), 256, 0, st>>>(x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps);
   }
   GDRN_CHECK_CUDA(cudaGetLastError());
+  gdrn_count_launch(1);
   return GDRN_OK;
 }
 
@@ -447,6 +450,7 @@ int launch_ln_patchify2(const float* x, const float* ln_w, const float* ln_b, __
   long long total = (long long)B * H * W;
   ln_patchify2_kernel<<<(int)((total + 7) / 8), 256, 0, st>>>(x, ln_w, ln_b, out, B, H, W, C, eps);
   GDRN_CHECK_CUDA(cudaGetLastError());
+  gdrn_count_launch(1);
   return GDRN_OK;
 }
 
@@ -456,6 +460,7 @@ int launch_cast_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStre
   if (blocks > 8192) blocks = 8192;
   cast_bf16_kernel<<<(int)blocks, 256, 0, st>>>(src, dst, n);
   GDRN_CHECK_CUDA(cudaGetLastError());
+  gdrn_count_launch(1);
   return GDRN_OK;
 }
 
@@ -464,6 +469,7 @@ int launch_bf16_to_f32(const __nv_bfloat16* src, float* dst, long long n, cudaSt
   if (blocks > 8192) blocks = 8192;
   bf16_to_f32_kernel<<<(int)blocks, 256, 0, st>>>(src, dst, n);
   GDRN_CHECK_CUDA(cudaGetLastError());
+  gdrn_count_launch(1);
   return GDRN_OK;
 }
 
@@ -474,6 +480,7 @@ int launch_gn_gelu(const void* raw, int raw_is_f32, const double* stats, const f
   gn_gelu_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(raw, raw_is_f32, stats, gn_w, gn_b, out, B, h, w, C, groups,
                                                             eps, up);
   GDRN_CHECK_CUDA(cudaGetLastError());
+  gdrn_count_launch(1);
   return GDRN_OK;
 }
 
@@ -481,5 +488,6 @@ int launch_pose_lift(const float* raw, int ld, const float* cams, const float* c
                      const float* ratios, float* out_rot, float* out_trans, float* out_raw9, int B, cudaStream_t st) {
   pose_lift_kernel<<<(B + 63) / 64, 64, 0, st>>>(raw, ld, cams, centers, whs, ratios, out_rot, out_trans, out_raw9, B);
   GDRN_CHECK_CUDA(cudaGetLastError());
+  gdrn_count_launch(1);
   return GDRN_OK;
 }

@@ -63,5 +63,6 @@ extern "C" int flow_forward_cuda(const float* depth_src, const float* depth_tgt,
   flow_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(depth_src, depth_tgt, KT, Kinv, flow, valid, batch, height,
                                                            width);
   GDRN_CHECK_CUDA(cudaGetLastError());
+  gdrn_count_launch(1);
   return GDRN_OK;
 }

@@ -3,8 +3,8 @@
 // NO fused multiply-add, float accumulation order (x*x + y*y) + z*z).
 //
 // One CTA per cloud.  The cloud (x,y,z SoA) and the running min-distance live in shared memory (up to
-// 14 208 points) or, for larger clouds, min-distance in shared memory and the points streamed from
-// L2 (up to 57 000 points).  Every iteration: each thread relaxes its points against the last pick
+// 14 000 points) or, for larger clouds, min-distance in shared memory and the points streamed from
+// L2 (up to 56 000 points).  Every iteration: each thread relaxes its points against the last pick
 // and keeps a local (value, index) arg-max; one shuffle tree + one __syncthreads per pick.
 // Algorithmic traffic: 12*pn + 4*sn bytes per cloud; the op is latency-bound on sn block reductions.
 #include <float.h>
@@ -15,8 +15,8 @@
 namespace {
 
 constexpr int FPS_THREADS = 1024;
-constexpr int FPS_SMEM_ALL = 14208;  // points with xyz+d resident: 16 B each  (227 KB)
-constexpr int FPS_SMEM_D = 57000;    // points with only d resident: 4 B each
+constexpr int FPS_SMEM_ALL = 14000;  // points with xyz+d resident: 16 B each  (224 000 B + 1.3 KB static)
+constexpr int FPS_SMEM_D = 56000;    // points with only d resident: 4 B each
 
 struct Cand {
   float v;
@@ -147,11 +147,11 @@ fps_kernel(const float* __restrict__ pts_all, int* __restrict__ idx_all, int pn,
 
 int fps_launch(const float* pts, int* idxs, int pn, int sn, int batch, const int* start_idx, cudaStream_t st) {
   GDRN_REQUIRE(pn > 0 && sn > 0 && batch > 0, "fps: pn, sn, batch must be positive");
-  GDRN_REQUIRE(pn <= FPS_SMEM_D, "fps: pn > 57000 points per cloud is not supported by the single-CTA kernel");
+  GDRN_REQUIRE(pn <= FPS_SMEM_D, "fps: pn > 56000 points per cloud is not supported by the single-CTA kernel");
   static bool configured = false;
   if (!configured) {
-    GDRN_CHECK_CUDA(cudaFuncSetAttribute(fps_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    GDRN_CHECK_CUDA(cudaFuncSetAttribute(fps_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GDRN_CHECK_CUDA(cudaFuncSetAttribute(fps_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224000));
+    GDRN_CHECK_CUDA(cudaFuncSetAttribute(fps_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224000));
     configured = true;
   }
   if (pn <= FPS_SMEM_ALL) {
@@ -160,6 +160,7 @@ int fps_launch(const float* pts, int* idxs, int pn, int sn, int batch, const int
     fps_kernel<false><<<batch, FPS_THREADS, (size_t)pn * 4, st>>>(pts, idxs, pn, sn, start_idx);
   }
   GDRN_CHECK_CUDA(cudaGetLastError());
+  gdrn_count_launch(1);
   return GDRN_OK;
 }
 

@@ -490,6 +490,7 @@ int launch_inst(const GemmPlan& plan, cudaStream_t stream) {
   int grid = total < gdrn_num_sms() ? total : gdrn_num_sms();
   kfn<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(plan);
   GDRN_CHECK_CUDA(cudaGetLastError());
+  gdrn_count_launch(1);
   return GDRN_OK;
 }
 

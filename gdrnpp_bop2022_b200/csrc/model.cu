@@ -84,6 +84,11 @@ struct GdrnModel {
   std::map<std::string, std::vector<LoadOp>> loaders;
   std::map<std::string, bool> loaded;
   int missing = 0;
+  // ---- optional per-category timing (bench.py roofline) ----
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_events;
+  std::vector<int> prof_cat;
+  int prof_used = 0;
 };
 
 namespace {
@@ -357,6 +362,22 @@ int plan_a5d_s2(GemmPlan& p, const void* act, int B, int H, int W, int C) {
 }
 
 #define RC(expr) do { int _rc = (expr); if (_rc != GDRN_OK) return _rc; } while (0)
+// profiled launch: category 0 = tcgen05 GEMM, 1 = depthwise conv + LN, 2 = other CUDA-core kernels
+#define RCP(cat, expr) do { prof_begin(m, (cat), st); int _rc = (expr); prof_end(m, st); if (_rc != GDRN_OK) return _rc; } while (0)
+
+void prof_begin(GdrnModel* m, int cat, cudaStream_t st) {
+  if (!m->prof_on) return;
+  if (m->prof_used + 2 > (int)m->prof_events.size()) {
+    for (int i = 0; i < 64; ++i) { cudaEvent_t e; cudaEventCreate(&e); m->prof_events.push_back(e); }
+  }
+  m->prof_cat.push_back(cat);
+  cudaEventRecord(m->prof_events[m->prof_used], st);
+}
+void prof_end(GdrnModel* m, cudaStream_t st) {
+  if (!m->prof_on) return;
+  cudaEventRecord(m->prof_events[m->prof_used + 1], st);
+  m->prof_used += 2;
+}
 
 }  // namespace
 
@@ -382,6 +403,7 @@ extern "C" int gdrn_model_create(GdrnModel** out, const char* arch, int num_clas
 extern "C" void gdrn_model_destroy(GdrnModel* m) {
   if (!m) return;
   for (void* p : m->allocs) cudaFree(p);
+  for (cudaEvent_t e : m->prof_events) cudaEventDestroy(e);
   delete m;
 }
 
@@ -442,6 +464,8 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
   const Arch& a = m->arch;
   void* wbase = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~(uintptr_t)1023);
   Workspace w = carve(m, B, wbase);
+  m->prof_used = 0;
+  m->prof_cat.clear();
   GDRN_CHECK_CUDA(cudaMemsetAsync(w.gn_stats, 0, (size_t)10 * B * 32 * 2 * 8, st));
 
   GemmPlan p;
@@ -449,7 +473,7 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
 
   // ---------------- stem: 4x4/s4 conv as GEMM (K=48 padded to 64) + bias + LayerNorm2d in the epilogue ----------------
   const long long M0 = (long long)B * 64 * 64;
-  RC(launch_stem_patchify(roi_img, w.A, B, 256, 256, st));
+  RCP(2, launch_stem_patchify(roi_img, w.A, B, 256, 256, st));
   {
     const int C0 = a.dims[0];
     reset();
@@ -458,7 +482,7 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
       RC(plan_b(p, m->stem_w, C0, 64, 128, C0));
       p.epi = EPI_BIAS_LN; p.out = w.X; p.ldo = C0; p.bias = m->stem_b;
       p.ln_w = m->stem_ln_w; p.ln_b = m->stem_ln_b; p.ln_eps = 1e-6f;
-      RC(gemm_tc_launch(p, 128, st));
+      RCP(0, gemm_tc_launch(p, 128, st));
     } else {
       gdrn_set_last_error(__FILE__, __LINE__, "forward: only convnext_base (C0=128) has a fused stem epilogue so far");
       return GDRN_ERR_INVALID;
@@ -470,7 +494,7 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
     const int C = a.dims[s];
     if (s > 0) {
       const int Ci = a.dims[s - 1];
-      RC(launch_ln_patchify2(w.X, m->down[s].ln_w, m->down[s].ln_b, w.A, B, res, res, Ci, 1e-6f, st));
+      RCP(2, launch_ln_patchify2(w.X, m->down[s].ln_w, m->down[s].ln_b, w.A, B, res, res, Ci, 1e-6f, st));
       res /= 2;
       const long long M = (long long)B * res * res;
       reset();
@@ -478,27 +502,27 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
       const int bn = 256;
       RC(plan_b(p, m->down[s].w, C, 4 * Ci, bn, C));
       p.epi = EPI_STORE; p.out_f32 = 1; p.out = w.X; p.ldo = C; p.bias = m->down[s].b;
-      RC(gemm_tc_launch(p, bn, st));
+      RCP(0, gemm_tc_launch(p, bn, st));
     }
     const long long M = (long long)B * res * res;
     for (int i = 0; i < a.depths[s]; ++i) {
       const BlockW& bw = m->blocks[s][i];
-      RC(launch_dwconv_ln(w.X, bw.dw_w, bw.dw_b, bw.ln_w, bw.ln_b, w.A, B, res, res, C, 1e-6f, st));
+      RCP(1, launch_dwconv_ln(w.X, bw.dw_w, bw.dw_b, bw.ln_w, bw.ln_b, w.A, B, res, res, C, 1e-6f, st));
       reset();
       RC(plan_a2d(p, w.A, M, C));
       RC(plan_b(p, bw.fc1_w, 4 * C, C, 256, 4 * C));
       p.epi = EPI_GELU; p.out = w.Hb; p.ldo = 4 * C; p.bias = bw.fc1_b;
-      RC(gemm_tc_launch(p, 256, st));
+      RCP(0, gemm_tc_launch(p, 256, st));
       reset();
       RC(plan_a2d(p, w.Hb, M, 4 * C));
       const int bn2 = C >= 256 ? 256 : 128;
       RC(plan_b(p, bw.fc2_w, C, 4 * C, bn2, C));
       p.epi = EPI_RESID; p.out_f32 = 1; p.out = w.X; p.resid = w.X; p.ldo = C; p.bias = bw.fc2_b; p.gamma = bw.gamma;
-      RC(gemm_tc_launch(p, bn2, st));
+      RCP(0, gemm_tc_launch(p, bn2, st));
     }
   }
   const int C3 = a.dims[3];
-  RC(launch_cast_bf16(w.X, w.feat, (long long)B * 64 * C3, st));
+  RCP(2, launch_cast_bf16(w.X, w.feat, (long long)B * 64 * C3, st));
 
   // ---------------- geometry head ----------------
   double* stats = w.gn_stats;
@@ -521,9 +545,9 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
       p.epi = EPI_GNSTATS; p.out_f32 = 0; p.out = w.R; p.ldo = 256;
       p.OH = 16; p.OW = 16; p.osy = 2; p.osx = 2; p.ooy = py; p.oox = px;
       p.gn_stats = stat_slot(0); p.gn_groups = 32; p.gn_cpg = 8;
-      RC(gemm_tc_launch(p, 256, st));
+      RCP(0, gemm_tc_launch(p, 256, st));
     }
-  RC(launch_gn_gelu(w.R, 0, stat_slot(0), m->gn_w[0], m->gn_b[0], w.P, B, 16, 16, 256, 32, 1e-5f, 1, st));
+  RCP(2, launch_gn_gelu(w.R, 0, stat_slot(0), m->gn_w[0], m->gn_b[0], w.P, B, 16, 16, 256, 32, 1e-5f, 1, st));
   __nv_bfloat16* cur = w.P;
   __nv_bfloat16* nxt = w.Q;
   int hres = 16;
@@ -539,9 +563,9 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
       p.epi = EPI_GNSTATS; p.out_f32 = 0; p.out = w.R; p.ldo = 256;
       p.OH = hres; p.OW = hres; p.osy = 1; p.osx = 1; p.ooy = 0; p.oox = 0;
       p.gn_stats = stat_slot(li + 1); p.gn_groups = 32; p.gn_cpg = 8;
-      RC(gemm_tc_launch(p, 256, st));
+      RCP(0, gemm_tc_launch(p, 256, st));
       const int up = (j == 1 && blk < 2) ? 2 : 1;
-      RC(launch_gn_gelu(w.R, 0, stat_slot(li + 1), m->gn_w[li + 1], m->gn_b[li + 1], nxt, B, hres, hres, 256, 32, 1e-5f,
+      RCP(2, launch_gn_gelu(w.R, 0, stat_slot(li + 1), m->gn_w[li + 1], m->gn_b[li + 1], nxt, B, hres, hres, 256, 32, 1e-5f,
                         up, st));
       std::swap(cur, nxt);
       hres *= up;
@@ -566,7 +590,7 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
     p.map_mask = maps->mask; p.map_full = maps->full_mask; p.map_x = maps->coor_x; p.map_y = maps->coor_y;
     p.map_z = maps->coor_z; p.map_region = maps->region;
   }
-  RC(gemm_tc_launch(p, 80, st));
+  RCP(0, gemm_tc_launch(p, 80, st));
 
   // ---------------- Patch-PnP ----------------
   {
@@ -589,8 +613,8 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
       p.epi = EPI_GNSTATS; p.out_f32 = 0; p.out = w.pR; p.ldo = 128;
       p.OH = ores; p.OW = ores; p.osy = 1; p.osx = 1;
       p.gn_stats = stat_slot(7 + i); p.gn_groups = 32; p.gn_cpg = 4;
-      RC(gemm_tc_launch(p, 128, st));
-      RC(launch_gn_gelu(w.pR, 0, stat_slot(7 + i), m->pgn_w[i], m->pgn_b[i], w.pP, B, ores, ores, 128, 32, 1e-5f, 1, st));
+      RCP(0, gemm_tc_launch(p, 128, st));
+      RCP(2, launch_gn_gelu(w.pR, 0, stat_slot(7 + i), m->pgn_w[i], m->pgn_b[i], w.pP, B, ores, ores, 128, 32, 1e-5f, 1, st));
       // ping-pong between pP and a second buffer is unnecessary: the conv reads pP (or pnp_in) and writes pR
       in = w.pP;
       ires = ores;
@@ -600,19 +624,41 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
     RC(plan_a2d(p, w.pP, B, 8192));
     RC(plan_b(p, m->pfc1_w, 1024, 8192, 64, 1024));
     p.epi = EPI_GELU; p.out = w.f1; p.ldo = 1024; p.bias = m->pfc1_b;
-    RC(gemm_tc_launch(p, 64, st));
+    RCP(0, gemm_tc_launch(p, 64, st));
     reset();
     RC(plan_a2d(p, w.f1, B, 1024));
     RC(plan_b(p, m->pfc2_w, 256, 1024, 64, 256));
     p.epi = EPI_GELU; p.out = w.f2; p.ldo = 256; p.bias = m->pfc2_b;
-    RC(gemm_tc_launch(p, 64, st));
+    RCP(0, gemm_tc_launch(p, 64, st));
     reset();
     RC(plan_a2d(p, w.f2, B, 256));
     RC(plan_b(p, m->pfcrt_w, 16, 256, 16, 16));
     p.epi = EPI_STORE; p.out_f32 = 1; p.out = w.fout; p.ldo = 16; p.bias = m->pfcrt_b;
-    RC(gemm_tc_launch(p, 16, st));
+    RCP(0, gemm_tc_launch(p, 16, st));
   }
-  RC(launch_pose_lift(w.fout, 16, roi_cams, roi_centers, roi_whs, resize_ratios, out_rot, out_trans, out_raw, B, st));
+  RCP(2, launch_pose_lift(w.fout, 16, roi_cams, roi_centers, roi_whs, resize_ratios, out_rot, out_trans, out_raw, B, st));
+  return GDRN_OK;
+}
+
+extern "C" int gdrn_model_set_profiling(GdrnModel* m, int enable) {
+  GDRN_REQUIRE(m != nullptr, "set_profiling: null model");
+  m->prof_on = enable != 0;
+  return GDRN_OK;
+}
+
+// Sums the CUDA-event durations of the last forward per category (blocks until that forward finished).
+extern "C" int gdrn_model_get_profile(GdrnModel* m, float* ms_out /*[3]*/, int* launches_out /*[3]*/) {
+  GDRN_REQUIRE(m && ms_out && launches_out, "get_profile: null argument");
+  for (int c = 0; c < 3; ++c) { ms_out[c] = 0.f; launches_out[c] = 0; }
+  if (m->prof_used == 0) return GDRN_OK;
+  GDRN_CHECK_CUDA(cudaEventSynchronize(m->prof_events[m->prof_used - 1]));
+  for (int i = 0; i < m->prof_used / 2; ++i) {
+    float ms = 0.f;
+    GDRN_CHECK_CUDA(cudaEventElapsedTime(&ms, m->prof_events[2 * i], m->prof_events[2 * i + 1]));
+    const int c = m->prof_cat[i];
+    ms_out[c] += ms;
+    launches_out[c] += 1;
+  }
   return GDRN_OK;
 }
 

@@ -88,6 +88,7 @@ extern "C" int nnd_forward_cuda(const float* xyz1, const float* xyz2, float* dis
     gdrn_set_last_error(__FILE__, __LINE__, cudaGetErrorString(e));
     return 0;
   }
+  gdrn_count_launch(2);
   return 1;
 }
 
@@ -106,5 +107,6 @@ extern "C" int nnd_backward_cuda(const float* xyz1, const float* xyz2, float* gr
     gdrn_set_last_error(__FILE__, __LINE__, cudaGetErrorString(e));
     return 0;
   }
+  gdrn_count_launch(2);
   return 1;
 }

@@ -156,6 +156,7 @@ int vote_launch(const float* direct, const float* coords, const float* hypo, uns
   if (COUNT) GDRN_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)hn * vn * 4, st));
   k<<<grid, RV_TILE_T, smem, st>>>(direct, coords, hypo, inliers, counts, tn, vn, hn, thresh);
   GDRN_CHECK_CUDA(cudaGetLastError());
+  gdrn_count_launch(1);
   return GDRN_OK;
 }
 
@@ -167,6 +168,7 @@ extern "C" int rv_generate_hypothesis(const float* direct, const float* coords, 
   int n = hn * vn;
   gen_hyp_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(direct, coords, idxs, hypo, tn, vn, hn);
   GDRN_CHECK_CUDA(cudaGetLastError());
+  gdrn_count_launch(1);
   return GDRN_OK;
 }
 extern "C" int rv_generate_hypothesis_vanishing_point(const float* direct, const float* coords, const int* idxs,
@@ -175,6 +177,7 @@ extern "C" int rv_generate_hypothesis_vanishing_point(const float* direct, const
   int n = hn * vn;
   gen_hyp_vp_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(direct, coords, idxs, hypo, tn, vn, hn);
   GDRN_CHECK_CUDA(cudaGetLastError());
+  gdrn_count_launch(1);
   return GDRN_OK;
 }
 extern "C" int rv_voting_for_hypothesis(const float* direct, const float* coords, const float* hypo,

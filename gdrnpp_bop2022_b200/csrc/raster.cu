@@ -231,6 +231,7 @@ extern "C" int rast_render_depth(const float* verts, const int* faces, int V, in
                                                             zbuf_scratch);
   rast_resolve_kernel<<<blocks, 256, 0, st>>>(zbuf_scratch, Ks, n, H, W, znear, zfar, quantize_bits, depth, xyz_cam);
   GDRN_CHECK_CUDA(cudaGetLastError());
+  gdrn_count_launch(3);
   return GDRN_OK;
 }
 
@@ -250,5 +251,6 @@ extern "C" int gdrn_depth_refine_step(const float* xyz, const float* mask, const
   depth_refine_kernel<<<n, DR_THREADS, smem, (cudaStream_t)stream>>>(xyz, mask, depth_sensor, ren_depth, K_crop, trans,
                                                                     hw, thresh);
   GDRN_CHECK_CUDA(cudaGetLastError());
+  gdrn_count_launch(1);
   return GDRN_OK;
 }

@@ -225,6 +225,7 @@ int upnp_launch(const double* pts2d, const double* pts3d, const double* wgt2d, c
   upnp_kernel<<<(n_problems + warps_per_block - 1) / warps_per_block, 32 * warps_per_block, 0, st>>>(
       pts2d, pts3d, wgt2d, K, init_rt, result_rt, pn, n_problems);
   GDRN_CHECK_CUDA(cudaGetLastError());
+  gdrn_count_launch(1);
   return GDRN_OK;
 }
 

@@ -1,0 +1,351 @@
+"""Python surfaces of the reference's native extensions, backed by libgdrn_b200.so.
+
+Mirrors (same names, argument meaning and error behaviour):
+  * core/csrc/fps/fps_utils.py:6-21                  -> farthest_point_sampling(pts, sn, init_center)
+  * core/csrc/ransac_voting (pybind module)          -> ransac_voting.{generate_hypothesis, voting_for_hypothesis,
+        generate_hypothesis_vanishing_point, voting_for_hypothesis_vanishing_point}
+    and the driver core/csrc/ransac_voting/ransac_voting_gpu.py:7-104 -> ransac_voting_layer / _v3
+  * core/csrc/torch_nndistance/torch_nndistance.py   -> NNDFunction, nnd
+  * core/csrc/flow/flow_torch.py:15-40               -> FlowFunction, flow; flow_cuda.forward
+  * core/csrc/uncertainty_pnp/un_pnp_utils.py:11-78  -> uncertainty_pnp (EPnP init stays cv2 on the host)
+There is no CPU fallback: CUDA tensors in, CUDA tensors out (the numpy FPS entry stages through the GPU).
+"""
+import ctypes
+
+import numpy as np
+import torch
+from torch.autograd import Function
+
+from . import _lib
+
+
+def _check_cuda_contig(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be a contiguous tensor")
+
+
+# ------------------------------------------------------------------------------------------------- FPS
+def farthest_point_sampling(pts, sn, init_center=False):
+    """numpy [pn,3] -> pts[idxs] (fps_utils.py:6-21)."""
+    pn, _ = pts.shape
+    assert pts.shape[1] == 3
+    pts = np.ascontiguousarray(pts, np.float32)
+    idxs = np.ascontiguousarray(np.zeros([sn], np.int32))
+    L = _lib.lib()
+    fn = L.farthest_point_sampling_init_center if init_center else L.farthest_point_sampling
+    fn(pts.ctypes.data_as(ctypes.c_void_p), idxs.ctypes.data_as(ctypes.c_void_p), pn, sn)
+    return pts[idxs]
+
+
+def farthest_point_sampling_idx(pts, sn, start_idx=None):
+    """Batched device FPS: pts [b,pn,3] f32 CUDA -> idx [b,sn] i32. start_idx None = init_center."""
+    _check_cuda_contig(pts, "pts")
+    b, pn, _ = pts.shape
+    idx = torch.empty((b, sn), dtype=torch.int32, device=pts.device)
+    st = None
+    if start_idx is not None:
+        st = start_idx.to(device=pts.device, dtype=torch.int32).contiguous()
+    _lib.check(_lib.lib().gdrn_fps_cuda(_lib.ptr(pts), _lib.ptr(idx), pn, sn, b, _lib.ptr(st), _lib.current_stream()),
+               "gdrn_fps_cuda")
+    return idx
+
+
+# --------------------------------------------------------------------------------------- ransac_voting
+class _RansacVotingModule:
+    """Drop-in for the pybind module `ransac_voting` (ransac_voting.cpp:112-117)."""
+
+    @staticmethod
+    def _dims(direct, coords):
+        for t, n in ((direct, "direct"), (coords, "coords")):
+            _check_cuda_contig(t, n)
+        tn, vn, two = direct.shape
+        assert two == 2 and tuple(coords.shape) == (tn, 2)
+        return tn, vn
+
+    def generate_hypothesis(self, direct, coords, idxs):
+        tn, vn = self._dims(direct, coords)
+        _check_cuda_contig(idxs, "idxs")
+        hn = idxs.shape[0]
+        assert tuple(idxs.shape) == (hn, vn, 2) and idxs.dtype == torch.int32
+        hypo = torch.zeros((hn, vn, 2), dtype=direct.dtype, device=direct.device)
+        _lib.check(_lib.lib().rv_generate_hypothesis(_lib.ptr(direct), _lib.ptr(coords), _lib.ptr(idxs), _lib.ptr(hypo),
+                                                     tn, vn, hn, _lib.current_stream()), "rv_generate_hypothesis")
+        return hypo
+
+    def generate_hypothesis_vanishing_point(self, direct, coords, idxs):
+        tn, vn = self._dims(direct, coords)
+        _check_cuda_contig(idxs, "idxs")
+        hn = idxs.shape[0]
+        assert tuple(idxs.shape) == (hn, vn, 2) and idxs.dtype == torch.int32
+        hypo = torch.zeros((hn, vn, 3), dtype=direct.dtype, device=direct.device)
+        _lib.check(_lib.lib().rv_generate_hypothesis_vanishing_point(
+            _lib.ptr(direct), _lib.ptr(coords), _lib.ptr(idxs), _lib.ptr(hypo), tn, vn, hn, _lib.current_stream()),
+            "rv_generate_hypothesis_vanishing_point")
+        return hypo
+
+    def voting_for_hypothesis(self, direct, coords, hypo_pts, inliers, inlier_thresh):
+        tn, vn = self._dims(direct, coords)
+        _check_cuda_contig(hypo_pts, "hypo_pts")
+        _check_cuda_contig(inliers, "inliers")
+        hn = hypo_pts.shape[0]
+        assert tuple(hypo_pts.shape) == (hn, vn, 2) and tuple(inliers.shape) == (hn, vn, tn)
+        assert inliers.dtype == torch.uint8
+        _lib.check(_lib.lib().rv_voting_for_hypothesis(_lib.ptr(direct), _lib.ptr(coords), _lib.ptr(hypo_pts),
+                                                       _lib.ptr(inliers), tn, vn, hn, float(inlier_thresh),
+                                                       _lib.current_stream()), "rv_voting_for_hypothesis")
+
+    def voting_for_hypothesis_vanishing_point(self, direct, coords, hypo_pts, inliers, inlier_thresh):
+        tn, vn = self._dims(direct, coords)
+        _check_cuda_contig(hypo_pts, "hypo_pts")
+        _check_cuda_contig(inliers, "inliers")
+        hn = hypo_pts.shape[0]
+        assert tuple(hypo_pts.shape) == (hn, vn, 3) and tuple(inliers.shape) == (hn, vn, tn)
+        _lib.check(_lib.lib().rv_voting_for_hypothesis_vanishing_point(
+            _lib.ptr(direct), _lib.ptr(coords), _lib.ptr(hypo_pts), _lib.ptr(inliers), tn, vn, hn, float(inlier_thresh),
+            _lib.current_stream()), "rv_voting_for_hypothesis_vanishing_point")
+
+    def vote_count(self, direct, coords, hypo_pts, inlier_thresh, vanishing_point=False):
+        """Fused vote + count (no [hn,vn,tn] mask): -> counts [hn,vn] int32."""
+        tn, vn = self._dims(direct, coords)
+        _check_cuda_contig(hypo_pts, "hypo_pts")
+        hn = hypo_pts.shape[0]
+        counts = torch.empty((hn, vn), dtype=torch.int32, device=direct.device)
+        _lib.check(_lib.lib().rv_vote_count(_lib.ptr(direct), _lib.ptr(coords), _lib.ptr(hypo_pts), _lib.ptr(counts),
+                                            tn, vn, hn, float(inlier_thresh), int(vanishing_point),
+                                            _lib.current_stream()), "rv_vote_count")
+        return counts
+
+
+ransac_voting = _RansacVotingModule()
+
+
+def _b_inv(b_mat):
+    eye = b_mat.new_ones(b_mat.size(-1)).diag().expand_as(b_mat)
+    try:
+        return torch.linalg.solve(b_mat, eye)
+    except Exception:  # singular: the reference falls back to identity (ransac_voting_gpu.py:107-119)
+        return eye
+
+
+def ransac_voting_layer(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20, min_num=5,
+                        max_num=30000, fused=True, idxs_fn=None):
+    """ransac_voting_gpu.py:7-104 (v3 = same loop with bool masks and b_inv).  mask [b,h,w], vertex [b,h,w,vn,2].
+
+    ``fused=True`` counts inliers with rv_vote_count instead of materialising the [hn,vn,tn] mask + torch.sum
+    (identical counts).  ``idxs_fn(round_hyp_num, vn, tn)`` may supply the hypothesis pixel pairs (tests)."""
+    b, h, w, vn, _ = vertex.shape
+    batch_win_pts = []
+    for bi in range(b):
+        hyp_num = 0
+        cur_mask = mask[bi].to(torch.bool)
+        foreground_num = torch.sum(cur_mask)
+        if foreground_num < min_num:
+            batch_win_pts.append(torch.zeros([1, vn, 2], dtype=torch.float32, device=mask.device))
+            continue
+        if foreground_num > max_num:
+            selection = torch.zeros(cur_mask.shape, dtype=torch.float32, device=mask.device).uniform_(0, 1)
+            cur_mask = cur_mask & (selection < (max_num / foreground_num.float()))
+        coords = torch.nonzero(cur_mask).float()[:, [1, 0]].contiguous()
+        direct = vertex[bi].masked_select(cur_mask[:, :, None, None]).view([coords.shape[0], vn, 2]).contiguous()
+        tn = coords.shape[0]
+        if idxs_fn is not None:
+            idxs = idxs_fn(round_hyp_num, vn, tn).to(device=mask.device, dtype=torch.int32).contiguous()
+        else:
+            idxs = torch.zeros([round_hyp_num, vn, 2], dtype=torch.int32, device=mask.device).random_(0, tn)
+        all_win_ratio = torch.zeros([vn], dtype=torch.float32, device=mask.device)
+        all_win_pts = torch.zeros([vn, 2], dtype=torch.float32, device=mask.device)
+        cur_iter = 0
+        while True:
+            cur_hyp_pts = ransac_voting.generate_hypothesis(direct, coords, idxs)
+            if fused:
+                cur_inlier_counts = ransac_voting.vote_count(direct, coords, cur_hyp_pts, inlier_thresh).long()
+            else:
+                cur_inlier = torch.zeros([round_hyp_num, vn, tn], dtype=torch.uint8, device=mask.device)
+                ransac_voting.voting_for_hypothesis(direct, coords, cur_hyp_pts, cur_inlier, inlier_thresh)
+                cur_inlier_counts = torch.sum(cur_inlier, 2)
+            cur_win_counts, cur_win_idx = torch.max(cur_inlier_counts, 0)
+            cur_win_pts = cur_hyp_pts[cur_win_idx, torch.arange(vn, device=mask.device)]
+            cur_win_ratio = cur_win_counts.float() / tn
+            larger_mask = all_win_ratio < cur_win_ratio
+            all_win_pts[larger_mask, :] = cur_win_pts[larger_mask, :]
+            all_win_ratio[larger_mask] = cur_win_ratio[larger_mask]
+            hyp_num += round_hyp_num
+            cur_iter += 1
+            cur_min_ratio = torch.min(all_win_ratio)
+            if (1 - (1 - cur_min_ratio**2) ** hyp_num) > confidence or cur_iter > max_iter:
+                break
+            if idxs_fn is None:
+                pass  # the reference re-uses the same idxs every round (ransac_voting_gpu.py:48 is outside the loop)
+        normal = torch.zeros_like(direct)
+        normal[:, :, 0] = direct[:, :, 1]
+        normal[:, :, 1] = -direct[:, :, 0]
+        all_inlier = torch.zeros([1, vn, tn], dtype=torch.uint8, device=mask.device)
+        ransac_voting.voting_for_hypothesis(direct, coords, all_win_pts[None].contiguous(), all_inlier, inlier_thresh)
+        all_inlier = torch.squeeze(all_inlier.float(), 0)
+        normal = normal.permute(1, 0, 2) * torch.unsqueeze(all_inlier, 2)
+        bvec = torch.sum(normal * torch.unsqueeze(coords, 0), 2)
+        ATA = torch.matmul(normal.permute(0, 2, 1), normal)
+        ATb = torch.sum(normal * torch.unsqueeze(bvec, 2), 1)
+        win = torch.matmul(_b_inv(ATA), torch.unsqueeze(ATb, 2))
+        batch_win_pts.append(win[None, :, :, 0])
+    return torch.cat(batch_win_pts)
+
+
+ransac_voting_layer_v3 = ransac_voting_layer
+
+
+# ------------------------------------------------------------------------------------------------ nnd
+class _NndModule:
+    """Drop-in for torch_nndistance_aten (nnd_cuda.cpp:86-89)."""
+
+    @staticmethod
+    def nnd_forward_cuda(xyz1, xyz2, dist1, dist2, idx1, idx2):
+        for t, n in ((xyz1, "xyz1"), (xyz2, "xyz2"), (dist1, "dist1"), (dist2, "dist2"), (idx1, "idx1"), (idx2, "idx2")):
+            _check_cuda_contig(t, n)
+        b, n, _ = xyz1.shape
+        m = xyz2.shape[1]
+        return _lib.lib().nnd_forward_cuda(_lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(dist1), _lib.ptr(dist2),
+                                           _lib.ptr(idx1), _lib.ptr(idx2), b, n, m, _lib.current_stream())
+
+    @staticmethod
+    def nnd_backward_cuda(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, idx1, idx2):
+        b, n, _ = xyz1.shape
+        m = xyz2.shape[1]
+        return _lib.lib().nnd_backward_cuda(_lib.ptr(xyz1), _lib.ptr(xyz2), _lib.ptr(gradxyz1), _lib.ptr(gradxyz2),
+                                            _lib.ptr(graddist1), _lib.ptr(graddist2), _lib.ptr(idx1), _lib.ptr(idx2),
+                                            b, n, m, _lib.current_stream())
+
+
+torch_nndistance_aten = _NndModule()
+
+
+class NNDFunction(Function):
+    """torch_nndistance.py:13-84."""
+
+    @staticmethod
+    def forward(ctx, xyz1, xyz2):
+        if not xyz1.is_cuda:
+            raise RuntimeError("nnd: CUDA tensors required (no CPU fallback)")
+        xyz1 = xyz1.contiguous().float()
+        xyz2 = xyz2.contiguous().float()
+        b, n, _ = xyz1.size()
+        m = xyz2.size(1)
+        dist1 = torch.zeros(b, n, device=xyz1.device)
+        dist2 = torch.zeros(b, m, device=xyz1.device)
+        idx1 = torch.zeros(b, n, dtype=torch.int32, device=xyz1.device)
+        idx2 = torch.zeros(b, m, dtype=torch.int32, device=xyz1.device)
+        if torch_nndistance_aten.nnd_forward_cuda(xyz1, xyz2, dist1, dist2, idx1, idx2) != 1:
+            raise _lib.GdrnError("nnd_forward_cuda failed: " + _lib.last_error())
+        ctx.save_for_backward(xyz1, xyz2, dist1, dist2, idx1, idx2)
+        return dist1, dist2
+
+    @staticmethod
+    def backward(ctx, graddist1, graddist2):
+        xyz1, xyz2, dist1, dist2, idx1, idx2 = ctx.saved_tensors
+        graddist1 = graddist1.contiguous()
+        graddist2 = graddist2.contiguous()
+        gradxyz1 = torch.zeros_like(xyz1)
+        gradxyz2 = torch.zeros_like(xyz2)
+        if torch_nndistance_aten.nnd_backward_cuda(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, idx1, idx2) != 1:
+            raise _lib.GdrnError("nnd_backward_cuda failed: " + _lib.last_error())
+        return gradxyz1, gradxyz2
+
+
+def nnd(xyz1, xyz2):
+    return NNDFunction.apply(xyz1, xyz2)
+
+
+# ----------------------------------------------------------------------------------------------- flow
+class _FlowModule:
+    """Drop-in for flow_cuda (flow_cuda.cpp:30-47)."""
+
+    @staticmethod
+    def forward(depth_src, depth_tgt, KT, Kinv):
+        for t, n in ((depth_src, "depth_src"), (depth_tgt, "depth_tgt"), (KT, "KT"), (Kinv, "Kinv")):
+            _check_cuda_contig(t, n)
+        if depth_src.dtype != torch.float32:
+            raise RuntimeError("flow_cuda.forward: float32 only on the B200 path")
+        B, _, H, W = depth_src.shape
+        flow = torch.empty((B, 2, H, W), dtype=torch.float32, device=depth_src.device)
+        valid = torch.empty((B, 1, H, W), dtype=torch.float32, device=depth_src.device)
+        _lib.check(_lib.lib().flow_forward_cuda(_lib.ptr(depth_src), _lib.ptr(depth_tgt), _lib.ptr(KT), _lib.ptr(Kinv),
+                                                _lib.ptr(flow), _lib.ptr(valid), B, H, W, _lib.current_stream()),
+                   "flow_forward_cuda")
+        return [flow, valid]
+
+
+flow_cuda = _FlowModule()
+
+
+def calc_se3_torch_batch(pose_src, pose_tgt):
+    """core/utils/pose_utils.py calc_se3_torch_batch: T = pose_tgt * inv(pose_src), [B,3,4]."""
+    R_s, t_s = pose_src[:, :3, :3], pose_src[:, :3, 3:4]
+    R_t, t_t = pose_tgt[:, :3, :3], pose_tgt[:, :3, 3:4]
+    R = R_t @ R_s.transpose(1, 2)
+    t = t_t - R @ t_s
+    return torch.cat([R, t], dim=2)
+
+
+class FlowFunction(Function):
+    """flow_torch.py:15-40."""
+
+    @staticmethod
+    def forward(ctx, depth_src, depth_tgt, pose_src, pose_tgt, K):
+        se3 = calc_se3_torch_batch(pose_src, pose_tgt)
+        KT = (K @ se3).contiguous()
+        Kinv = K.inverse().contiguous()
+        out = flow_cuda.forward(depth_src.contiguous(), depth_tgt.contiguous(), KT, Kinv)
+        return out[0], out[1]
+
+
+flow = FlowFunction.apply
+
+
+# ------------------------------------------------------------------------------------ uncertainty pnp
+def uncertainty_pnp_refine(points_2d, weights_2d, points_3d, camera_matrix, init_rt):
+    """The compiled part of un_pnp_utils.uncertainty_pnp (lib.uncertainty_pnp): host f64 arrays -> result_rt [6]."""
+    pn = points_2d.shape[0]
+    a2 = np.ascontiguousarray(points_2d, np.float64)
+    a3 = np.ascontiguousarray(points_3d, np.float64)
+    aw = np.ascontiguousarray(weights_2d, np.float64)
+    aK = np.ascontiguousarray(camera_matrix, np.float64)
+    ai = np.ascontiguousarray(init_rt, np.float64).reshape(6)
+    res = np.empty([6], np.float64)
+    c = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    _lib.lib().uncertainty_pnp(c(a2), c(a3), c(aw), c(aK), c(ai), c(res), pn)
+    return res
+
+
+def uncertainty_pnp(points_2d, weights_2d, points_3d, camera_matrix):
+    """un_pnp_utils.py:11-78: EPnP on the 4 highest-weight points (cv2, host) then weighted LM refine -> [3,4]."""
+    import cv2
+
+    pn = points_2d.shape[0]
+    assert points_3d.shape[0] == pn and pn >= 4
+    dist_coeffs = np.zeros(shape=[8, 1], dtype=np.float64)
+    points_3d = points_3d.astype(np.float64)
+    points_2d = points_2d.astype(np.float64)
+    weights_2d = weights_2d.astype(np.float64)
+    camera_matrix = camera_matrix.astype(np.float64)
+    idxs = np.argsort(weights_2d[:, 0] + weights_2d[:, 1])[-4:]
+    _, R_exp, t = cv2.solvePnP(np.expand_dims(points_3d[idxs, :], 0), np.expand_dims(points_2d[idxs, :], 0),
+                               camera_matrix, dist_coeffs, None, None, False, flags=cv2.SOLVEPNP_EPNP)
+    if pn == 4:
+        R, _ = cv2.Rodrigues(R_exp)
+        return np.concatenate([R, t], axis=-1)
+    init_rt = np.concatenate([R_exp, t], 0)
+    result_rt = uncertainty_pnp_refine(points_2d, weights_2d, points_3d, camera_matrix, init_rt)
+    R, _ = cv2.Rodrigues(result_rt[:3])
+    return np.concatenate([R, result_rt[3:, None]], axis=-1)
+
+
+def uncertainty_pnp_batched(pts2d, pts3d, wgt2d, K, init_rt):
+    """Device batched refine: pts2d [n,pn,2], pts3d [n,pn,3], wgt2d [n,pn,3], K [n,3,3], init_rt [n,6] (f64 CUDA)."""
+    n, pn, _ = pts2d.shape
+    ts = [t.to(torch.float64).contiguous() for t in (pts2d, pts3d, wgt2d, K, init_rt)]
+    res = torch.empty((n, 6), dtype=torch.float64, device=pts2d.device)
+    _lib.check(_lib.lib().upnp_batched(*[_lib.ptr(t) for t in ts], _lib.ptr(res), pn, n, _lib.current_stream()),
+               "upnp_batched")
+    return res

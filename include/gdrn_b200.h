@@ -25,6 +25,8 @@ extern "C" {
 
 const char* gdrn_last_error(void);
 int gdrn_version(void);
+/* number of CUDA kernels this library has launched in the calling process (monotonic) */
+long long gdrn_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Dense path: GDRN_DoubleMask.forward (eval, do_loss=False)
@@ -69,6 +71,12 @@ int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int64_t* roi_cl
                        const float* resize_ratios, const float* roi_extents, int batch, float* out_rot,
                        float* out_trans, float* out_raw, const GdrnMaps* maps, void* workspace,
                        size_t workspace_bytes, void* stream);
+
+/* Per-category device timing of the LAST forward (CUDA events on the launch stream): categories
+ * 0 = tcgen05 GEMM kernel, 1 = depthwise-7x7+LayerNorm kernel, 2 = other CUDA-core kernels.
+ * get_profile blocks until that forward has finished. */
+int gdrn_model_set_profiling(GdrnModel* m, int enable);
+int gdrn_model_get_profile(GdrnModel* m, float* ms_out, int* launches_out);
 
 /* debugging / parity hooks: copy an internal activation (after the last forward on the same workspace)
  * as fp32 into dst.  name: "conv_feat" ([B,8,8,C3] NHWC) | "stage0".."stage3" | "head16"|"head32"|"head64"

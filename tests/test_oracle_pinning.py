@@ -1,0 +1,151 @@
+"""Pin the oracle: against the reference's own code where it runs here (FPS .cpp compiled into oracle/_ref,
+Python head/PnP/pose classes imported with stubbed third-party deps -> tests/golden/*.npz), and against
+independent formulations elsewhere."""
+import ctypes
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from oracle import gdrn_model_oracle as O
+from oracle import ops_oracle as OO
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_fps_oracle_matches_survey_vector():
+    # reference build, RandomState(0).rand(5000,3) f32, init_center, 8 samples
+    pts = np.random.RandomState(0).rand(5000, 3).astype(np.float32)
+    assert OO.fps(pts, 8).tolist() == [2895, 884, 2241, 4602, 3356, 3779, 3096, 4550]
+
+
+def test_fps_oracle_matches_golden_fixture():
+    g = np.load(os.path.join(GOLD, "fps_golden.npz"))
+    for i in range(int(g["n_cases"])):
+        pts, idx = g[f"pts_{i}"], g[f"idx_{i}"]
+        assert (OO.fps(pts, len(idx)) == idx).all(), i
+
+
+def test_fps_oracle_matches_reference_build_when_present():
+    path = os.path.join(ROOT, "oracle", "_ref", "libfps_ref.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libfps_ref.so not built (no /root/reference)")
+    ref = ctypes.CDLL(path)
+    rs = np.random.RandomState(5)
+    for pn, sn in ((1, 1), (7, 7), (100, 16), (3000, 64), (20000, 128)):
+        pts = (rs.rand(pn, 3).astype(np.float32) - 0.5) * 0.3
+        if pn == 100:
+            pts[10:20] = pts[0]  # duplicates -> zero distances / ties
+        idx = np.zeros(sn, np.int32)
+        ref.farthest_point_sampling_init_center(pts.ctypes.data_as(ctypes.c_void_p), idx.ctypes.data_as(ctypes.c_void_p), pn, sn)
+        assert (OO.fps(pts, sn) == idx).all(), (pn, sn)
+
+
+def test_head_pnp_pose_oracle_matches_reference_classes():
+    """tests/golden/ref_heads.npz was produced by tools/make_golden_ref_heads.py, which imports the reference's
+    own TopDownDoubleMaskXyzRegionHead / ConvPnPNet / rot6d / pose_from_predictions_test / allo->ego code."""
+    path = os.path.join(GOLD, "ref_heads.npz")
+    g = np.load(path)
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd/")}
+    feat = torch.from_numpy(g["in/feat"])
+    with torch.no_grad():
+        outs = O.geo_head(sd, feat, num_classes=int(g["num_classes"]))
+    for name, o in zip(("vis", "full", "cx", "cy", "cz", "region"), outs):
+        assert torch.allclose(o, torch.from_numpy(g["out/" + name]), atol=2e-5, rtol=1e-4), name
+    with torch.no_grad():
+        rot, t = O.conv_pnp_net(sd, torch.from_numpy(g["in/coor_feat"]), torch.from_numpy(g["in/region"]),
+                                torch.from_numpy(g["in/extents"]))
+    assert torch.allclose(rot, torch.from_numpy(g["out/pnp_rot"]), atol=1e-5, rtol=1e-4)
+    assert torch.allclose(t, torch.from_numpy(g["out/pnp_t_raw"]), atol=1e-5, rtol=1e-4)
+    Rm = O.rot6d_to_mat_batch(torch.from_numpy(g["out/pnp_rot"]))
+    assert torch.allclose(Rm, torch.from_numpy(g["out/rot_m"]), atol=1e-6)
+    ego, trans = O.pose_from_predictions_test(
+        torch.from_numpy(g["out/rot_m"]), torch.from_numpy(g["out/pnp_t"])[:, :2], torch.from_numpy(g["out/pnp_t"])[:, 2:3],
+        torch.from_numpy(g["in/cams"]), torch.from_numpy(g["in/centers"]), torch.from_numpy(g["in/ratios"]),
+        torch.from_numpy(g["in/whs"]))
+    assert np.allclose(ego.numpy(), g["out/ego_rot"], atol=1e-6)
+    assert np.allclose(trans.numpy(), g["out/trans"], atol=1e-7)
+
+
+def test_backbone_oracle_param_count_and_fp64_agreement():
+    from gdrnpp_bop2022_b200.synthetic import make_batch, make_state_dict
+
+    sd = make_state_dict("convnext_tiny")
+    batch = make_batch(B=1, seed=2)
+    with torch.no_grad():
+        f32 = O.convnext_features(sd, batch["roi_img"], "convnext_tiny")
+        f64 = O.convnext_features(O.cast_state_dict(sd, torch.float64), batch["roi_img"].double(), "convnext_tiny")
+    assert f32.shape == (1, 768, 8, 8)
+    assert (f32.double() - f64).abs().max() / f64.abs().max() < 1e-4
+    sdb = make_state_dict("convnext_base")
+    assert sum(v.numel() for k, v in sdb.items() if k.startswith("backbone.")) == 87564416
+
+
+def test_gelu_epilogue_fit_accuracy():
+    hdr = open(os.path.join(ROOT, "gdrnpp_bop2022_b200", "csrc", "gelu_coeffs.h")).read()
+    c = [float(l.split()[2].rstrip("f")) for l in hdr.splitlines() if l.startswith("#define GELU_C") and "CLAMP" not in l]
+    clamp = float([l for l in hdr.splitlines() if "GELU_CLAMP" in l][0].split()[2].rstrip("f"))
+    x = np.linspace(-8, 8, 40001)
+    xc = np.clip(x, -clamp, clamp)
+    p = ((c[3] * xc**2 + c[2]) * xc**2 + c[1]) * xc**2 + c[0]
+    g = x / (1 + np.exp2(xc * p))
+    ref = torch.nn.functional.gelu(torch.from_numpy(x)).numpy()
+    assert np.abs(g - ref).max() < 3e-5
+
+
+def test_nnd_oracle_vs_cdist():
+    rs = np.random.RandomState(1)
+    a, b = rs.rand(2, 200, 3).astype(np.float32), rs.rand(2, 300, 3).astype(np.float32)
+    d1, d2, i1, i2 = OO.nnd_forward(a, b)
+    cd = torch.cdist(torch.from_numpy(a).double(), torch.from_numpy(b).double()) ** 2
+    assert np.abs(d1 - cd.min(2)[0].numpy()).max() < 1e-6
+    assert (i1 == cd.argmin(2).numpy()).mean() > 0.999
+
+
+def test_voting_oracle_geometry():
+    # all pixels point exactly at a known keypoint -> every valid hypothesis is that keypoint and all vote for it
+    rs = np.random.RandomState(2)
+    tn, vn, hn = 500, 3, 32
+    coords = rs.rand(tn, 2).astype(np.float32) * 100
+    kp = np.array([[50.3, 40.2], [10.0, 90.0], [70.5, 20.25]], np.float32)
+    d = kp[None] - coords[:, None]
+    direct = (d / np.linalg.norm(d, axis=2, keepdims=True)).astype(np.float32)
+    idxs = rs.randint(0, tn, (hn, vn, 2)).astype(np.int32)
+    hyp = OO.generate_hypothesis(direct, coords, idxs)
+    ok = np.abs(hyp).sum(2) > 0
+    assert ok.mean() > 0.9
+    assert np.abs(hyp[ok] - np.broadcast_to(kp[None], hyp.shape)[ok]).max() < 0.05
+    inl, cnt = OO.voting(direct, coords, hyp, 0.999)
+    assert (cnt[ok] > 0.95 * tn).all()
+    assert (inl.sum(2) == cnt).all()
+
+
+def test_raster_oracle_sphere_depth():
+    from gdrnpp_bop2022_b200.synthetic import make_icosphere_mesh
+
+    v, f = make_icosphere_mesh(3, (0.1, 0.1, 0.1))
+    pose = np.hstack([np.eye(3), [[0.0], [0.0], [0.5]]]).astype(np.float32)
+    K = np.array([[100, 0, 32], [0, 100, 32], [0, 0, 1]], np.float32)
+    d = OO.render_depth(v, f, pose, K, 64, 64)
+    assert abs(d[32, 32] - 0.45) < 2e-3 and d[0, 0] == 0
+    # silhouette radius: r/z*f = 0.05/sqrt(0.5^2-0.05^2)*100 ~ 10.05 px -> area ~ 317 px
+    assert abs((d > 0).sum() - 317) < 20
+
+
+def test_upnp_oracle_known_answer():
+    # recipe of the reference's own main() (uncertainty_pnp.cpp:98-156)
+    rs = np.random.RandomState(3)
+    rt = rs.rand(6)
+    p3 = rs.rand(8, 3)
+    K = np.array([[400.0, 0, 128], [0, 400, 128], [0, 0, 1]])
+    p2 = np.zeros((8, 2))
+    for i in range(8):
+        q = OO._rodrigues_point(rt[:3], p3[i]) + rt[3:]
+        p2[i] = [K[0, 0] * q[0] / q[2] + K[0, 2], K[1, 1] * q[1] / q[2] + K[1, 2]]
+    w = np.tile(np.array([[1.0, 0.0, 1.0]]), (8, 1))
+    init = rt + rs.rand(6) * 0.1
+    sol = OO.uncertainty_pnp(p2, p3, w, K, init)
+    assert np.abs(sol - rt).max() < 1e-5
