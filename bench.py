@@ -146,7 +146,7 @@ def bench_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -214,11 +214,17 @@ def main():
     torch.cuda.synchronize()
 
     # ---------------- device-resident timing (value) ----------------
+    # nvidia-smi needs ~0.3 s to deliver its first sample: start it while the (untimed) load is already running
+    # so that every sample is taken under the same load as the timed region.
     sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_spin = time.perf_counter()
+    while len(sampler.lines) < 2 and time.perf_counter() - t_spin < 3.0:
+        fwd(resident[0])
+        torch.cuda.synchronize()
     launches0 = L.gdrn_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    sampler.start()
     e0.record()
     rots, transes = [], []
     for i in range(args.steps):

@@ -1,4 +1,5 @@
 // Error channel, version, and the exported plain-GEMM entry (tests + roofline measurement).
+#include <stdlib.h>
 #include <string.h>
 #include <atomic>
 
@@ -24,6 +25,8 @@ extern "C" int gdrn_gemm_bf16(const void* A, const void* W, const float* bias, c
   GDRN_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem");
   GDRN_REQUIRE(K % 8 == 0, "gemm: K must be a multiple of 8 (16-byte TMA row pitch)");
   GDRN_REQUIRE(epi >= 0 && epi <= 2, "gemm: epi must be 0 (store), 1 (gelu) or 2 (resid)");
+  GDRN_REQUIRE(block_n < 64 || N % (block_n / 2 < 64 ? block_n / 2 : 64) == 0,
+               "gemm: N must be a multiple of min(block_n/2, 64) for block_n >= 64");
   GemmPlan p;
   memset(&p, 0, sizeof(p));
   uint64_t dims_a[2] = {(uint64_t)K, (uint64_t)M};
@@ -46,6 +49,7 @@ extern "C" int gdrn_gemm_bf16(const void* A, const void* W, const float* bias, c
   p.N = N;
   p.epi = epi;
   p.out_f32 = (epi == 2) ? 1 : (epi == 1 ? 0 : out_f32);
+  if (const char* e = getenv("GDRN_GELU_MODE")) p.gelu_mode = atoi(e);
   p.out = out;
   p.ldo = N;
   p.bias = bias;

@@ -3,8 +3,12 @@
 // Reference semantics: timm 0.6.7 ConvNeXtBlock (third-party), heads/top_down_doublemask_xyz_region_head.py,
 // heads/conv_pnp_net.py, core/utils/rot_reps.py:34-55, models/pose_from_pred_centroid_z.py:56-154,
 // core/utils/utils.py:31-88.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "dense_ops.h"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -184,6 +188,173 @@ dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ w49c, co
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// depthwise 7x7 + bias + LayerNorm(C), thread-block-cluster version (the one the forward uses).
+//   CTA  = one TWxTW output tile of one image x CPC channels (64 for TW=16, 128 for TW=8); the zero-padded
+//          (TW+6)^2 x CPC fp32 input tile lives in shared memory (124 KB / 100 KB).
+//   thread = ONE channel x (2 rows x TW pixels): its 49 filter taps stay in registers, every input row it
+//          loads from smem feeds two output rows (>= 9 FMA per LDS -> FP32-FMA bound, not LSU bound).
+//   cluster = the C/CPC CTAs (2/4/8) that together hold all channels of the tile: the LayerNorm mean and
+//          centred variance are reduced across them through distributed shared memory (two exchanges).
+// In-warp per-pixel channel sums use a transposing shuffle reduction (31 shuffles for 32 values).
+template <int N>
+__device__ __forceinline__ float lane_transpose_reduce(float (&a)[N], int lane) {
+  static_assert(N == 32 || N == 16, "N");
+  constexpr int STEPS = (N == 32) ? 5 : 4;
+#pragma unroll
+  for (int st = 0; st < STEPS; ++st) {
+    const int o = 16 >> st;        // lane bit
+    const int n = (N / 2) >> st;   // values kept after this step
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+      const float send = up ? a[j] : a[j + n];
+      const float keep = up ? a[j + n] : a[j];
+      a[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  if (N == 16) a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+  return a[0];  // N == 32: lane L holds element L;  N == 16: lane L holds element L >> 1
+}
+
+template <int TW>
+__global__ void __launch_bounds__(512, 1)
+dwconv_ln_cluster_kernel(const float* __restrict__ x, const float* __restrict__ w49c, const float* __restrict__ bias,
+                         const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                         __nv_bfloat16* __restrict__ out, int B, int H, int W, int C, float eps) {
+  constexpr int CPC = (TW == 16) ? 64 : 128;  // channels per CTA
+  constexpr int IW = TW + 6;
+  constexpr int NPIX = TW * TW;
+  constexpr int NP = 2 * TW;                  // pixels per thread
+  constexpr int WPR = CPC / 32;               // channel-warps per row pair
+  extern __shared__ float smem_dw[];
+  float* tile = smem_dw;                      // [IW][IW][CPC]
+  float* s_part = tile + IW * IW * CPC;       // [WPR][NPIX]
+  float* s_cta1 = s_part + WPR * NPIX;        // [NPIX] this CTA's channel-slice sums (read by the cluster)
+  float* s_cta2 = s_cta1 + NPIX;              // [NPIX] centred sums of squares
+  float* s_mean = s_cta2 + NPIX;              // [NPIX]
+  float* s_rstd = s_mean + NPIX;              // [NPIX]
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int nrank = (int)cluster.num_blocks();
+  const int c0 = blockIdx.x * CPC;
+  const int tiles_x = W / TW;
+  const int x0 = (blockIdx.y % tiles_x) * TW;
+  const int y0 = (blockIdx.y / tiles_x) * TW;
+  const int b = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int c_local = tid % CPC;
+  const int rp = tid / CPC;                   // row pair: output rows 2rp, 2rp+1
+  const int wc = (tid >> 5) % WPR;
+
+  // ---- stage the zero-padded input tile ----
+  {
+    constexpr int Q = CPC / 4;
+    const float* xb = x + (long long)b * H * W * C + c0;
+    for (int i = tid; i < IW * IW * Q; i += 512) {
+      const int q = i % Q, pix = i / Q;
+      const int iy = pix / IW, ix = pix % IW;
+      const int gy = y0 + iy - 3, gx = x0 + ix - 3;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = *reinterpret_cast<const float4*>(xb + ((long long)gy * W + gx) * C + q * 4);
+      *reinterpret_cast<float4*>(tile + pix * CPC + q * 4) = v;
+    }
+  }
+  float wreg[49];
+#pragma unroll
+  for (int t = 0; t < 49; ++t) wreg[t] = __ldg(w49c + t * C + c0 + c_local);
+  __syncthreads();
+
+  // ---- convolution: 2 output rows x TW pixels for one channel ----
+  float acc[NP];
+  {
+    const float bv = __ldg(bias + c0 + c_local);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) acc[i] = bv;
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    float v[IW];
+    const float* rowp = tile + ((2 * rp + r) * IW) * CPC + c_local;
+#pragma unroll
+    for (int j = 0; j < IW; ++j) v[j] = rowp[j * CPC];
+#pragma unroll
+    for (int oy = 0; oy < 2; ++oy) {
+      const int ky = r - oy;
+      if (ky >= 0 && ky < 7) {
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx)
+#pragma unroll
+          for (int ox = 0; ox < TW; ++ox) acc[oy * TW + ox] = fmaf(v[ox + kx], wreg[ky * 7 + kx], acc[oy * TW + ox]);
+      }
+    }
+  }
+
+  // ---- LayerNorm pass 1: mean over all C channels of each pixel ----
+  const int my_slot = rp * NP + ((NP == 32) ? lane : (lane >> 1));
+  {
+    float a[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) a[i] = acc[i];
+    const float s = lane_transpose_reduce<NP>(a, lane);
+    if (NP == 32 || (lane & 1) == 0) s_part[wc * NPIX + my_slot] = s;
+  }
+  __syncthreads();
+  if (tid < NPIX) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < WPR; ++k) s += s_part[k * NPIX + tid];
+    s_cta1[tid] = s;
+  }
+  cluster.sync();
+  if (tid < NPIX) {
+    float s = 0.f;
+    for (int rk = 0; rk < nrank; ++rk) s += cluster.map_shared_rank(s_cta1, rk)[tid];
+    s_mean[tid] = s / (float)C;
+  }
+  __syncthreads();
+  // ---- pass 2: centred variance ----
+  float mean_r[NP];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) mean_r[i] = s_mean[rp * NP + i];
+  {
+    float a[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) { const float d = acc[i] - mean_r[i]; a[i] = d * d; }
+    const float s = lane_transpose_reduce<NP>(a, lane);
+    if (NP == 32 || (lane & 1) == 0) s_part[wc * NPIX + my_slot] = s;
+  }
+  __syncthreads();
+  if (tid < NPIX) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < WPR; ++k) s += s_part[k * NPIX + tid];
+    s_cta2[tid] = s;
+  }
+  cluster.sync();
+  if (tid < NPIX) {
+    float s = 0.f;
+    for (int rk = 0; rk < nrank; ++rk) s += cluster.map_shared_rank(s_cta2, rk)[tid];
+    s_rstd[tid] = rsqrtf(s / (float)C + eps);
+  }
+  __syncthreads();
+  // ---- normalise + affine, bf16 out ----
+  const float gw = __ldg(ln_w + c0 + c_local), gb = __ldg(ln_b + c0 + c_local);
+#pragma unroll
+  for (int oy = 0; oy < 2; ++oy) {
+    const int gy = y0 + 2 * rp + oy;
+    __nv_bfloat16* orow = out + (((long long)b * H + gy) * W + x0) * C + c0 + c_local;
+#pragma unroll
+    for (int ox = 0; ox < TW; ++ox) {
+      const int i = oy * TW + ox;
+      const float r = s_rstd[rp * NP + i];
+      orow[(long long)ox * C] = __float2bfloat16(fmaf((acc[i] - mean_r[i]) * r, gw, gb));
+    }
+  }
+  cluster.sync();  // nobody leaves while a peer may still read its shared memory
+}
+
 // ------------------------------------------------------------------------------------------------
 // LayerNorm2d + 2x2 stride-2 patchify: one warp per source pixel.
 __global__ void __launch_bounds__(256)
@@ -269,10 +440,21 @@ __device__ __forceinline__ void load8(const void* raw, int is_f32, long long off
   }
 }
 
+// per-(image, group) mean / rstd from the double sums accumulated by the conv epilogue
+__global__ void gn_finalize_kernel(const double* __restrict__ stats, float2* __restrict__ mr, int n_bg, double count,
+                                   float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_bg) return;
+  const double mean = stats[2 * i] / count;
+  double var = stats[2 * i + 1] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  mr[i] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+}
+
 __global__ void __launch_bounds__(256)
-gn_gelu_kernel(const void* __restrict__ raw, int raw_is_f32, const double* __restrict__ stats,
+gn_gelu_kernel(const void* __restrict__ raw, int raw_is_f32, const float2* __restrict__ mr,
                const float* __restrict__ gn_w, const float* __restrict__ gn_b, __nv_bfloat16* __restrict__ out, int B,
-               int h, int w, int C, int groups, float eps, int up) {
+               int h, int w, int C, int groups, int up) {
   const int cv = C >> 3;
   const int oh = h * up, ow = w * up;
   const long long total = (long long)B * oh * ow * cv;
@@ -287,18 +469,18 @@ gn_gelu_kernel(const void* __restrict__ raw, int raw_is_f32, const double* __res
   // per-channel scale/shift: y = v * a + s
   float a[8], s[8];
   {
-    const double n = (double)h * w * cpg;
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(gn_w + c8)), w1 = __ldg(reinterpret_cast<const float4*>(gn_w + c8 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(gn_b + c8)), b1 = __ldg(reinterpret_cast<const float4*>(gn_b + c8 + 4));
+    const float gw[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    const float gb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float2 m = __ldg(mr + (long long)b * groups + c8 / cpg);
+    int gcur = c8 / cpg;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int g = (c8 + k) / cpg;
-      const double su = stats[((long long)b * groups + g) * 2], sq = stats[((long long)b * groups + g) * 2 + 1];
-      const double mean = su / n;
-      double var = sq / n - mean * mean;
-      if (var < 0.0) var = 0.0;
-      const float r = (float)(1.0 / sqrt(var + (double)eps));
-      const float gw = __ldg(gn_w + c8 + k), gb = __ldg(gn_b + c8 + k);
-      a[k] = r * gw;
-      s[k] = fmaf(-(float)mean, a[k], gb);
+      if (g != gcur) { m = __ldg(mr + (long long)b * groups + g); gcur = g; }
+      a[k] = m.y * gw[k];
+      s[k] = fmaf(-m.x, a[k], gb[k]);
     }
   }
   float o[8];
@@ -306,7 +488,7 @@ gn_gelu_kernel(const void* __restrict__ raw, int raw_is_f32, const double* __res
     float v[8];
     load8(raw, raw_is_f32, (((long long)b * h + oy) * w + ox) * C + c8, v);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = gelu_erf(fmaf(v[k], a[k], s[k]));
+    for (int k = 0; k < 8; ++k) o[k] = gelu_fast(fmaf(v[k], a[k], s[k]));
   } else {
     // nn.UpsamplingBilinear2d(scale_factor=2): align_corners=True, src = dst * (in-1)/(out-1)
     const float fy = (oh > 1) ? (float)oy * ((float)(h - 1) / (float)(oh - 1)) : 0.f;
@@ -322,8 +504,8 @@ gn_gelu_kernel(const void* __restrict__ raw, int raw_is_f32, const double* __res
     load8(raw, raw_is_f32, (((long long)b * h + y1) * w + x1) * C + c8, v11);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      float g00 = gelu_erf(fmaf(v00[k], a[k], s[k])), g01 = gelu_erf(fmaf(v01[k], a[k], s[k]));
-      float g10 = gelu_erf(fmaf(v10[k], a[k], s[k])), g11 = gelu_erf(fmaf(v11[k], a[k], s[k]));
+      float g00 = gelu_fast(fmaf(v00[k], a[k], s[k])), g01 = gelu_fast(fmaf(v01[k], a[k], s[k]));
+      float g10 = gelu_fast(fmaf(v10[k], a[k], s[k])), g11 = gelu_fast(fmaf(v11[k], a[k], s[k]));
       o[k] = w00 * g00 + w01 * g01 + w10 * g10 + w11 * g11;
     }
   }
@@ -427,9 +609,43 @@ int launch_stem_patchify(const float* img, __nv_bfloat16* out, int B, int H, int
   return GDRN_OK;
 }
 
+template <int TW>
+static int launch_dwconv_cluster(const float* x, const float* w49c, const float* bias, const float* ln_w,
+                                 const float* ln_b, __nv_bfloat16* out, int B, int H, int W, int C, float eps,
+                                 cudaStream_t st) {
+  constexpr int CPC = (TW == 16) ? 64 : 128;
+  constexpr int IW = TW + 6;
+  constexpr int NPIX = TW * TW;
+  const size_t smem = (size_t)(IW * IW * CPC + (CPC / 32) * NPIX + 4 * NPIX) * sizeof(float);
+  auto kfn = dwconv_ln_cluster_kernel<TW>;
+  static bool configured = false;
+  if (!configured) {
+    GDRN_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(C / CPC, (H / TW) * (W / TW), B);
+  cfg.blockDim = dim3(512);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = C / CPC;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GDRN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kfn, x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps));
+  gdrn_count_launch(1);
+  return GDRN_OK;
+}
+
 int launch_dwconv_ln(const float* x, const float* w49c, const float* bias, const float* ln_w, const float* ln_b,
                      __nv_bfloat16* out, int B, int H, int W, int C, float eps, cudaStream_t st) {
   GDRN_REQUIRE(C % 128 == 0 && C <= 1024, "dwconv: C must be a multiple of 128 and <= 1024");
+  // cluster kernel: 16x16 tiles x 64 channels (cluster C/64 <= 8) or 8x8 tiles x 128 channels (cluster C/128 <= 8)
+  if (H % 16 == 0 && W % 16 == 0 && C / 64 <= 8) return launch_dwconv_cluster<16>(x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps, st);
+  if (H % 8 == 0 && W % 8 == 0 && C / 128 <= 8) return launch_dwconv_cluster<8>(x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps, st);
   const int S = 256 / (C / 4);
   if (W % 16 == 0) {
     long long strips = (long long)B * H * (W / 16);
@@ -473,14 +689,18 @@ int launch_bf16_to_f32(const __nv_bfloat16* src, float* dst, long long n, cudaSt
   return GDRN_OK;
 }
 
-int launch_gn_gelu(const void* raw, int raw_is_f32, const double* stats, const float* gn_w, const float* gn_b,
-                   __nv_bfloat16* out, int B, int h, int w, int C, int groups, float eps, int up, cudaStream_t st) {
+int launch_gn_gelu(const void* raw, int raw_is_f32, const double* stats, float* mean_rstd_scratch, const float* gn_w,
+                   const float* gn_b, __nv_bfloat16* out, int B, int h, int w, int C, int groups, float eps, int up,
+                   cudaStream_t st) {
   GDRN_REQUIRE(C % 8 == 0 && (up == 1 || up == 2), "gn_gelu: unsupported shape");
+  const int n_bg = B * groups;
+  gn_finalize_kernel<<<(n_bg + 127) / 128, 128, 0, st>>>(stats, reinterpret_cast<float2*>(mean_rstd_scratch), n_bg,
+                                                        (double)h * w * (C / groups), eps);
   long long total = (long long)B * h * up * w * up * (C / 8);
-  gn_gelu_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(raw, raw_is_f32, stats, gn_w, gn_b, out, B, h, w, C, groups,
-                                                            eps, up);
+  gn_gelu_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(raw, raw_is_f32, reinterpret_cast<const float2*>(mean_rstd_scratch),
+                                                            gn_w, gn_b, out, B, h, w, C, groups, up);
   GDRN_CHECK_CUDA(cudaGetLastError());
-  gdrn_count_launch(1);
+  gdrn_count_launch(2);
   return GDRN_OK;
 }
 

@@ -20,8 +20,11 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-constexpr int NUM_THREADS = 256;
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int NUM_THREADS = 384;              // 4 control warps + 8 epilogue warps
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int EPI_STAGE_PITCH = 272;          // 256-byte row segment + 16 B pad (conflict-free 16-byte accesses)
+constexpr int EPI_STAGE_BYTES = 32 * EPI_STAGE_PITCH + 256;  // per epilogue warp: 32 rows + 32 x int64 row map
+constexpr int SMEM_BUDGET = 225 * 1024 - NUM_EPI_WARPS * EPI_STAGE_BYTES - 1024 - 256;
 
 template <int BLOCK_N>
 struct Cfg {
@@ -30,7 +33,7 @@ struct Cfg {
   static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (SMEM_BUDGET / STAGE_BYTES);
   static constexpr int ACC_COLS = BLOCK_N <= 128 ? 128 : 256;  // TMEM columns per accumulator stage
   static constexpr int TMEM_COLS = 2 * ACC_COLS;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + NUM_EPI_WARPS * EPI_STAGE_BYTES;
 };
 
 struct RowInfo {
@@ -333,6 +336,175 @@ __device__ __forceinline__ void epilogue_tile(const GemmPlan& p, int m_tile, int
   }
 }
 
+
+// GELU with packed half2 math (mode 1): 0.5*(1+tanh.approx.f16x2(x*(c0+c1*x^2))) evaluated for two
+// elements per instruction, multiplied by the fp32 x.  ~5 instructions and 0.5 MUFU per element.
+__device__ __forceinline__ uint32_t gelu_pack2_f16(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const __half2 x2 = __hmul2(h, h);
+  const __half2 pl = __hfma2(x2, __float2half2_rn(0.0356774f), __float2half2_rn(0.7978846f));
+  const __half2 q = __hmul2(h, pl);
+  uint32_t qi = *reinterpret_cast<const uint32_t*>(&q), ti;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(qi));
+  const __half2 t = *reinterpret_cast<const __half2*>(&ti);
+  const __half2 phi = __hfma2(t, __float2half2_rn(0.5f), __float2half2_rn(0.5f));
+  const float2 pf = __half22float2(phi);
+  return pack_bf16(a * pf.x, b * pf.y);
+}
+
+// Epilogue for EPI_STORE / EPI_GELU / EPI_RESID / EPI_GNSTATS with coalesced global traffic.
+// Eight warps: warp ew owns TMEM lanes [32*(ew&3), +32) and the column half (ew>>2) of the tile.  A thread owns
+// one accumulator row; 256-byte row segments are staged in the warp's private shared-memory buffer
+// (pitch 272 B) and then written (and, for the residual, first read) with 16-byte accesses in which 16 lanes
+// cover one row segment: every warp-wide access touches two full 256-byte runs instead of 32 scattered sectors.
+template <int BLOCK_N, int EPI>
+__device__ __forceinline__ void epilogue_tile_staged(const GemmPlan& p, int m_tile, int n_tile, uint32_t tmem_acc,
+                                                     int ew, int lane, uint8_t* stg) {
+  static_assert(BLOCK_N >= 64, "staged epilogue needs BLOCK_N >= 64");
+  constexpr int CPW = BLOCK_N / 2;  // columns per warp
+  const int q = ew & 3, half = ew >> 2;
+  const int r = q * 32 + lane;
+  const RowInfo ri = map_row(p, m_tile, r);
+  long long* s_orow = reinterpret_cast<long long*>(stg + 32 * EPI_STAGE_PITCH);
+  s_orow[lane] = ri.valid ? ri.orow : -1;
+  __syncwarp();
+  const bool f32 = (EPI == EPI_RESID) || (EPI != EPI_GELU && p.out_f32 != 0);
+  const int esz = f32 ? 4 : 2;
+  const int unit_cols = (CPW * esz <= 256) ? CPW : 256 / esz;  // columns per 256-byte (or shorter) row segment
+  const int seg16 = unit_cols * esz / 16;                      // 16-byte pieces per row segment (4, 8 or 16)
+  const int rows_per_pass = 32 / seg16;
+  const int n0 = n_tile * BLOCK_N + half * CPW;
+  const uint32_t tmem_row = tmem_acc + ((uint32_t)(q * 32) << 16) + half * CPW;
+  uint8_t* my_row = stg + lane * EPI_STAGE_PITCH;
+  const int cpg = p.gn_cpg;
+
+#pragma unroll 1
+  for (int u = 0; u < CPW; u += unit_cols) {
+    const int ucol = n0 + u;
+    if (ucol >= p.N) break;  // warp-uniform (N is a multiple of the unit width for every caller)
+    if constexpr (EPI == EPI_RESID) {
+      // coalesced read of the residual segment rows into the staging buffer
+      for (int pass = 0; pass < 32; pass += rows_per_pass) {
+        const int rr = pass + lane / seg16, piece = lane % seg16;
+        const long long orow = s_orow[rr];
+        if (orow >= 0) {
+          const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.resid + orow * p.ldo + ucol) + piece * 16);
+          *reinterpret_cast<uint4*>(stg + rr * EPI_STAGE_PITCH + piece * 16) = v;
+        }
+      }
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int c = 0; c < unit_cols; c += 32) {
+      float v[32];
+      tmem_load_chunk<32>(tmem_row + u + c, v);
+      const int col = ucol + c;
+      if constexpr (EPI == EPI_STORE) {
+        float bias[32];
+        load_vec<32>(p.bias, col, p.N, bias);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += bias[j];
+      } else if constexpr (EPI == EPI_GELU) {
+        float bias[32];
+        load_vec<32>(p.bias, col, p.N, bias);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += bias[j];
+      } else if constexpr (EPI == EPI_RESID) {
+        float bias[32], g[32];
+        load_vec<32>(p.bias, col, p.N, bias);
+        load_vec<32>(p.gamma, col, p.N, g);
+        const float4* xr = reinterpret_cast<const float4*>(my_row + c * 4);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 x = xr[j >> 2];
+          v[j] = fmaf(g[j], v[j] + bias[j], x.x);
+          v[j + 1] = fmaf(g[j + 1], v[j + 1] + bias[j + 1], x.y);
+          v[j + 2] = fmaf(g[j + 2], v[j + 2] + bias[j + 2], x.z);
+          v[j + 3] = fmaf(g[j + 3], v[j + 3] + bias[j + 3], x.w);
+        }
+      }
+      // ---- registers -> staging row ----
+      if (f32) {
+        float4* dst = reinterpret_cast<float4*>(my_row + c * 4);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) dst[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+        uint4* dst = reinterpret_cast<uint4*>(my_row + c * 2);
+        if (EPI == EPI_GELU && p.gelu_mode == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 w;
+            w.x = gelu_pack2_f16(v[j], v[j + 1]); w.y = gelu_pack2_f16(v[j + 2], v[j + 3]);
+            w.z = gelu_pack2_f16(v[j + 4], v[j + 5]); w.w = gelu_pack2_f16(v[j + 6], v[j + 7]);
+            dst[j >> 3] = w;
+          }
+        } else {
+          if constexpr (EPI == EPI_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 w;
+            w.x = pack_bf16(v[j], v[j + 1]); w.y = pack_bf16(v[j + 2], v[j + 3]);
+            w.z = pack_bf16(v[j + 4], v[j + 5]); w.w = pack_bf16(v[j + 6], v[j + 7]);
+            dst[j >> 3] = w;
+          }
+        }
+      }
+      if constexpr (EPI == EPI_GNSTATS) {
+        // per-(image, group) sum / sum of squares of the values as stored
+        float s[8], ss[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) { s[g] = 0.f; ss[g] = 0.f; }
+        if (!f32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16(v[j]));
+        }
+        if (cpg == 8) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { s[j >> 3] += v[j]; ss[j >> 3] = fmaf(v[j], v[j], ss[j >> 3]); }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { s[j >> 2] += v[j]; ss[j >> 2] = fmaf(v[j], v[j], ss[j >> 2]); }
+        }
+        const int ng = 32 / cpg;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          if (g < ng) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              s[g] += __shfl_xor_sync(0xffffffffu, s[g], o);
+              ss[g] += __shfl_xor_sync(0xffffffffu, ss[g], o);
+            }
+          }
+        }
+        if (ri.valid) {  // warp-uniform: a warp's 32 rows lie in one image
+          double* st = p.gn_stats + ((long long)ri.b * p.gn_groups + col / cpg) * 2;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (g < ng && lane == g) {
+              atomicAdd(st + 2 * g, (double)s[g]);
+              atomicAdd(st + 2 * g + 1, (double)ss[g]);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // ---- coalesced flush of the 32 row segments ----
+    for (int pass = 0; pass < 32; pass += rows_per_pass) {
+      const int rr = pass + lane / seg16, piece = lane % seg16;
+      const long long orow = s_orow[rr];
+      if (orow >= 0) {
+        const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * EPI_STAGE_PITCH + piece * 16);
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + (orow * p.ldo + ucol) * esz + piece * 16) = v;
+      }
+    }
+    __syncwarp();
+  }
+}
+
 template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmPlan p) {
   using C = Cfg<BLOCK_N>;
@@ -351,6 +523,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // epilogues that need the whole row in one thread (LayerNorm, out-conv) or tiny N keep 4 warps + direct stores
+  constexpr bool kStaged = (BLOCK_N >= 64) && (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_RESID || EPI == EPI_GNSTATS);
+  uint8_t* stage_base = smem_gen + C::STAGES * C::STAGE_BYTES + 256;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.tmap_a);
@@ -363,7 +538,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(tfull_bar(s), 1);
-      ptx::mbar_init(tempty_bar(s), 4);
+      ptx::mbar_init(tempty_bar(s), kStaged ? NUM_EPI_WARPS : 4);
     }
     ptx::fence_barrier_init();
   }
@@ -449,9 +624,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       }
       ptx::tc_commit(tfull_bar(as));  // accumulator complete
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && (kStaged || warp < 8)) {
     // ================= epilogue =================
-    const int q = warp & 3;
+    const int ew = warp - 4;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int n_tile = tile % p.n_tiles;
@@ -460,8 +635,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       const uint32_t aphase = (it >> 1) & 1;
       ptx::mbar_wait(tfull_bar(as), aphase);
       ptx::tc_fence_after();
-      const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * C::ACC_COLS;
-      epilogue_tile<BLOCK_N, EPI>(p, m_tile, n_tile, tmem_row, lane);
+      if constexpr (kStaged) {
+        epilogue_tile_staged<BLOCK_N, EPI>(p, m_tile, n_tile, tmem_base + as * C::ACC_COLS, ew, lane,
+                                           stage_base + ew * EPI_STAGE_BYTES);
+      } else {
+        const uint32_t tmem_row = tmem_base + ((uint32_t)((ew & 3) * 32) << 16) + as * C::ACC_COLS;
+        epilogue_tile<BLOCK_N, EPI>(p, m_tile, n_tile, tmem_row, lane);
+      }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(as));

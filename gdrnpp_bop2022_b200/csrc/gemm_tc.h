@@ -45,6 +45,7 @@ struct GemmPlan {
   // ---- epilogue ----
   int epi;
   int out_f32;          // EPI_STORE / EPI_GNSTATS: 1 -> fp32 output, 0 -> bf16
+  int gelu_mode;        // EPI_GELU: 0 = fp32 ex2/rcp form (1.2e-5 of erf), 1 = packed half2 tanh.approx (faster, ~7e-4)
   void* out;            // [rows, ldo]
   long long ldo;        // output row stride (elements)
   int OH, OW, osy, osx, ooy, oox;  // rank 4/5: out row = (b*OH + y*osy+ooy)*OW + x*osx+oox

@@ -14,6 +14,7 @@
 #include <map>
 #include <string>
 #include <vector>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -59,6 +60,7 @@ struct GdrnModel {
   int num_classes;
   int max_batch;
   int in_res = 256, out_res = 64;
+  int gelu_mode = 0;  // GDRN_GELU_MODE=1 selects the packed-half2 tanh.approx GELU in the fc1 epilogues
   // ---- weights (device) ----
   std::vector<void*> allocs;
   __nv_bfloat16* stem_w;  // [C0][64]
@@ -264,6 +266,7 @@ struct Workspace {
   __nv_bfloat16 *f1, *f2;
   float* fout;      // [B][16]
   double* gn_stats; // [10][B][32][2]
+  float* gn_mr;     // [B][32][2] mean / rstd scratch of the layer being applied
   size_t total;
 };
 
@@ -297,6 +300,7 @@ Workspace carve(const GdrnModel* m, int B, void* base) {
   w.f2 = reinterpret_cast<__nv_bfloat16*>(take((size_t)B * 256 * 2));
   w.fout = reinterpret_cast<float*>(take((size_t)B * 16 * 4));
   w.gn_stats = reinterpret_cast<double*>(take((size_t)10 * B * 32 * 2 * 8));
+  w.gn_mr = reinterpret_cast<float*>(take((size_t)B * 32 * 2 * 4));
   w.total = off;
   return w;
 }
@@ -391,6 +395,7 @@ extern "C" int gdrn_model_create(GdrnModel** out, const char* arch, int num_clas
   m->arch = a;
   m->num_classes = num_classes;
   m->max_batch = max_batch;
+  if (const char* e = getenv("GDRN_GELU_MODE")) m->gelu_mode = atoi(e);
   if (!build_weights(m)) {
     gdrn_model_destroy(m);
     gdrn_set_last_error(__FILE__, __LINE__, "model_create: cudaMalloc failed");
@@ -511,7 +516,7 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
       reset();
       RC(plan_a2d(p, w.A, M, C));
       RC(plan_b(p, bw.fc1_w, 4 * C, C, 256, 4 * C));
-      p.epi = EPI_GELU; p.out = w.Hb; p.ldo = 4 * C; p.bias = bw.fc1_b;
+      p.epi = EPI_GELU; p.gelu_mode = m->gelu_mode; p.out = w.Hb; p.ldo = 4 * C; p.bias = bw.fc1_b;
       RCP(0, gemm_tc_launch(p, 256, st));
       reset();
       RC(plan_a2d(p, w.Hb, M, 4 * C));
@@ -547,7 +552,7 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
       p.gn_stats = stat_slot(0); p.gn_groups = 32; p.gn_cpg = 8;
       RCP(0, gemm_tc_launch(p, 256, st));
     }
-  RCP(2, launch_gn_gelu(w.R, 0, stat_slot(0), m->gn_w[0], m->gn_b[0], w.P, B, 16, 16, 256, 32, 1e-5f, 1, st));
+  RCP(2, launch_gn_gelu(w.R, 0, stat_slot(0), w.gn_mr, m->gn_w[0], m->gn_b[0], w.P, B, 16, 16, 256, 32, 1e-5f, 1, st));
   __nv_bfloat16* cur = w.P;
   __nv_bfloat16* nxt = w.Q;
   int hres = 16;
@@ -565,7 +570,7 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
       p.gn_stats = stat_slot(li + 1); p.gn_groups = 32; p.gn_cpg = 8;
       RCP(0, gemm_tc_launch(p, 256, st));
       const int up = (j == 1 && blk < 2) ? 2 : 1;
-      RCP(2, launch_gn_gelu(w.R, 0, stat_slot(li + 1), m->gn_w[li + 1], m->gn_b[li + 1], nxt, B, hres, hres, 256, 32, 1e-5f,
+      RCP(2, launch_gn_gelu(w.R, 0, stat_slot(li + 1), w.gn_mr, m->gn_w[li + 1], m->gn_b[li + 1], nxt, B, hres, hres, 256, 32, 1e-5f,
                         up, st));
       std::swap(cur, nxt);
       hres *= up;
@@ -614,7 +619,7 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
       p.OH = ores; p.OW = ores; p.osy = 1; p.osx = 1;
       p.gn_stats = stat_slot(7 + i); p.gn_groups = 32; p.gn_cpg = 4;
       RCP(0, gemm_tc_launch(p, 128, st));
-      RCP(2, launch_gn_gelu(w.pR, 0, stat_slot(7 + i), m->pgn_w[i], m->pgn_b[i], w.pP, B, ores, ores, 128, 32, 1e-5f, 1, st));
+      RCP(2, launch_gn_gelu(w.pR, 0, stat_slot(7 + i), w.gn_mr, m->pgn_w[i], m->pgn_b[i], w.pP, B, ores, ores, 128, 32, 1e-5f, 1, st));
       // ping-pong between pP and a second buffer is unnecessary: the conv reads pP (or pnp_in) and writes pR
       in = w.pP;
       ires = ores;

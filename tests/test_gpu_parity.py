@@ -100,7 +100,13 @@ def test_pose_lift_exact_given_head_output(dev):
     Rm = O.rot6d_to_mat_batch(raw[:, :6])
     ego, trans = O.pose_from_predictions_test(Rm, raw[:, 6:8], raw[:, 8:9], batch["roi_cams"], batch["roi_centers"],
                                               batch["resize_ratios"], batch["roi_whs"])
-    assert _rot_err(out["rot"].cpu(), ego).max().item() < 1e-4
+    # The reference's allo->ego step takes acos() of a float32 cosine (core/utils/utils.py:49-50): for a ROI at angle
+    # a from the optical axis, one float32 ulp in |t| moves the result by ~6e-8/sin(a) rad, and numpy's float32 norm
+    # (BLAS sdot) is itself platform dependent at that level -> tolerance 1e-4 + 4 ulp / sin(a).
+    t = trans.double()
+    sin_a = (t[:, :2].norm(dim=1) / t.norm(dim=1)).clamp_min(1e-6)
+    tol = 1e-4 + 4 * 6e-8 / sin_a
+    assert (_rot_err(out["rot"].cpu(), ego) < tol).all(), (_rot_err(out["rot"].cpu(), ego), tol)
     assert (out["trans"].cpu() - trans).abs().max().item() < 1e-6
 
 
@@ -314,13 +320,16 @@ def test_nnd_vs_reference_cuda_build(dev):
 def _flow_inputs(B, H, W, seed):
     rs = np.random.RandomState(seed)
     K = np.array([[572.4, 0, W / 2 - 3.5], [0, 573.6, H / 2 + 2.1], [0, 0, 1]], np.float32)
-    depth_src = (0.6 + 0.2 * rs.rand(B, 1, H, W)).astype(np.float32)
-    depth_src[:, :, : H // 8] = 0  # invalid depth
+    yy, xx = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+    smooth = (0.7 + 0.02 * np.sin(xx / 40.0) + 0.02 * np.cos(yy / 30.0)).astype(np.float32)
+    depth_src = np.tile(smooth[None, None], (B, 1, 1, 1)).copy()
+    depth_src[:, :, : max(1, H // 8)] = 0  # invalid depth rows
     T = np.tile(np.eye(4, dtype=np.float32)[:3][None], (B, 1, 1))
-    T[:, :, 3] = rs.randn(B, 3) * 0.01
+    T[:, :, 3] = rs.randn(B, 3) * 0.0007  # sub-pixel .. ~1 px of image motion
     KT = (K[None] @ T).astype(np.float32)
     Kinv = np.tile(np.linalg.inv(K)[None], (B, 1, 1)).astype(np.float32)
-    depth_tgt = (depth_src + T[:, 2, 3][:, None, None, None] + (rs.rand(B, 1, H, W) < 0.3) * 0.01).astype(np.float32)
+    depth_tgt = (np.tile(smooth[None, None], (B, 1, 1, 1)) + T[:, 2, 3][:, None, None, None]
+                 + (rs.rand(B, 1, H, W) < 0.3) * 0.01).astype(np.float32)  # 30 % of the target pixels are occluders
     return depth_src, depth_tgt, KT, Kinv
 
 
@@ -333,7 +342,7 @@ def test_flow_bit_exact(dev, B, H, W):
     ofl, ova = OO.flow(ds, dt, KT, Kinv)
     assert np.array_equal(va.cpu().numpy(), ova)
     assert np.array_equal(fl.cpu().numpy().view(np.uint32), ofl.view(np.uint32))
-    assert 0.05 < ova.mean() < 0.99  # the case exercises both branches
+    assert 0.2 < ova.mean() < 0.9  # the case exercises both branches
     ref = load_ref_ext("flow_cuda")
     if ref is not None:
         rfl, rva = ref.forward(*(torch.from_numpy(x).to(dev) for x in (ds, dt, KT, Kinv)))
