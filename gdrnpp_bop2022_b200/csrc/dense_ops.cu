@@ -7,6 +7,7 @@
 
 #include "common.cuh"
 #include "dense_ops.h"
+#include "gemm_tc.h"
 
 namespace cg = cooperative_groups;
 
@@ -220,7 +221,7 @@ __device__ __forceinline__ float lane_transpose_reduce(float (&a)[N], int lane) 
 
 template <int TW>
 __global__ void __launch_bounds__(512, 1)
-dwconv_ln_cluster_kernel(const float* __restrict__ x, const float* __restrict__ w49c, const float* __restrict__ bias,
+dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ w49c, const float* __restrict__ bias,
                          const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                          __nv_bfloat16* __restrict__ out, int B, int H, int W, int C, float eps) {
   constexpr int CPC = (TW == 16) ? 64 : 128;  // channels per CTA
@@ -248,23 +249,22 @@ dwconv_ln_cluster_kernel(const float* __restrict__ x, const float* __restrict__ 
   const int rp = tid / CPC;                   // row pair: output rows 2rp, 2rp+1
   const int wc = (tid >> 5) % WPR;
 
-  // ---- stage the zero-padded input tile ----
-  {
-    constexpr int Q = CPC / 4;
-    const float* xb = x + (long long)b * H * W * C + c0;
-    for (int i = tid; i < IW * IW * Q; i += 512) {
-      const int q = i % Q, pix = i / Q;
-      const int iy = pix / IW, ix = pix % IW;
-      const int gy = y0 + iy - 3, gx = x0 + ix - 3;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = *reinterpret_cast<const float4*>(xb + ((long long)gy * W + gx) * C + q * 4);
-      *reinterpret_cast<float4*>(tile + pix * CPC + q * 4) = v;
-    }
+  // ---- stage the zero-padded input tile: ONE TMA box load (CPC x IW x IW x 1 fp32), halo = out-of-bounds zero fill ----
+  __shared__ __align__(8) unsigned long long tma_bar;
+  const uint32_t bar = ptx::smem_u32(&tma_bar);
+  if (tid == 0) {
+    ptx::mbar_init(bar, 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    ptx::mbar_arrive_expect_tx(bar, (uint32_t)(IW * IW * CPC * sizeof(float)));
+    ptx::tma_load_4d(ptx::smem_u32(tile), &tmap_x, bar, c0, x0 - 3, y0 - 3, b);
   }
   float wreg[49];
 #pragma unroll
   for (int t = 0; t < 49; ++t) wreg[t] = __ldg(w49c + t * C + c0 + c_local);
-  __syncthreads();
+  ptx::mbar_wait(bar, 0);
 
   // ---- convolution: 2 output rows x TW pixels for one channel ----
   float acc[NP];
@@ -457,14 +457,15 @@ gn_gelu_kernel(const void* __restrict__ raw, int raw_is_f32, const float2* __res
                int h, int w, int C, int groups, int up) {
   const int cv = C >> 3;
   const int oh = h * up, ow = w * up;
-  const long long total = (long long)B * oh * ow * cv;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned total = (unsigned)B * oh * ow * cv;  // < 2^31 (checked by the launcher): 32-bit index math
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int c8 = (int)(idx % cv) * 8;
-  const long long p = idx / cv;
-  const int ox = (int)(p % ow);
-  const int oy = (int)((p / ow) % oh);
-  const int b = (int)(p / ((long long)ow * oh));
+  const int c8 = (int)(idx % (unsigned)cv) * 8;
+  const unsigned p = idx / (unsigned)cv;
+  const int ox = (int)(p % (unsigned)ow);
+  const unsigned prow = p / (unsigned)ow;
+  const int oy = (int)(prow % (unsigned)oh);
+  const int b = (int)(prow / (unsigned)oh);
   const int cpg = C / groups;
   // per-channel scale/shift: y = v * a + s
   float a[8], s[8];
@@ -623,6 +624,14 @@ static int launch_dwconv_cluster(const float* x, const float* w49c, const float*
     GDRN_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
+  CUtensorMap tmap;
+  {
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)C * 4, (uint64_t)W * C * 4, (uint64_t)H * W * C * 4};
+    const uint32_t box[4] = {(uint32_t)CPC, (uint32_t)IW, (uint32_t)IW, 1};
+    int rc = make_tmap_f32_plain(&tmap, x, 4, dims, str, box);
+    if (rc != GDRN_OK) return rc;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(C / CPC, (H / TW) * (W / TW), B);
   cfg.blockDim = dim3(512);
@@ -635,7 +644,7 @@ static int launch_dwconv_cluster(const float* x, const float* w49c, const float*
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  GDRN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kfn, x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps));
+  GDRN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kfn, tmap, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps));
   gdrn_count_launch(1);
   return GDRN_OK;
 }
@@ -697,6 +706,7 @@ int launch_gn_gelu(const void* raw, int raw_is_f32, const double* stats, float* 
   gn_finalize_kernel<<<(n_bg + 127) / 128, 128, 0, st>>>(stats, reinterpret_cast<float2*>(mean_rstd_scratch), n_bg,
                                                         (double)h * w * (C / groups), eps);
   long long total = (long long)B * h * up * w * up * (C / 8);
+  GDRN_REQUIRE(total < (1LL << 31), "gn_gelu: tensor too large for 32-bit indexing");
   gn_gelu_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(raw, raw_is_f32, reinterpret_cast<const float2*>(mean_rstd_scratch),
                                                             gn_w, gn_b, out, B, h, w, C, groups, up);
   GDRN_CHECK_CUDA(cudaGetLastError());

@@ -17,9 +17,10 @@ flow_kernel(const float* __restrict__ depth_src, const float* __restrict__ depth
   const long long total = hw * batch;
   for (long long index = (long long)blockIdx.x * blockDim.x + threadIdx.x; index < total;
        index += (long long)gridDim.x * blockDim.x) {
-    const int w = (int)(index % width);
-    const int h = (int)((index / width) % height);
     const int b = (int)(index / hw);
+    const unsigned rem = (unsigned)(index - (long long)b * hw);  // < H*W: 32-bit division below
+    const int h = (int)(rem / (unsigned)width);
+    const int w = (int)(rem - (unsigned)h * (unsigned)width);
     const float d = depth_src[index];
     float f0 = 0.f, f1 = 0.f, ok = 0.f;
     if ((double)d > 1E-3) {

@@ -69,5 +69,8 @@ struct GemmPlan {
 int gemm_tc_launch(const GemmPlan& plan, int block_n, cudaStream_t stream);
 
 // tensor-map builders (bf16). dims/strides innermost first; strides in BYTES for dims 1..rank-1.
+// fp32, no swizzle, zero OOB fill (dense [..][box0] shared-memory image)
+int make_tmap_f32_plain(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                        const uint64_t* strides_bytes, const uint32_t* box);
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box);

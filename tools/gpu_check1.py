@@ -142,8 +142,7 @@ def model_check():
     for k in ("mask", "full_mask", "coor_x", "coor_y", "coor_z", "region"):
         res[k + "_maxabs"] = float((out[k].cpu() - ref[k]).abs().max())
     R, Rr = out["rot"].cpu().double(), ref["rot"].double()
-    cosang = ((torch.einsum("bij,bij->b", R, Rr) - 1) / 2).clamp(-1, 1)
-    res["rot_err_rad_max"] = float(torch.acos(cosang).max())
+    res["rot_err_rad_max"] = float((2 * torch.asin(((R - Rr).flatten(1).norm(dim=1) / (2 * 2 ** 0.5)).clamp(max=1.0))).max())
     res["trans_maxabs"] = float((out["trans"].cpu() - ref["trans"]).abs().max())
     return res
 
