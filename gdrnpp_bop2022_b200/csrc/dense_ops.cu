@@ -229,13 +229,14 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const float
   constexpr int NPIX = TW * TW;
   constexpr int NP = 2 * TW;                  // pixels per thread
   constexpr int WPR = CPC / 32;               // channel-warps per row pair
-  extern __shared__ float smem_dw[];
+  extern __shared__ __align__(1024) float smem_dw[];   // TMA destination: 128-byte aligned (no static smem before it)
   float* tile = smem_dw;                      // [IW][IW][CPC]
   float* s_part = tile + IW * IW * CPC;       // [WPR][NPIX]
   float* s_cta1 = s_part + WPR * NPIX;        // [NPIX] this CTA's channel-slice sums (read by the cluster)
   float* s_cta2 = s_cta1 + NPIX;              // [NPIX] centred sums of squares
   float* s_mean = s_cta2 + NPIX;              // [NPIX]
   float* s_rstd = s_mean + NPIX;              // [NPIX]
+  unsigned long long* tma_bar_p = reinterpret_cast<unsigned long long*>(s_rstd + NPIX);  // 8-byte aligned tail
 
   cg::cluster_group cluster = cg::this_cluster();
   const int nrank = (int)cluster.num_blocks();
@@ -250,8 +251,7 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const float
   const int wc = (tid >> 5) % WPR;
 
   // ---- stage the zero-padded input tile: ONE TMA box load (CPC x IW x IW x 1 fp32), halo = out-of-bounds zero fill ----
-  __shared__ __align__(8) unsigned long long tma_bar;
-  const uint32_t bar = ptx::smem_u32(&tma_bar);
+  const uint32_t bar = ptx::smem_u32(tma_bar_p);
   if (tid == 0) {
     ptx::mbar_init(bar, 1);
     ptx::fence_barrier_init();
@@ -617,7 +617,7 @@ static int launch_dwconv_cluster(const float* x, const float* w49c, const float*
   constexpr int CPC = (TW == 16) ? 64 : 128;
   constexpr int IW = TW + 6;
   constexpr int NPIX = TW * TW;
-  const size_t smem = (size_t)(IW * IW * CPC + (CPC / 32) * NPIX + 4 * NPIX) * sizeof(float);
+  const size_t smem = (size_t)(IW * IW * CPC + (CPC / 32) * NPIX + 4 * NPIX) * sizeof(float) + 16;
   auto kfn = dwconv_ln_cluster_kernel<TW>;
   static bool configured = false;
   if (!configured) {
