@@ -191,18 +191,37 @@ dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ w49c, co
 
 
 // ------------------------------------------------------------------------------------------------
-// depthwise 7x7 + bias + LayerNorm(C), thread-block-cluster version (the one the forward uses).
-//   CTA  = one TWxTW output tile of one image x CPC channels (64 for TW=16, 128 for TW=8); the zero-padded
-//          (TW+6)^2 x CPC fp32 input tile lives in shared memory (124 KB / 100 KB).
-//   thread = ONE channel x (2 rows x TW pixels): its 49 filter taps stay in registers, every input row it
-//          loads from smem feeds two output rows (>= 9 FMA per LDS -> FP32-FMA bound, not LSU bound).
-//   cluster = the C/CPC CTAs (2/4/8) that together hold all channels of the tile: the LayerNorm mean and
-//          centred variance are reduced across them through distributed shared memory (two exchanges).
-// In-warp per-pixel channel sums use a transposing shuffle reduction (31 shuffles for 32 values).
+// depthwise 7x7 + bias + LayerNorm(C), thread-block-cluster + packed-FP32 version (the one the forward uses).
+//   CTA  = one TWxTW output tile of one image x CPC channels (64 for TW=16, 128 for TW=8).  The zero-padded
+//          (TW+6)^2 x CPC fp32 input tile is fetched by ONE TMA box load (halo = out-of-bounds zero fill).
+//   thread = a PAIR of adjacent channels x one output row (TW pixels).  All arithmetic is fma.rn.f32x2
+//          (SASS FFMA2: two FMAs per issued instruction, the Blackwell packed-FP32 path); the input pairs
+//          and the filter pairs are 8-byte shared-memory loads, conflict-free with lanes = channel pairs.
+//   cluster = the C/CPC CTAs (2/4/8) that together hold all channels of the tile: LayerNorm mean and centred
+//          variance are reduced across them through distributed shared memory (two exchanges).
+// In-warp per-pixel channel sums use a transposing shuffle reduction.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 f2_unpack(f32x2_t v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+// sum over the 32 lanes of N per-lane values, N in {32,16,8}: lane L ends up with element (L * N) >> 5
 template <int N>
 __device__ __forceinline__ float lane_transpose_reduce(float (&a)[N], int lane) {
-  static_assert(N == 32 || N == 16, "N");
-  constexpr int STEPS = (N == 32) ? 5 : 4;
+  static_assert(N == 32 || N == 16 || N == 8, "N");
+  constexpr int STEPS = (N == 32) ? 5 : (N == 16 ? 4 : 3);
 #pragma unroll
   for (int st = 0; st < STEPS; ++st) {
     const int o = 16 >> st;        // lane bit
@@ -215,28 +234,32 @@ __device__ __forceinline__ float lane_transpose_reduce(float (&a)[N], int lane) 
       a[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
     }
   }
-  if (N == 16) a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
-  return a[0];  // N == 32: lane L holds element L;  N == 16: lane L holds element L >> 1
+#pragma unroll
+  for (int o = (16 >> STEPS); o > 0; o >>= 1) a[0] += __shfl_xor_sync(0xffffffffu, a[0], o);
+  return a[0];
 }
 
 template <int TW>
 __global__ void __launch_bounds__(512, 1)
-dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ w49c, const float* __restrict__ bias,
-                         const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                         __nv_bfloat16* __restrict__ out, int B, int H, int W, int C, float eps) {
+dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ w49c,
+                         const float* __restrict__ bias, const float* __restrict__ ln_w,
+                         const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out, int B, int H, int W, int C,
+                         float eps) {
   constexpr int CPC = (TW == 16) ? 64 : 128;  // channels per CTA
+  constexpr int PAIRS = CPC / 2;              // channel pairs = threads per output row
   constexpr int IW = TW + 6;
   constexpr int NPIX = TW * TW;
-  constexpr int NP = 2 * TW;                  // pixels per thread
-  constexpr int WPR = CPC / 32;               // channel-warps per row pair
-  extern __shared__ __align__(1024) float smem_dw[];   // TMA destination: 128-byte aligned (no static smem before it)
+  constexpr int WPR = PAIRS / 32;             // warps per output row
+  constexpr int LPP = 32 / TW;                // lanes per pixel after the transposing reduction (2 or 4)
+  extern __shared__ __align__(1024) float smem_dw[];   // TMA destination first: 128-byte aligned
   float* tile = smem_dw;                      // [IW][IW][CPC]
-  float* s_part = tile + IW * IW * CPC;       // [WPR][NPIX]
+  float* wsm = tile + IW * IW * CPC;          // [49][CPC]
+  float* s_part = wsm + 49 * CPC;             // [WPR][NPIX]
   float* s_cta1 = s_part + WPR * NPIX;        // [NPIX] this CTA's channel-slice sums (read by the cluster)
   float* s_cta2 = s_cta1 + NPIX;              // [NPIX] centred sums of squares
   float* s_mean = s_cta2 + NPIX;              // [NPIX]
   float* s_rstd = s_mean + NPIX;              // [NPIX]
-  unsigned long long* tma_bar_p = reinterpret_cast<unsigned long long*>(s_rstd + NPIX);  // 8-byte aligned tail
+  unsigned long long* tma_bar_p = reinterpret_cast<unsigned long long*>(s_rstd + NPIX);
 
   cg::cluster_group cluster = cg::this_cluster();
   const int nrank = (int)cluster.num_blocks();
@@ -246,11 +269,11 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const float
   const int y0 = (blockIdx.y / tiles_x) * TW;
   const int b = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31;
-  const int c_local = tid % CPC;
-  const int rp = tid / CPC;                   // row pair: output rows 2rp, 2rp+1
+  const int pair = tid % PAIRS;
+  const int row = tid / PAIRS;                // output row of the tile
   const int wc = (tid >> 5) % WPR;
+  const int cl = 2 * pair;                    // first channel of the pair (CTA-local)
 
-  // ---- stage the zero-padded input tile: ONE TMA box load (CPC x IW x IW x 1 fp32), halo = out-of-bounds zero fill ----
   const uint32_t bar = ptx::smem_u32(tma_bar_p);
   if (tid == 0) {
     ptx::mbar_init(bar, 1);
@@ -261,44 +284,42 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const float
     ptx::mbar_arrive_expect_tx(bar, (uint32_t)(IW * IW * CPC * sizeof(float)));
     ptx::tma_load_4d(ptx::smem_u32(tile), &tmap_x, bar, c0, x0 - 3, y0 - 3, b);
   }
-  float wreg[49];
-#pragma unroll
-  for (int t = 0; t < 49; ++t) wreg[t] = __ldg(w49c + t * C + c0 + c_local);
-  ptx::mbar_wait(bar, 0);
-
-  // ---- convolution: 2 output rows x TW pixels for one channel ----
-  float acc[NP];
+  for (int i = tid; i < 49 * CPC; i += 512) wsm[i] = __ldg(w49c + (i / CPC) * C + c0 + (i % CPC));
+  f32x2_t acc[TW];
   {
-    const float bv = __ldg(bias + c0 + c_local);
+    const f32x2_t bv = f2_pack(__ldg(bias + c0 + cl), __ldg(bias + c0 + cl + 1));
 #pragma unroll
-    for (int i = 0; i < NP; ++i) acc[i] = bv;
+    for (int i = 0; i < TW; ++i) acc[i] = bv;
   }
+  __syncthreads();           // filter taps staged
+  ptx::mbar_wait(bar, 0);    // input tile landed
+
+  // ---- convolution: one output row x TW pixels for a channel pair, 7 input rows ----
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    float v[IW];
-    const float* rowp = tile + ((2 * rp + r) * IW) * CPC + c_local;
+  for (int ky = 0; ky < 7; ++ky) {
+    f32x2_t v[IW], wk[7];
+    const float* rowp = tile + ((row + ky) * IW) * CPC + cl;
 #pragma unroll
-    for (int j = 0; j < IW; ++j) v[j] = rowp[j * CPC];
+    for (int j = 0; j < IW; ++j) v[j] = *reinterpret_cast<const f32x2_t*>(rowp + j * CPC);
 #pragma unroll
-    for (int oy = 0; oy < 2; ++oy) {
-      const int ky = r - oy;
-      if (ky >= 0 && ky < 7) {
+    for (int kx = 0; kx < 7; ++kx) wk[kx] = *reinterpret_cast<const f32x2_t*>(wsm + (ky * 7 + kx) * CPC + cl);
 #pragma unroll
-        for (int kx = 0; kx < 7; ++kx)
+    for (int kx = 0; kx < 7; ++kx)
 #pragma unroll
-          for (int ox = 0; ox < TW; ++ox) acc[oy * TW + ox] = fmaf(v[ox + kx], wreg[ky * 7 + kx], acc[oy * TW + ox]);
-      }
-    }
+      for (int ox = 0; ox < TW; ++ox) acc[ox] = f2_fma(v[ox + kx], wk[kx], acc[ox]);
   }
+  float ax[TW], ay[TW];
+#pragma unroll
+  for (int i = 0; i < TW; ++i) { const float2 t = f2_unpack(acc[i]); ax[i] = t.x; ay[i] = t.y; }
 
   // ---- LayerNorm pass 1: mean over all C channels of each pixel ----
-  const int my_slot = rp * NP + ((NP == 32) ? lane : (lane >> 1));
+  const int my_slot = row * TW + lane / LPP;
   {
-    float a[NP];
+    float a[TW];
 #pragma unroll
-    for (int i = 0; i < NP; ++i) a[i] = acc[i];
-    const float s = lane_transpose_reduce<NP>(a, lane);
-    if (NP == 32 || (lane & 1) == 0) s_part[wc * NPIX + my_slot] = s;
+    for (int i = 0; i < TW; ++i) a[i] = ax[i] + ay[i];
+    const float s = lane_transpose_reduce<TW>(a, lane);
+    if ((lane % LPP) == 0) s_part[wc * NPIX + my_slot] = s;
   }
   __syncthreads();
   if (tid < NPIX) {
@@ -315,15 +336,18 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const float
   }
   __syncthreads();
   // ---- pass 2: centred variance ----
-  float mean_r[NP];
+  float mean_r[TW];
 #pragma unroll
-  for (int i = 0; i < NP; ++i) mean_r[i] = s_mean[rp * NP + i];
+  for (int i = 0; i < TW; ++i) mean_r[i] = s_mean[row * TW + i];
   {
-    float a[NP];
+    float a[TW];
 #pragma unroll
-    for (int i = 0; i < NP; ++i) { const float d = acc[i] - mean_r[i]; a[i] = d * d; }
-    const float s = lane_transpose_reduce<NP>(a, lane);
-    if (NP == 32 || (lane & 1) == 0) s_part[wc * NPIX + my_slot] = s;
+    for (int i = 0; i < TW; ++i) {
+      const float dx = ax[i] - mean_r[i], dy = ay[i] - mean_r[i];
+      a[i] = fmaf(dx, dx, dy * dy);
+    }
+    const float s = lane_transpose_reduce<TW>(a, lane);
+    if ((lane % LPP) == 0) s_part[wc * NPIX + my_slot] = s;
   }
   __syncthreads();
   if (tid < NPIX) {
@@ -339,18 +363,16 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const float
     s_rstd[tid] = rsqrtf(s / (float)C + eps);
   }
   __syncthreads();
-  // ---- normalise + affine, bf16 out ----
-  const float gw = __ldg(ln_w + c0 + c_local), gb = __ldg(ln_b + c0 + c_local);
+  // ---- normalise + affine, bf16x2 out (a warp writes 128 contiguous bytes per pixel) ----
+  const float gw0 = __ldg(ln_w + c0 + cl), gw1 = __ldg(ln_w + c0 + cl + 1);
+  const float gb0 = __ldg(ln_b + c0 + cl), gb1 = __ldg(ln_b + c0 + cl + 1);
+  __nv_bfloat16* orow = out + (((long long)b * H + (y0 + row)) * W + x0) * C + c0 + cl;
 #pragma unroll
-  for (int oy = 0; oy < 2; ++oy) {
-    const int gy = y0 + 2 * rp + oy;
-    __nv_bfloat16* orow = out + (((long long)b * H + gy) * W + x0) * C + c0 + c_local;
-#pragma unroll
-    for (int ox = 0; ox < TW; ++ox) {
-      const int i = oy * TW + ox;
-      const float r = s_rstd[rp * NP + i];
-      orow[(long long)ox * C] = __float2bfloat16(fmaf((acc[i] - mean_r[i]) * r, gw, gb));
-    }
+  for (int ox = 0; ox < TW; ++ox) {
+    const float r = s_rstd[row * TW + ox];
+    const __nv_bfloat162 o = __floats2bfloat162_rn(fmaf((ax[ox] - mean_r[ox]) * r, gw0, gb0),
+                                                   fmaf((ay[ox] - mean_r[ox]) * r, gw1, gb1));
+    *reinterpret_cast<__nv_bfloat162*>(orow + (long long)ox * C) = o;
   }
   cluster.sync();  // nobody leaves while a peer may still read its shared memory
 }
@@ -617,7 +639,7 @@ static int launch_dwconv_cluster(const float* x, const float* w49c, const float*
   constexpr int CPC = (TW == 16) ? 64 : 128;
   constexpr int IW = TW + 6;
   constexpr int NPIX = TW * TW;
-  const size_t smem = (size_t)(IW * IW * CPC + (CPC / 32) * NPIX + 4 * NPIX) * sizeof(float) + 16;
+  const size_t smem = (size_t)(IW * IW * CPC + 49 * CPC + (CPC / 64) * NPIX + 4 * NPIX) * sizeof(float) + 16;
   auto kfn = dwconv_ln_cluster_kernel<TW>;
   static bool configured = false;
   if (!configured) {

@@ -22,9 +22,9 @@ constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int NUM_THREADS = 384;              // 4 control warps + 8 epilogue warps
 constexpr int NUM_EPI_WARPS = 8;
-constexpr int EPI_STAGE_PITCH = 272;          // 256-byte row segment + 16 B pad (conflict-free 16-byte accesses)
+constexpr int EPI_STAGE_PITCH = 80;           // 64-byte row segment + 16 B pad (conflict-free 16-byte accesses)
 constexpr int EPI_STAGE_BYTES = 32 * EPI_STAGE_PITCH + 256;  // per epilogue warp: 32 rows + 32 x int64 row map
-constexpr int SMEM_BUDGET = 225 * 1024 - NUM_EPI_WARPS * EPI_STAGE_BYTES - 1024 - 256;
+constexpr int SMEM_BUDGET = 227 * 1024 - NUM_EPI_WARPS * EPI_STAGE_BYTES - 1024 - 256;
 
 template <int BLOCK_N>
 struct Cfg {
@@ -66,6 +66,8 @@ __device__ __forceinline__ RowInfo map_row(const GemmPlan& p, int m_tile, int r)
   }
   return ri;
 }
+
+constexpr int PREFETCH_AHEAD = 6;  // k-iterations of A/B requested into L2 ahead of the shared-memory ring
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
@@ -352,156 +354,178 @@ __device__ __forceinline__ uint32_t gelu_pack2_f16(float a, float b) {
   return pack_bf16(a * pf.x, b * pf.y);
 }
 
+// GELU mode 2: fp32 tanh form with the hardware tanh.approx.f32 (1 MUFU / element):
+// 0.5*x*(1 + tanh(x*(c0 + c1*x^2 + c2*x^4))) with (c0,c1,c2) fitted to the erf form (tools/fit_gelu.py).
+__device__ __forceinline__ float gelu_tanh_f32(float x) {
+  const float xc = fminf(fmaxf(x, -8.f), 8.f);  // the fitted polynomial changes sign beyond |x| ~ 11
+  const float x2 = xc * xc;
+  float p = fmaf(x2, GELU_T2, GELU_T1);
+  p = fmaf(p, x2, GELU_T0);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(xc * p));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
+
 // Epilogue for EPI_STORE / EPI_GELU / EPI_RESID / EPI_GNSTATS with coalesced global traffic.
 // Eight warps: warp ew owns TMEM lanes [32*(ew&3), +32) and the column half (ew>>2) of the tile.  A thread owns
-// one accumulator row; 256-byte row segments are staged in the warp's private shared-memory buffer
-// (pitch 272 B) and then written (and, for the residual, first read) with 16-byte accesses in which 16 lanes
-// cover one row segment: every warp-wide access touches two full 256-byte runs instead of 32 scattered sectors.
-template <int BLOCK_N, int EPI>
-__device__ __forceinline__ void epilogue_tile_staged(const GemmPlan& p, int m_tile, int n_tile, uint32_t tmem_acc,
-                                                     int ew, int lane, uint8_t* stg) {
+// one accumulator row; 64-byte row segments (32 bf16 or 16 fp32 columns) are staged in the warp's private
+// shared-memory buffer (pitch 80 B, conflict-free 16-byte accesses) and then written (and, for the residual,
+// first read) with 16-byte accesses in which 4 lanes cover one row segment: every warp-wide access touches
+// eight full 64-byte runs (16 whole sectors) instead of 32 scattered 16-byte pieces.
+template <int BLOCK_N, int EPI, bool F32>
+__device__ __forceinline__ void epilogue_tile_staged_t(const GemmPlan& p, int m_tile, int n_tile, uint32_t tmem_acc,
+                                                       int ew, int lane, uint8_t* stg) {
   static_assert(BLOCK_N >= 64, "staged epilogue needs BLOCK_N >= 64");
-  constexpr int CPW = BLOCK_N / 2;  // columns per warp
+  constexpr int CPW = BLOCK_N / 2;      // columns per warp
+  constexpr int CH = F32 ? 16 : 32;     // columns per staged row segment (64 bytes)
+  constexpr int ESZ = F32 ? 4 : 2;
   const int q = ew & 3, half = ew >> 2;
   const int r = q * 32 + lane;
   const RowInfo ri = map_row(p, m_tile, r);
   long long* s_orow = reinterpret_cast<long long*>(stg + 32 * EPI_STAGE_PITCH);
   s_orow[lane] = ri.valid ? ri.orow : -1;
   __syncwarp();
-  const bool f32 = (EPI == EPI_RESID) || (EPI != EPI_GELU && p.out_f32 != 0);
-  const int esz = f32 ? 4 : 2;
-  const int unit_cols = (CPW * esz <= 256) ? CPW : 256 / esz;  // columns per 256-byte (or shorter) row segment
-  const int seg16 = unit_cols * esz / 16;                      // 16-byte pieces per row segment (4, 8 or 16)
-  const int rows_per_pass = 32 / seg16;
   const int n0 = n_tile * BLOCK_N + half * CPW;
   const uint32_t tmem_row = tmem_acc + ((uint32_t)(q * 32) << 16) + half * CPW;
   uint8_t* my_row = stg + lane * EPI_STAGE_PITCH;
   const int cpg = p.gn_cpg;
+  const int fl_row = lane >> 2, fl_piece = lane & 3;  // flush / prefetch mapping: 8 rows x 4 pieces per pass
 
 #pragma unroll 1
-  for (int u = 0; u < CPW; u += unit_cols) {
-    const int ucol = n0 + u;
-    if (ucol >= p.N) break;  // warp-uniform (N is a multiple of the unit width for every caller)
+  for (int c = 0; c < CPW; c += CH) {
+    const int col = n0 + c;
+    if (col >= p.N) break;  // warp-uniform
     if constexpr (EPI == EPI_RESID) {
       // coalesced read of the residual segment rows into the staging buffer
-      for (int pass = 0; pass < 32; pass += rows_per_pass) {
-        const int rr = pass + lane / seg16, piece = lane % seg16;
+#pragma unroll
+      for (int pass = 0; pass < 32; pass += 8) {
+        const int rr = pass + fl_row;
         const long long orow = s_orow[rr];
-        if (orow >= 0) {
-          const uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.resid + orow * p.ldo + ucol) + piece * 16);
-          *reinterpret_cast<uint4*>(stg + rr * EPI_STAGE_PITCH + piece * 16) = v;
-        }
+        if (orow >= 0)
+          *reinterpret_cast<uint4*>(stg + rr * EPI_STAGE_PITCH + fl_piece * 16) =
+              *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.resid + orow * p.ldo + col) + fl_piece * 16);
       }
       __syncwarp();
     }
-#pragma unroll 1
-    for (int c = 0; c < unit_cols; c += 32) {
-      float v[32];
-      tmem_load_chunk<32>(tmem_row + u + c, v);
-      const int col = ucol + c;
-      if constexpr (EPI == EPI_STORE) {
-        float bias[32];
-        load_vec<32>(p.bias, col, p.N, bias);
+    float v[CH];
+    tmem_load_chunk<CH>(tmem_row + c, v);
+    if constexpr (EPI == EPI_STORE || EPI == EPI_GELU) {
+      float bias[CH];
+      load_vec<CH>(p.bias, col, p.N, bias);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += bias[j];
-      } else if constexpr (EPI == EPI_GELU) {
-        float bias[32];
-        load_vec<32>(p.bias, col, p.N, bias);
+      for (int j = 0; j < CH; ++j) v[j] += bias[j];
+    } else if constexpr (EPI == EPI_RESID) {
+      float bias[CH], g[CH];
+      load_vec<CH>(p.bias, col, p.N, bias);
+      load_vec<CH>(p.gamma, col, p.N, g);
+      const float4* xr = reinterpret_cast<const float4*>(my_row);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += bias[j];
-      } else if constexpr (EPI == EPI_RESID) {
-        float bias[32], g[32];
-        load_vec<32>(p.bias, col, p.N, bias);
-        load_vec<32>(p.gamma, col, p.N, g);
-        const float4* xr = reinterpret_cast<const float4*>(my_row + c * 4);
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 x = xr[j >> 2];
-          v[j] = fmaf(g[j], v[j] + bias[j], x.x);
-          v[j + 1] = fmaf(g[j + 1], v[j + 1] + bias[j + 1], x.y);
-          v[j + 2] = fmaf(g[j + 2], v[j + 2] + bias[j + 2], x.z);
-          v[j + 3] = fmaf(g[j + 3], v[j + 3] + bias[j + 3], x.w);
-        }
+      for (int j = 0; j < CH; j += 4) {
+        const float4 x = xr[j >> 2];
+        v[j] = fmaf(g[j], v[j] + bias[j], x.x);
+        v[j + 1] = fmaf(g[j + 1], v[j + 1] + bias[j + 1], x.y);
+        v[j + 2] = fmaf(g[j + 2], v[j + 2] + bias[j + 2], x.z);
+        v[j + 3] = fmaf(g[j + 3], v[j + 3] + bias[j + 3], x.w);
       }
-      // ---- registers -> staging row ----
-      if (f32) {
-        float4* dst = reinterpret_cast<float4*>(my_row + c * 4);
+    }
+    // ---- registers -> staging row ----
+    if constexpr (F32) {
+      float4* dst = reinterpret_cast<float4*>(my_row);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) dst[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      for (int j = 0; j < CH; j += 4) dst[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+      uint4* dst = reinterpret_cast<uint4*>(my_row);
+      if (EPI == EPI_GELU && p.gelu_mode == 1) {
+#pragma unroll
+        for (int j = 0; j < CH; j += 8) {
+          uint4 w;
+          w.x = gelu_pack2_f16(v[j], v[j + 1]); w.y = gelu_pack2_f16(v[j + 2], v[j + 3]);
+          w.z = gelu_pack2_f16(v[j + 4], v[j + 5]); w.w = gelu_pack2_f16(v[j + 6], v[j + 7]);
+          dst[j >> 3] = w;
+        }
       } else {
-        uint4* dst = reinterpret_cast<uint4*>(my_row + c * 2);
-        if (EPI == EPI_GELU && p.gelu_mode == 1) {
+        if constexpr (EPI == EPI_GELU) {
+          if (p.gelu_mode == 2) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 w;
-            w.x = gelu_pack2_f16(v[j], v[j + 1]); w.y = gelu_pack2_f16(v[j + 2], v[j + 3]);
-            w.z = gelu_pack2_f16(v[j + 4], v[j + 5]); w.w = gelu_pack2_f16(v[j + 6], v[j + 7]);
-            dst[j >> 3] = w;
+            for (int j = 0; j < CH; ++j) v[j] = gelu_tanh_f32(v[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) v[j] = gelu_fast(v[j]);
           }
-        } else {
-          if constexpr (EPI == EPI_GELU) {
+        }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
-          }
+        for (int j = 0; j < CH; j += 8) {
+          uint4 w;
+          w.x = pack_bf16(v[j], v[j + 1]); w.y = pack_bf16(v[j + 2], v[j + 3]);
+          w.z = pack_bf16(v[j + 4], v[j + 5]); w.w = pack_bf16(v[j + 6], v[j + 7]);
+          dst[j >> 3] = w;
+        }
+      }
+    }
+    if constexpr (EPI == EPI_GNSTATS) {
+      // per-(image, group) sum / sum of squares of the values as stored
+      constexpr int NG_MAX = CH / 4;
+      float s[NG_MAX], ss[NG_MAX];
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 w;
-            w.x = pack_bf16(v[j], v[j + 1]); w.y = pack_bf16(v[j + 2], v[j + 3]);
-            w.z = pack_bf16(v[j + 4], v[j + 5]); w.w = pack_bf16(v[j + 6], v[j + 7]);
-            dst[j >> 3] = w;
+      for (int g = 0; g < NG_MAX; ++g) { s[g] = 0.f; ss[g] = 0.f; }
+      if (!F32) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] = __bfloat162float(__float2bfloat16(v[j]));
+      }
+      if (cpg == 8) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) { s[j >> 3] += v[j]; ss[j >> 3] = fmaf(v[j], v[j], ss[j >> 3]); }
+      } else {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) { s[j >> 2] += v[j]; ss[j >> 2] = fmaf(v[j], v[j], ss[j >> 2]); }
+      }
+      const int ng = CH / cpg;
+#pragma unroll
+      for (int g = 0; g < NG_MAX; ++g) {
+        if (g < ng) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            s[g] += __shfl_xor_sync(0xffffffffu, s[g], o);
+            ss[g] += __shfl_xor_sync(0xffffffffu, ss[g], o);
           }
         }
       }
-      if constexpr (EPI == EPI_GNSTATS) {
-        // per-(image, group) sum / sum of squares of the values as stored
-        float s[8], ss[8];
+      if (ri.valid) {  // warp-uniform: a warp's 32 rows lie in one image
+        double* st = p.gn_stats + ((long long)ri.b * p.gn_groups + col / cpg) * 2;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) { s[g] = 0.f; ss[g] = 0.f; }
-        if (!f32) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16(v[j]));
-        }
-        if (cpg == 8) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { s[j >> 3] += v[j]; ss[j >> 3] = fmaf(v[j], v[j], ss[j >> 3]); }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { s[j >> 2] += v[j]; ss[j >> 2] = fmaf(v[j], v[j], ss[j >> 2]); }
-        }
-        const int ng = 32 / cpg;
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          if (g < ng) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              s[g] += __shfl_xor_sync(0xffffffffu, s[g], o);
-              ss[g] += __shfl_xor_sync(0xffffffffu, ss[g], o);
-            }
-          }
-        }
-        if (ri.valid) {  // warp-uniform: a warp's 32 rows lie in one image
-          double* st = p.gn_stats + ((long long)ri.b * p.gn_groups + col / cpg) * 2;
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            if (g < ng && lane == g) {
-              atomicAdd(st + 2 * g, (double)s[g]);
-              atomicAdd(st + 2 * g + 1, (double)ss[g]);
-            }
+        for (int g = 0; g < NG_MAX; ++g) {
+          if (g < ng && lane == g) {
+            atomicAdd(st + 2 * g, (double)s[g]);
+            atomicAdd(st + 2 * g + 1, (double)ss[g]);
           }
         }
       }
     }
     __syncwarp();
     // ---- coalesced flush of the 32 row segments ----
-    for (int pass = 0; pass < 32; pass += rows_per_pass) {
-      const int rr = pass + lane / seg16, piece = lane % seg16;
+#pragma unroll
+    for (int pass = 0; pass < 32; pass += 8) {
+      const int rr = pass + fl_row;
       const long long orow = s_orow[rr];
-      if (orow >= 0) {
-        const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * EPI_STAGE_PITCH + piece * 16);
-        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + (orow * p.ldo + ucol) * esz + piece * 16) = v;
-      }
+      if (orow >= 0)
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + (orow * p.ldo + col) * ESZ + fl_piece * 16) =
+            *reinterpret_cast<const uint4*>(stg + rr * EPI_STAGE_PITCH + fl_piece * 16);
     }
     __syncwarp();
+  }
+}
+
+template <int BLOCK_N, int EPI>
+__device__ __forceinline__ void epilogue_tile_staged(const GemmPlan& p, int m_tile, int n_tile, uint32_t tmem_acc,
+                                                     int ew, int lane, uint8_t* stg) {
+  if constexpr (EPI == EPI_RESID) {
+    epilogue_tile_staged_t<BLOCK_N, EPI, true>(p, m_tile, n_tile, tmem_acc, ew, lane, stg);
+  } else if constexpr (EPI == EPI_GELU) {
+    epilogue_tile_staged_t<BLOCK_N, EPI, false>(p, m_tile, n_tile, tmem_acc, ew, lane, stg);
+  } else {
+    if (p.out_f32) epilogue_tile_staged_t<BLOCK_N, EPI, true>(p, m_tile, n_tile, tmem_acc, ew, lane, stg);
+    else epilogue_tile_staged_t<BLOCK_N, EPI, false>(p, m_tile, n_tile, tmem_acc, ew, lane, stg);
   }
 }
 
@@ -585,6 +609,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           const int k0 = kc * BLOCK_K;
           if (p.a_rank == 2) {
             ptx::tma_load_2d(sa, &p.tmap_a, full_bar(stage), k0, m_tile * BLOCK_M);
+            // A is streamed from HBM (it was written by the previous kernel): request it into L2 several
+            // k-iterations ahead so the shared-memory ring only has to cover L2 latency, not DRAM latency.
+            int pk = kc + PREFETCH_AHEAD, pm = m_tile;
+            if (pk >= p.k_chunks) {
+              pk -= p.k_chunks;
+              const int nt = tile + gridDim.x;
+              pm = (nt < total_tiles && (nt / p.n_tiles) != m_tile) ? nt / p.n_tiles : -1;
+            }
+            if (pm >= 0 && pk < p.k_chunks) ptx::tma_prefetch_2d(&p.tmap_a, pk * BLOCK_K, pm * BLOCK_M);
           } else if (p.a_rank == 4) {
             ptx::tma_load_4d(sa, &p.tmap_a, full_bar(stage), k0 + tp.c0, x0 + tp.d1, y0 + tp.d2, b0);
           } else {
