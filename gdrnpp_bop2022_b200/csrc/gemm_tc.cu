@@ -391,20 +391,34 @@ __device__ __forceinline__ void epilogue_tile_staged_t(const GemmPlan& p, int m_
   uint8_t* my_row = stg + lane * EPI_STAGE_PITCH;
   const int cpg = p.gn_cpg;
   const int fl_row = lane >> 2, fl_piece = lane & 3;  // flush / prefetch mapping: 8 rows x 4 pieces per pass
+  uint4 rres[4];
+  if constexpr (EPI == EPI_RESID) {
+    if (n0 < p.N) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const long long orow = s_orow[k * 8 + fl_row];
+        rres[k] = (orow >= 0) ? *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.resid + orow * p.ldo + n0) + fl_piece * 16)
+                              : make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
 
 #pragma unroll 1
   for (int c = 0; c < CPW; c += CH) {
     const int col = n0 + c;
     if (col >= p.N) break;  // warp-uniform
     if constexpr (EPI == EPI_RESID) {
-      // coalesced read of the residual segment rows into the staging buffer
+      // residual segment rows: registers (fetched one chunk ahead, see below) -> staging buffer
 #pragma unroll
-      for (int pass = 0; pass < 32; pass += 8) {
-        const int rr = pass + fl_row;
-        const long long orow = s_orow[rr];
-        if (orow >= 0)
-          *reinterpret_cast<uint4*>(stg + rr * EPI_STAGE_PITCH + fl_piece * 16) =
-              *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.resid + orow * p.ldo + col) + fl_piece * 16);
+      for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(stg + (k * 8 + fl_row) * EPI_STAGE_PITCH + fl_piece * 16) = rres[k];
+      // issue the coalesced loads of the NEXT chunk now; they complete while this chunk is processed
+      if (c + CH < CPW && col + CH < p.N) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const long long orow = s_orow[k * 8 + fl_row];
+          rres[k] = (orow >= 0) ? *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.resid + orow * p.ldo + col + CH) + fl_piece * 16)
+                                : make_uint4(0, 0, 0, 0);
+        }
       }
       __syncwarp();
     }
@@ -666,6 +680,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       const int m_tile = tile / p.n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      if constexpr (kStaged && EPI == EPI_RESID) {
+        // the residual rows of this tile are not produced by the MMAs: pull them into L2 while the mainloop runs
+        const RowInfo pri = map_row(p, m_tile, (ew & 3) * 32 + lane);
+        if (pri.valid) {
+          const float* rp = p.resid + pri.orow * p.ldo + n_tile * BLOCK_N + (ew >> 2) * (BLOCK_N / 2);
+#pragma unroll
+          for (int b = 0; b < (BLOCK_N / 2) * 4; b += 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(rp) + b));
+        }
+      }
       ptx::mbar_wait(tfull_bar(as), aphase);
       ptx::tc_fence_after();
       if constexpr (kStaged) {

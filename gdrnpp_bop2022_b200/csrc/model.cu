@@ -60,7 +60,7 @@ struct GdrnModel {
   int num_classes;
   int max_batch;
   int in_res = 256, out_res = 64;
-  int gelu_mode = 0;  // GDRN_GELU_MODE=1 selects the packed-half2 tanh.approx GELU in the fc1 epilogues
+  int gelu_mode = 1;  // fc1 epilogue GELU: 1 = packed-half2 tanh.approx (default, fastest), 0 = fp32 ex2/rcp form, 2 = fp32 tanh.approx; env GDRN_GELU_MODE
   // ---- weights (device) ----
   std::vector<void*> allocs;
   __nv_bfloat16* stem_w;  // [C0][64]

@@ -49,6 +49,27 @@ def test_gemm_vs_torch(dev, lib, M, N, K, bn, epi, f32):
     assert err < (2e-4 if is_f32 else 0.04), err
 
 
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_gemm_gelu_modes(dev, lib, mode, monkeypatch):
+    """The three epilogue GELU evaluations (fp32 ex2/rcp, packed half2 tanh.approx, fp32 tanh.approx) vs erf-GELU."""
+    L = _lib()
+    monkeypatch.setenv("GDRN_GELU_MODE", str(mode))
+    g = torch.Generator().manual_seed(mode)
+    M, N, K = 512, 512, 256
+    A = (torch.randn(M, K, generator=g)).to(dev).bfloat16()
+    W = (torch.randn(N, K, generator=g) * (3.0 / np.sqrt(K))).to(dev).bfloat16()   # pre-activations up to ~ +-12
+    bias = torch.randn(N, generator=g).to(dev)
+    pre = A.float() @ W.float().t() + bias
+    ref = torch.nn.functional.gelu(pre)
+    out = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+    L.check(lib.gdrn_gemm_bf16(L.ptr(A), L.ptr(W), L.ptr(bias), None, None, L.ptr(out), M, N, K, 1, 0, 256,
+                               L.current_stream()), "gemm")
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs()
+    tol = 2.0 ** -8 * ref.abs().clamp_min(1.0) + (0.0 if mode == 0 else 6e-4 * pre.abs().clamp_min(1.0))
+    assert (err <= tol).all(), float((err - tol).max())
+
+
 # ----------------------------------------------------------------------------------------------- model
 def _run_model(dev, B, seed, with_maps=True):
     from gdrnpp_bop2022_b200.gdrn_model import GDRN_DoubleMask, default_cfg
