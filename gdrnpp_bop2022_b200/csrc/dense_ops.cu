@@ -192,8 +192,9 @@ dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ w49c, co
 
 // ------------------------------------------------------------------------------------------------
 // depthwise 7x7 + bias + LayerNorm(C), thread-block-cluster + packed-FP32 version (the one the forward uses).
-//   CTA  = one TWxTW output tile of one image x CPC channels (64 for TW=16, 128 for TW=8).  The zero-padded
-//          (TW+6)^2 x CPC fp32 input tile is fetched by ONE TMA box load (halo = out-of-bounds zero fill).
+//   CTA  = one TW x TH output tile of one image x CPC channels (16x8 x 64 ch, two CTAs per SM so that one CTA's tile
+//          load overlaps the other's arithmetic; 8x8 x 128 ch for 8x8 images).  The zero-padded (TW+6)x(TH+6) x CPC
+//          fp32 input tile is fetched by ONE TMA box load (halo = out-of-bounds zero fill).
 //   thread = a PAIR of adjacent channels x one output row (TW pixels).  All arithmetic is fma.rn.f32x2
 //          (SASS FFMA2: two FMAs per issued instruction, the Blackwell packed-FP32 path); the input pairs
 //          and the filter pairs are 8-byte shared-memory loads, conflict-free with lanes = channel pairs.
@@ -239,8 +240,8 @@ __device__ __forceinline__ float lane_transpose_reduce(float (&a)[N], int lane) 
   return a[0];
 }
 
-template <int TW>
-__global__ void __launch_bounds__(512, 1)
+template <int TW, int TH>
+__global__ void __launch_bounds__(((TW == 16) ? 32 : 64) * TH, (TW == 16) ? 2 : 1)
 dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ w49c,
                          const float* __restrict__ bias, const float* __restrict__ ln_w,
                          const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out, int B, int H, int W, int C,
@@ -248,12 +249,14 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const float
   constexpr int CPC = (TW == 16) ? 64 : 128;  // channels per CTA
   constexpr int PAIRS = CPC / 2;              // channel pairs = threads per output row
   constexpr int IW = TW + 6;
-  constexpr int NPIX = TW * TW;
+  constexpr int IH = TH + 6;
+  constexpr int NPIX = TW * TH;
+  constexpr int NTHREADS = PAIRS * TH;
   constexpr int WPR = PAIRS / 32;             // warps per output row
   constexpr int LPP = 32 / TW;                // lanes per pixel after the transposing reduction (2 or 4)
   extern __shared__ __align__(1024) float smem_dw[];   // TMA destination first: 128-byte aligned
-  float* tile = smem_dw;                      // [IW][IW][CPC]
-  float* wsm = tile + IW * IW * CPC;          // [49][CPC]
+  float* tile = smem_dw;                      // [IH][IW][CPC]
+  float* wsm = tile + IH * IW * CPC;          // [49][CPC]
   float* s_part = wsm + 49 * CPC;             // [WPR][NPIX]
   float* s_cta1 = s_part + WPR * NPIX;        // [NPIX] this CTA's channel-slice sums (read by the cluster)
   float* s_cta2 = s_cta1 + NPIX;              // [NPIX] centred sums of squares
@@ -266,7 +269,7 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const float
   const int c0 = blockIdx.x * CPC;
   const int tiles_x = W / TW;
   const int x0 = (blockIdx.y % tiles_x) * TW;
-  const int y0 = (blockIdx.y / tiles_x) * TW;
+  const int y0 = (blockIdx.y / tiles_x) * TH;
   const int b = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31;
   const int pair = tid % PAIRS;
@@ -281,10 +284,10 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const float
   }
   __syncthreads();
   if (tid == 0) {
-    ptx::mbar_arrive_expect_tx(bar, (uint32_t)(IW * IW * CPC * sizeof(float)));
+    ptx::mbar_arrive_expect_tx(bar, (uint32_t)(IH * IW * CPC * sizeof(float)));
     ptx::tma_load_4d(ptx::smem_u32(tile), &tmap_x, bar, c0, x0 - 3, y0 - 3, b);
   }
-  for (int i = tid; i < 49 * CPC; i += 512) wsm[i] = __ldg(w49c + (i / CPC) * C + c0 + (i % CPC));
+  for (int i = tid; i < 49 * CPC; i += NTHREADS) wsm[i] = __ldg(w49c + (i / CPC) * C + c0 + (i % CPC));
   f32x2_t acc[TW];
   {
     const f32x2_t bv = f2_pack(__ldg(bias + c0 + cl), __ldg(bias + c0 + cl + 1));
@@ -632,15 +635,16 @@ int launch_stem_patchify(const float* img, __nv_bfloat16* out, int B, int H, int
   return GDRN_OK;
 }
 
-template <int TW>
+template <int TW, int TH>
 static int launch_dwconv_cluster(const float* x, const float* w49c, const float* bias, const float* ln_w,
                                  const float* ln_b, __nv_bfloat16* out, int B, int H, int W, int C, float eps,
                                  cudaStream_t st) {
   constexpr int CPC = (TW == 16) ? 64 : 128;
-  constexpr int IW = TW + 6;
-  constexpr int NPIX = TW * TW;
-  const size_t smem = (size_t)(IW * IW * CPC + 49 * CPC + (CPC / 64) * NPIX + 4 * NPIX) * sizeof(float) + 16;
-  auto kfn = dwconv_ln_cluster_kernel<TW>;
+  constexpr int IW = TW + 6, IH = TH + 6;
+  constexpr int NPIX = TW * TH;
+  constexpr int NTHREADS = (CPC / 2) * TH;
+  const size_t smem = (size_t)(IH * IW * CPC + 49 * CPC + (CPC / 64) * NPIX + 4 * NPIX) * sizeof(float) + 16;
+  auto kfn = dwconv_ln_cluster_kernel<TW, TH>;
   static bool configured = false;
   if (!configured) {
     GDRN_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -650,13 +654,13 @@ static int launch_dwconv_cluster(const float* x, const float* w49c, const float*
   {
     const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     const uint64_t str[3] = {(uint64_t)C * 4, (uint64_t)W * C * 4, (uint64_t)H * W * C * 4};
-    const uint32_t box[4] = {(uint32_t)CPC, (uint32_t)IW, (uint32_t)IW, 1};
+    const uint32_t box[4] = {(uint32_t)CPC, (uint32_t)IW, (uint32_t)IH, 1};
     int rc = make_tmap_f32_plain(&tmap, x, 4, dims, str, box);
     if (rc != GDRN_OK) return rc;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(C / CPC, (H / TW) * (W / TW), B);
-  cfg.blockDim = dim3(512);
+  cfg.gridDim = dim3(C / CPC, (H / TH) * (W / TW), B);
+  cfg.blockDim = dim3(NTHREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -674,9 +678,9 @@ static int launch_dwconv_cluster(const float* x, const float* w49c, const float*
 int launch_dwconv_ln(const float* x, const float* w49c, const float* bias, const float* ln_w, const float* ln_b,
                      __nv_bfloat16* out, int B, int H, int W, int C, float eps, cudaStream_t st) {
   GDRN_REQUIRE(C % 128 == 0 && C <= 1024, "dwconv: C must be a multiple of 128 and <= 1024");
-  // cluster kernel: 16x16 tiles x 64 channels (cluster C/64 <= 8) or 8x8 tiles x 128 channels (cluster C/128 <= 8)
-  if (H % 16 == 0 && W % 16 == 0 && C / 64 <= 8) return launch_dwconv_cluster<16>(x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps, st);
-  if (H % 8 == 0 && W % 8 == 0 && C / 128 <= 8) return launch_dwconv_cluster<8>(x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps, st);
+  // cluster kernel: 16x8 tiles x 64 channels (cluster C/64 <= 8) or 8x8 tiles x 128 channels (cluster C/128 <= 8)
+  if (H % 8 == 0 && W % 16 == 0 && C / 64 <= 8) return launch_dwconv_cluster<16, 8>(x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps, st);
+  if (H % 8 == 0 && W % 8 == 0 && C / 128 <= 8) return launch_dwconv_cluster<8, 8>(x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps, st);
   const int S = 256 / (C / 4);
   if (W % 16 == 0) {
     long long strips = (long long)B * H * (W / 16);
