@@ -198,8 +198,8 @@ dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ w49c, co
 //   thread = a PAIR of adjacent channels x one output row (TW pixels).  All arithmetic is fma.rn.f32x2
 //          (SASS FFMA2: two FMAs per issued instruction, the Blackwell packed-FP32 path); the input pairs
 //          and the filter pairs are 8-byte shared-memory loads, conflict-free with lanes = channel pairs.
-//   cluster = the C/CPC CTAs (2/4/8) that together hold all channels of the tile: LayerNorm mean and centred
-//          variance are reduced across them through distributed shared memory (two exchanges).
+//   cluster = the C/CPC CTAs (2/4/8) that together hold all channels of the tile: the LayerNorm statistics are
+//          combined across them through distributed shared memory with ONE cluster barrier (see below).
 // In-warp per-pixel channel sums use a transposing shuffle reduction.
 typedef unsigned long long f32x2_t;
 __device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) {
@@ -257,12 +257,8 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const float
   extern __shared__ __align__(1024) float smem_dw[];   // TMA destination first: 128-byte aligned
   float* tile = smem_dw;                      // [IH][IW][CPC]
   float* wsm = tile + IH * IW * CPC;          // [49][CPC]
-  float* s_part = wsm + 49 * CPC;             // [WPR][NPIX]
-  float* s_cta1 = s_part + WPR * NPIX;        // [NPIX] this CTA's channel-slice sums (read by the cluster)
-  float* s_cta2 = s_cta1 + NPIX;              // [NPIX] centred sums of squares
-  float* s_mean = s_cta2 + NPIX;              // [NPIX]
-  float* s_rstd = s_mean + NPIX;              // [NPIX]
-  unsigned long long* tma_bar_p = reinterpret_cast<unsigned long long*>(s_rstd + NPIX);
+  float2* s_parts = reinterpret_cast<float2*>(wsm + 49 * CPC);  // [8 ranks * WPR][NPIX] (sum, M2) partials, pushed by peers
+  unsigned long long* tma_bar_p = reinterpret_cast<unsigned long long*>(s_parts + 8 * WPR * NPIX);
 
   cg::cluster_group cluster = cg::this_cluster();
   const int nrank = (int)cluster.num_blocks();
@@ -274,7 +270,7 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const float
   const int tid = threadIdx.x, lane = tid & 31;
   const int pair = tid % PAIRS;
   const int row = tid / PAIRS;                // output row of the tile
-  const int wc = (tid >> 5) % WPR;
+  const int wc = (tid >> 5) % WPR;            // which 64-channel group of the CTA this warp holds
   const int cl = 2 * pair;                    // first channel of the pair (CTA-local)
 
   const uint32_t bar = ptx::smem_u32(tma_bar_p);
@@ -315,69 +311,60 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const float
 #pragma unroll
   for (int i = 0; i < TW; ++i) { const float2 t = f2_unpack(acc[i]); ax[i] = t.x; ay[i] = t.y; }
 
-  // ---- LayerNorm pass 1: mean over all C channels of each pixel ----
-  const int my_slot = row * TW + lane / LPP;
+  // ---- LayerNorm over all C channels of each pixel ----
+  // A warp holds 64 channels of its row's TW pixels: it computes (sum, M2 about its own mean) per pixel with
+  // shuffles only, PUSHES that partial into every CTA of the cluster (distributed shared memory stores), and after
+  // ONE cluster barrier each warp combines the C/64 partials with Chan's parallel-variance formula.  No block-level
+  // barrier, no remote loads, and nothing remote is touched after the barrier (so no exit barrier is needed).
+  constexpr float INV_W = 1.0f / 64.0f;  // channels per warp = 64
+  const int pix = row * TW + lane / LPP;
+  float s_loc, m2_loc;
   {
     float a[TW];
 #pragma unroll
     for (int i = 0; i < TW; ++i) a[i] = ax[i] + ay[i];
-    const float s = lane_transpose_reduce<TW>(a, lane);
-    if ((lane % LPP) == 0) s_part[wc * NPIX + my_slot] = s;
-  }
-  __syncthreads();
-  if (tid < NPIX) {
-    float s = 0.f;
-#pragma unroll
-    for (int k = 0; k < WPR; ++k) s += s_part[k * NPIX + tid];
-    s_cta1[tid] = s;
-  }
-  cluster.sync();
-  if (tid < NPIX) {
-    float s = 0.f;
-    for (int rk = 0; rk < nrank; ++rk) s += cluster.map_shared_rank(s_cta1, rk)[tid];
-    s_mean[tid] = s / (float)C;
-  }
-  __syncthreads();
-  // ---- pass 2: centred variance ----
-  float mean_r[TW];
-#pragma unroll
-  for (int i = 0; i < TW; ++i) mean_r[i] = s_mean[row * TW + i];
-  {
-    float a[TW];
+    s_loc = lane_transpose_reduce<TW>(a, lane);           // lane L: pixel L / LPP of this row
 #pragma unroll
     for (int i = 0; i < TW; ++i) {
-      const float dx = ax[i] - mean_r[i], dy = ay[i] - mean_r[i];
+      const float m = __shfl_sync(0xffffffffu, s_loc, i * LPP) * INV_W;
+      const float dx = ax[i] - m, dy = ay[i] - m;
       a[i] = fmaf(dx, dx, dy * dy);
     }
-    const float s = lane_transpose_reduce<TW>(a, lane);
-    if ((lane % LPP) == 0) s_part[wc * NPIX + my_slot] = s;
+    m2_loc = lane_transpose_reduce<TW>(a, lane);
   }
-  __syncthreads();
-  if (tid < NPIX) {
-    float s = 0.f;
-#pragma unroll
-    for (int k = 0; k < WPR; ++k) s += s_part[k * NPIX + tid];
-    s_cta2[tid] = s;
+  const int nparts = nrank * WPR;
+  {
+    const int part = (int)cluster.block_rank() * WPR + wc;
+    if ((lane % LPP) == 0) {
+      const float2 v = make_float2(s_loc, m2_loc);
+      for (int rk = 0; rk < nrank; ++rk) cluster.map_shared_rank(s_parts, rk)[part * NPIX + pix] = v;
+    }
   }
   cluster.sync();
-  if (tid < NPIX) {
-    float s = 0.f;
-    for (int rk = 0; rk < nrank; ++rk) s += cluster.map_shared_rank(s_cta2, rk)[tid];
-    s_rstd[tid] = rsqrtf(s / (float)C + eps);
+  float mean_p, rstd_p;
+  {
+    float tot = 0.f;
+    for (int k = 0; k < nparts; ++k) tot += s_parts[k * NPIX + pix].x;
+    mean_p = tot / (float)C;
+    float m2 = 0.f;
+    for (int k = 0; k < nparts; ++k) {
+      const float2 v = s_parts[k * NPIX + pix];
+      const float d = v.x * INV_W - mean_p;
+      m2 += fmaf(64.0f * d, d, v.y);
+    }
+    rstd_p = rsqrtf(m2 / (float)C + eps);
   }
-  __syncthreads();
   // ---- normalise + affine, bf16x2 out (a warp writes 128 contiguous bytes per pixel) ----
   const float gw0 = __ldg(ln_w + c0 + cl), gw1 = __ldg(ln_w + c0 + cl + 1);
   const float gb0 = __ldg(ln_b + c0 + cl), gb1 = __ldg(ln_b + c0 + cl + 1);
   __nv_bfloat16* orow = out + (((long long)b * H + (y0 + row)) * W + x0) * C + c0 + cl;
 #pragma unroll
   for (int ox = 0; ox < TW; ++ox) {
-    const float r = s_rstd[row * TW + ox];
-    const __nv_bfloat162 o = __floats2bfloat162_rn(fmaf((ax[ox] - mean_r[ox]) * r, gw0, gb0),
-                                                   fmaf((ay[ox] - mean_r[ox]) * r, gw1, gb1));
+    const float m = __shfl_sync(0xffffffffu, mean_p, ox * LPP);
+    const float r = __shfl_sync(0xffffffffu, rstd_p, ox * LPP);
+    const __nv_bfloat162 o = __floats2bfloat162_rn(fmaf((ax[ox] - m) * r, gw0, gb0), fmaf((ay[ox] - m) * r, gw1, gb1));
     *reinterpret_cast<__nv_bfloat162*>(orow + (long long)ox * C) = o;
   }
-  cluster.sync();  // nobody leaves while a peer may still read its shared memory
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -643,7 +630,7 @@ static int launch_dwconv_cluster(const float* x, const float* w49c, const float*
   constexpr int IW = TW + 6, IH = TH + 6;
   constexpr int NPIX = TW * TH;
   constexpr int NTHREADS = (CPC / 2) * TH;
-  const size_t smem = (size_t)(IH * IW * CPC + 49 * CPC + (CPC / 64) * NPIX + 4 * NPIX) * sizeof(float) + 16;
+  const size_t smem = (size_t)(IH * IW * CPC + 49 * CPC + 2 * 8 * (CPC / 64) * NPIX) * sizeof(float) + 16;
   auto kfn = dwconv_ln_cluster_kernel<TW, TH>;
   static bool configured = false;
   if (!configured) {
