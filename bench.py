@@ -212,6 +212,26 @@ def main():
     for i in range(args.warmup):
         fwd(resident[i % NB])
     torch.cuda.synchronize()
+    # one CUDA graph per static input buffer: a step = one graph launch (~150 kernels)
+    use_graphs = os.environ.get("GDRN_BENCH_GRAPHS", "1") != "0"
+    graphs = {}
+
+    def graphed(b):
+        if not use_graphs:
+            return fwd(b)
+        key = b["roi_img"].data_ptr()
+        if key not in graphs:
+            graphs[key] = model.capture_graph({"roi_img": b["roi_img"], "roi_classes": b["roi_classes"],
+                                               "roi_coord_2d": b["roi_coord_2d"], "roi_cams": b["roi_cams"],
+                                               "roi_centers": b["roi_centers"], "roi_whs": b["roi_whs"],
+                                               "roi_extents": b["roi_extents"], "resize_ratios": b["resize_ratios"]})
+        replay, out = graphs[key]
+        replay()
+        return out
+
+    for i in range(NB):
+        graphed(resident[i])
+    torch.cuda.synchronize()
 
     # ---------------- device-resident timing (value) ----------------
     # nvidia-smi needs ~0.3 s to deliver its first sample: start it while the (untimed) load is already running
@@ -228,15 +248,19 @@ def main():
     e0.record()
     rots, transes = [], []
     for i in range(args.steps):
-        o = fwd(resident[i % NB])
-        rots.append(o["rot"])
-        transes.append(o["trans"])
+        o = graphed(resident[i % NB])
+        rots.append(o["rot"].clone() if use_graphs else o["rot"])
+        transes.append(o["trans"].clone() if use_graphs else o["trans"])
     if world > 1:
         all_gather_poses(torch.cat(rots), torch.cat(transes))
     e1.record()
     barrier()
     clocks = sampler.stop()
     launches = L.gdrn_launch_count() - launches0
+    if use_graphs:  # graph replays do not pass through the launch counter: count the kernels of one captured forward
+        c0_ = L.gdrn_launch_count()
+        fwd(resident[0])
+        launches = (L.gdrn_launch_count() - c0_) * args.steps
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     value = world * BATCH * args.steps / (ms_total / 1e3)
 
@@ -271,7 +295,7 @@ def main():
             if i + 1 < nsteps:
                 upload(i + 1)
             comp_stream.wait_event(ready[sl])
-            o = fwd(stagings[sl])
+            o = graphed(stagings[sl])
             consumed[sl].record(comp_stream)
             rot_hosts[sl].copy_(o["rot"], non_blocking=True)
             trans_hosts[sl].copy_(o["trans"], non_blocking=True)
@@ -283,6 +307,8 @@ def main():
         checksum += float(trans_hosts[(nsteps - 1) % 2][0, 2])
         return checksum
 
+    for sl in range(2):
+        graphed(stagings[sl])
     run_e2e(2)
     barrier()
     e0.record()

@@ -23,7 +23,7 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int NUM_THREADS = 384;              // 4 control warps + 8 epilogue warps
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int EPI_STAGE_PITCH = 80;           // 64-byte row segment + 16 B pad (conflict-free 16-byte accesses)
-constexpr int EPI_STAGE_BYTES = 32 * EPI_STAGE_PITCH + 256;  // per epilogue warp: 32 rows + 32 x int64 row map
+constexpr int EPI_STAGE_BYTES = 32 * EPI_STAGE_PITCH + 256 + 1024;  // per epilogue warp: 32 rows + 32 x int64 row map + bias/gamma (2 x 128 f32)
 constexpr int SMEM_BUDGET = 227 * 1024 - NUM_EPI_WARPS * EPI_STAGE_BYTES - 1024 - 256;
 
 template <int BLOCK_N>
@@ -384,6 +384,7 @@ __device__ __forceinline__ void epilogue_tile_staged_t(const GemmPlan& p, int m_
   const int r = q * 32 + lane;
   const RowInfo ri = map_row(p, m_tile, r);
   long long* s_orow = reinterpret_cast<long long*>(stg + 32 * EPI_STAGE_PITCH);
+  const float* s_bias = reinterpret_cast<const float*>(stg + 32 * EPI_STAGE_PITCH + 256);  // [128] bias, [128] gamma
   s_orow[lane] = ri.valid ? ri.orow : -1;
   __syncwarp();
   const int n0 = n_tile * BLOCK_N + half * CPW;
@@ -425,14 +426,24 @@ __device__ __forceinline__ void epilogue_tile_staged_t(const GemmPlan& p, int m_
     float v[CH];
     tmem_load_chunk<CH>(tmem_row + c, v);
     if constexpr (EPI == EPI_STORE || EPI == EPI_GELU) {
-      float bias[CH];
-      load_vec<CH>(p.bias, col, p.N, bias);
+      const float4* sb = reinterpret_cast<const float4*>(s_bias + c);  // warp-wide broadcast reads
 #pragma unroll
-      for (int j = 0; j < CH; ++j) v[j] += bias[j];
+      for (int j = 0; j < CH; j += 4) {
+        const float4 b4 = sb[j >> 2];
+        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+      }
     } else if constexpr (EPI == EPI_RESID) {
       float bias[CH], g[CH];
-      load_vec<CH>(p.bias, col, p.N, bias);
-      load_vec<CH>(p.gamma, col, p.N, g);
+      {
+        const float4* sb = reinterpret_cast<const float4*>(s_bias + c);
+        const float4* sg = reinterpret_cast<const float4*>(s_bias + 128 + c);
+#pragma unroll
+        for (int j = 0; j < CH; j += 4) {
+          const float4 b4 = sb[j >> 2], g4 = sg[j >> 2];
+          bias[j] = b4.x; bias[j + 1] = b4.y; bias[j + 2] = b4.z; bias[j + 3] = b4.w;
+          g[j] = g4.x; g[j + 1] = g4.y; g[j + 2] = g4.z; g[j + 3] = g4.w;
+        }
+      }
       const float4* xr = reinterpret_cast<const float4*>(my_row);
 #pragma unroll
       for (int j = 0; j < CH; j += 4) {
@@ -680,6 +691,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       const int m_tile = tile / p.n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      if constexpr (kStaged && EPI != EPI_GNSTATS) {
+        // this warp's bias (and layer-scale gamma) segment -> its shared-memory slot, before the accumulator wait
+        float* sbw = reinterpret_cast<float*>(stage_base + ew * EPI_STAGE_BYTES + 32 * EPI_STAGE_PITCH + 256);
+        const int cb = n_tile * BLOCK_N + (ew >> 2) * (BLOCK_N / 2) + lane * 4;
+        if (lane * 4 < BLOCK_N / 2) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = b4;
+          if (cb + 3 < p.N) {
+            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + cb));
+            if (EPI == EPI_RESID) g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + cb));
+          }
+          *reinterpret_cast<float4*>(sbw + lane * 4) = b4;
+          if (EPI == EPI_RESID) *reinterpret_cast<float4*>(sbw + 128 + lane * 4) = g4;
+        }
+        __syncwarp();
+      }
       if constexpr (kStaged && EPI == EPI_RESID) {
         // the residual rows of this tile are not produced by the MMAs: pull them into L2 while the mainloop runs
         const RowInfo pri = map_row(p, m_tile, (ew & 3) * 32 + lane);
