@@ -286,7 +286,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmPlan& p, int m_tile, int
     if (ri.valid) {
       const int b = ri.b;
       const int pix = (int)(ri.orow - (long long)b * p.rows_per_roi);
-      const int cls = (int)p.roi_classes[b];
+      int cls = (int)p.roi_classes[b];
+      cls = cls < 0 ? 0 : (cls >= p.num_classes ? p.num_classes - 1 : cls);
       const float* ob = p.oc_bias + cls * 80;
 #pragma unroll
       for (int j = 0; j < 72; j += 4) {
@@ -622,7 +623,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       if (EPI == EPI_OUTCONV) {
         long long grow = (long long)m_tile * BLOCK_M;
         int b = (int)(grow / p.rows_per_roi);
-        brow += (int)p.roi_classes[b] * p.b_rows_per_class;
+        int cls = (int)p.roi_classes[b];
+        cls = cls < 0 ? 0 : (cls >= p.num_classes ? p.num_classes - 1 : cls);  // never index outside the weights
+        brow += cls * p.b_rows_per_class;
       }
       for (int tap = 0; tap < p.num_taps; ++tap) {
         const GemmTap tp = p.taps[tap];

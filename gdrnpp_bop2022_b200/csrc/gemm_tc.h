@@ -57,6 +57,7 @@ struct GemmPlan {
   const float* ln_w; const float* ln_b; float ln_eps;  // EPI_BIAS_LN
   // EPI_OUTCONV
   const long long* roi_classes;  // [B]
+  int num_classes;               // roi_classes are clamped to [0, num_classes)
   int rows_per_roi;              // 4096
   const float* oc_bias;          // [num_classes, 80]
   const float* roi_extents;      // [B,3]

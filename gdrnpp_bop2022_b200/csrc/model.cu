@@ -584,6 +584,7 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
   p.b_rows_per_class = 80;
   p.epi = EPI_OUTCONV;
   p.roi_classes = reinterpret_cast<const long long*>(roi_classes);
+  p.num_classes = m->num_classes;
   p.rows_per_roi = 4096;
   p.oc_bias = m->out_b;
   p.roi_extents = roi_extents;
