@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -197,6 +198,26 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
 
 // exact-erf GELU (torch nn.GELU() default), used by the light elementwise kernels
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// GELU with packed half2 math (mode 1): 0.5*(1+tanh.approx.f16x2(x*(c0+c1*x^2))) evaluated for two
+// elements per instruction, multiplied by the fp32 x.  ~5 instructions and 0.5 MUFU per element.
+__device__ __forceinline__ uint32_t gelu_pack2_f16(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const __half2 x2 = __hmul2(h, h);
+  const __half2 pl = __hfma2(x2, __float2half2_rn(0.0356774f), __float2half2_rn(0.7978846f));
+  const __half2 q = __hmul2(h, pl);
+  uint32_t qi = *reinterpret_cast<const uint32_t*>(&q), ti;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(qi));
+  const __half2 t = *reinterpret_cast<const __half2*>(&ti);
+  const __half2 phi = __hfma2(t, __float2half2_rn(0.5f), __float2half2_rn(0.5f));
+  const float2 pf = __half22float2(phi);
+  return pack_bf16(a * pf.x, b * pf.y);
+}
 
 // GELU for the GEMM epilogues: x * sigmoid(2*q(x)) with q an odd polynomial fitted so that
 // 0.5*(1+tanh(q(x))) == Phi(x) (the erf form), evaluated with ex2.approx + rcp.approx

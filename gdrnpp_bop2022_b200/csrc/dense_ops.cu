@@ -242,7 +242,7 @@ __device__ __forceinline__ float lane_transpose_reduce(float (&a)[N], int lane) 
 
 template <int TW, int TH>
 __global__ void __launch_bounds__(((TW == 16) ? 32 : 64) * TH, (TW == 16) ? 2 : 1)
-dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __restrict__ w49c,
+dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                          const float* __restrict__ bias, const float* __restrict__ ln_w,
                          const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out, int B, int H, int W, int C,
                          float eps) {
@@ -280,18 +280,17 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const float
   }
   __syncthreads();
   if (tid == 0) {
-    ptx::mbar_arrive_expect_tx(bar, (uint32_t)(IH * IW * CPC * sizeof(float)));
+    ptx::mbar_arrive_expect_tx(bar, (uint32_t)((IH * IW + 49) * CPC * sizeof(float)));
+    ptx::tma_load_2d(ptx::smem_u32(wsm), &tmap_w, bar, c0, 0);          // this CTA's 49 x CPC filter taps
     ptx::tma_load_4d(ptx::smem_u32(tile), &tmap_x, bar, c0, x0 - 3, y0 - 3, b);
   }
-  for (int i = tid; i < 49 * CPC; i += NTHREADS) wsm[i] = __ldg(w49c + (i / CPC) * C + c0 + (i % CPC));
   f32x2_t acc[TW];
   {
     const f32x2_t bv = f2_pack(__ldg(bias + c0 + cl), __ldg(bias + c0 + cl + 1));
 #pragma unroll
     for (int i = 0; i < TW; ++i) acc[i] = bv;
   }
-  __syncthreads();           // filter taps staged
-  ptx::mbar_wait(bar, 0);    // input tile landed
+  ptx::mbar_wait(bar, 0);    // filter taps + input tile landed
 
   // ---- convolution: one output row x TW pixels for a channel pair, 7 input rows ----
 #pragma unroll
@@ -463,23 +462,22 @@ __global__ void gn_finalize_kernel(const double* __restrict__ stats, float2* __r
   mr[i] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
 }
 
+// GroupNorm apply + GELU: one thread per (4 consecutive pixels, 8 channels); the per-channel scale/shift is
+// computed once per thread, GELU uses the packed-half2 tanh.approx form (two elements per instruction).
+constexpr int GN_PPT = 4;
 __global__ void __launch_bounds__(256)
 gn_gelu_kernel(const void* __restrict__ raw, int raw_is_f32, const float2* __restrict__ mr,
                const float* __restrict__ gn_w, const float* __restrict__ gn_b, __nv_bfloat16* __restrict__ out, int B,
-               int h, int w, int C, int groups, int up) {
+               int hw, int C, int groups) {
   const int cv = C >> 3;
-  const int oh = h * up, ow = w * up;
-  const unsigned total = (unsigned)B * oh * ow * cv;  // < 2^31 (checked by the launcher): 32-bit index math
+  const unsigned total = (unsigned)B * (hw / GN_PPT) * cv;  // < 2^31 (checked by the launcher)
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int c8 = (int)(idx % (unsigned)cv) * 8;
-  const unsigned p = idx / (unsigned)cv;
-  const int ox = (int)(p % (unsigned)ow);
-  const unsigned prow = p / (unsigned)ow;
-  const int oy = (int)(prow % (unsigned)oh);
-  const int b = (int)(prow / (unsigned)oh);
+  const unsigned pg = idx / (unsigned)cv;                  // pixel group over all images
+  const int b = (int)(pg / (unsigned)(hw / GN_PPT));
+  const long long pix0 = (long long)pg * GN_PPT;           // first pixel (global index over B*hw)
   const int cpg = C / groups;
-  // per-channel scale/shift: y = v * a + s
   float a[8], s[8];
   {
     const float4 w0 = __ldg(reinterpret_cast<const float4*>(gn_w + c8)), w1 = __ldg(reinterpret_cast<const float4*>(gn_w + c8 + 4));
@@ -496,37 +494,50 @@ gn_gelu_kernel(const void* __restrict__ raw, int raw_is_f32, const float2* __res
       s[k] = fmaf(-m.x, a[k], gb[k]);
     }
   }
-  float o[8];
-  if (up == 1) {
-    float v[8];
-    load8(raw, raw_is_f32, (((long long)b * h + oy) * w + ox) * C + c8, v);
+  float v[GN_PPT][8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = gelu_fast(fmaf(v[k], a[k], s[k]));
-  } else {
-    // nn.UpsamplingBilinear2d(scale_factor=2): align_corners=True, src = dst * (in-1)/(out-1)
-    const float fy = (oh > 1) ? (float)oy * ((float)(h - 1) / (float)(oh - 1)) : 0.f;
-    const float fx = (ow > 1) ? (float)ox * ((float)(w - 1) / (float)(ow - 1)) : 0.f;
-    const int y0 = (int)fy, x0 = (int)fx;
-    const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
-    const float ly = fy - (float)y0, lx = fx - (float)x0;
-    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-    float v00[8], v01[8], v10[8], v11[8];
-    load8(raw, raw_is_f32, (((long long)b * h + y0) * w + x0) * C + c8, v00);
-    load8(raw, raw_is_f32, (((long long)b * h + y0) * w + x1) * C + c8, v01);
-    load8(raw, raw_is_f32, (((long long)b * h + y1) * w + x0) * C + c8, v10);
-    load8(raw, raw_is_f32, (((long long)b * h + y1) * w + x1) * C + c8, v11);
+  for (int i = 0; i < GN_PPT; ++i) load8(raw, raw_is_f32, (pix0 + i) * C + c8, v[i]);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float g00 = gelu_fast(fmaf(v00[k], a[k], s[k])), g01 = gelu_fast(fmaf(v01[k], a[k], s[k]));
-      float g10 = gelu_fast(fmaf(v10[k], a[k], s[k])), g11 = gelu_fast(fmaf(v11[k], a[k], s[k]));
-      o[k] = w00 * g00 + w01 * g01 + w10 * g10 + w11 * g11;
-    }
+  for (int i = 0; i < GN_PPT; ++i) {
+    uint4 u;
+    u.x = gelu_pack2_f16(fmaf(v[i][0], a[0], s[0]), fmaf(v[i][1], a[1], s[1]));
+    u.y = gelu_pack2_f16(fmaf(v[i][2], a[2], s[2]), fmaf(v[i][3], a[3], s[3]));
+    u.z = gelu_pack2_f16(fmaf(v[i][4], a[4], s[4]), fmaf(v[i][5], a[5], s[5]));
+    u.w = gelu_pack2_f16(fmaf(v[i][6], a[6], s[6]), fmaf(v[i][7], a[7], s[7]));
+    *reinterpret_cast<uint4*>(out + (pix0 + i) * C + c8) = u;
   }
+}
+
+// nn.UpsamplingBilinear2d(scale_factor=2) (align_corners=True) on NHWC bf16: src = dst * (in-1)/(out-1)
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int h, int w, int C) {
+  const int cv = C >> 3;
+  const int oh = 2 * h, ow = 2 * w;
+  const unsigned total = (unsigned)B * oh * ow * cv;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % (unsigned)cv) * 8;
+  const unsigned p = idx / (unsigned)cv;
+  const int ox = (int)(p % (unsigned)ow);
+  const unsigned prow = p / (unsigned)ow;
+  const int oy = (int)(prow % (unsigned)oh);
+  const int b = (int)(prow / (unsigned)oh);
+  const float fy = (float)oy * ((float)(h - 1) / (float)(oh - 1));
+  const float fx = (float)ox * ((float)(w - 1) / (float)(ow - 1));
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+  const float ly = fy - (float)y0, lx = fx - (float)x0;
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  float v00[8], v01[8], v10[8], v11[8];
+  load8(in, 0, (((long long)b * h + y0) * w + x0) * C + c8, v00);
+  load8(in, 0, (((long long)b * h + y0) * w + x1) * C + c8, v01);
+  load8(in, 0, (((long long)b * h + y1) * w + x0) * C + c8, v10);
+  load8(in, 0, (((long long)b * h + y1) * w + x1) * C + c8, v11);
+  float o[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) o[k] = w00 * v00[k] + w01 * v01[k] + w10 * v10[k] + w11 * v11[k];
   uint4 u;
-  __nv_bfloat162 p0 = __floats2bfloat162_rn(o[0], o[1]), p1 = __floats2bfloat162_rn(o[2], o[3]);
-  __nv_bfloat162 p2 = __floats2bfloat162_rn(o[4], o[5]), p3 = __floats2bfloat162_rn(o[6], o[7]);
-  u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-  u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+  u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
   *reinterpret_cast<uint4*>(out + (((long long)b * oh + oy) * ow + ox) * C + c8) = u;
 }
 
@@ -645,6 +656,14 @@ static int launch_dwconv_cluster(const float* x, const float* w49c, const float*
     int rc = make_tmap_f32_plain(&tmap, x, 4, dims, str, box);
     if (rc != GDRN_OK) return rc;
   }
+  CUtensorMap tmap_w;
+  {
+    const uint64_t dims[2] = {(uint64_t)C, 49};
+    const uint64_t str[1] = {(uint64_t)C * 4};
+    const uint32_t box[2] = {(uint32_t)CPC, 49};
+    int rc = make_tmap_f32_plain(&tmap_w, w49c, 2, dims, str, box);
+    if (rc != GDRN_OK) return rc;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(C / CPC, (H / TH) * (W / TW), B);
   cfg.blockDim = dim3(NTHREADS);
@@ -657,7 +676,7 @@ static int launch_dwconv_cluster(const float* x, const float* w49c, const float*
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  GDRN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kfn, tmap, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps));
+  GDRN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kfn, tmap, tmap_w, bias, ln_w, ln_b, out, B, H, W, C, eps));
   gdrn_count_launch(1);
   return GDRN_OK;
 }
@@ -712,18 +731,28 @@ int launch_bf16_to_f32(const __nv_bfloat16* src, float* dst, long long n, cudaSt
 }
 
 int launch_gn_gelu(const void* raw, int raw_is_f32, const double* stats, float* mean_rstd_scratch, const float* gn_w,
-                   const float* gn_b, __nv_bfloat16* out, int B, int h, int w, int C, int groups, float eps, int up,
+                   const float* gn_b, __nv_bfloat16* out, int B, int h, int w, int C, int groups, float eps,
                    cudaStream_t st) {
-  GDRN_REQUIRE(C % 8 == 0 && (up == 1 || up == 2), "gn_gelu: unsupported shape");
+  GDRN_REQUIRE(C % 8 == 0 && (h * w) % GN_PPT == 0, "gn_gelu: unsupported shape");
   const int n_bg = B * groups;
   gn_finalize_kernel<<<(n_bg + 127) / 128, 128, 0, st>>>(stats, reinterpret_cast<float2*>(mean_rstd_scratch), n_bg,
                                                         (double)h * w * (C / groups), eps);
-  long long total = (long long)B * h * up * w * up * (C / 8);
+  long long total = (long long)B * (h * w / GN_PPT) * (C / 8);
   GDRN_REQUIRE(total < (1LL << 31), "gn_gelu: tensor too large for 32-bit indexing");
   gn_gelu_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(raw, raw_is_f32, reinterpret_cast<const float2*>(mean_rstd_scratch),
-                                                            gn_w, gn_b, out, B, h, w, C, groups, up);
+                                                            gn_w, gn_b, out, B, h * w, C, groups);
   GDRN_CHECK_CUDA(cudaGetLastError());
   gdrn_count_launch(2);
+  return GDRN_OK;
+}
+
+int launch_upsample2x(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int h, int w, int C, cudaStream_t st) {
+  GDRN_REQUIRE(C % 8 == 0 && h > 1 && w > 1, "upsample2x: unsupported shape");
+  long long total = (long long)B * 4 * h * w * (C / 8);
+  GDRN_REQUIRE(total < (1LL << 31), "upsample2x: tensor too large for 32-bit indexing");
+  upsample2x_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(in, out, B, h, w, C);
+  GDRN_CHECK_CUDA(cudaGetLastError());
+  gdrn_count_launch(1);
   return GDRN_OK;
 }
 

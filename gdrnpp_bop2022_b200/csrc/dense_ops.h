@@ -28,11 +28,13 @@ int launch_ln_patchify2(const float* x, const float* ln_w, const float* ln_b, __
 
 int launch_cast_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t st);
 
-// GroupNorm apply (+GELU erf) (+ bilinear x2 upsample, align_corners=True) on NHWC.
-// raw: bf16 or fp32 [B,h,w,C]; stats: double [B,G,2] (sum, sumsq over h*w*cpg); out bf16 [B,h*up,w*up,C].
+// GroupNorm apply + GELU on NHWC.  raw: bf16 or fp32 [B,h,w,C]; stats: double [B,G,2] (sum, sumsq over h*w*cpg);
+// out bf16 [B,h,w,C].
 int launch_gn_gelu(const void* raw, int raw_is_f32, const double* stats, float* mean_rstd_scratch /*[B*groups*2]*/,
                    const float* gn_w, const float* gn_b, __nv_bfloat16* out, int B, int h, int w, int C, int groups, float eps,
-                   int up, cudaStream_t st);
+                   cudaStream_t st);
+// bilinear x2 (align_corners=True) on NHWC bf16: [B,h,w,C] -> [B,2h,2w,C]
+int launch_upsample2x(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int h, int w, int C, cudaStream_t st);
 
 // rot6d -> R_allo, centroid/z -> t, allocentric -> egocentric. raw: [B, ld] fp32 (rot6d at 0..5, t_ at 6..8)
 int launch_pose_lift(const float* raw, int ld, const float* cams, const float* centers, const float* whs,

@@ -69,10 +69,6 @@ __device__ __forceinline__ RowInfo map_row(const GemmPlan& p, int m_tile, int r)
 
 constexpr int PREFETCH_AHEAD = 6;  // k-iterations of A/B requested into L2 ahead of the shared-memory ring
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
 
 template <int CH>
 __device__ __forceinline__ void store_row_chunk(const GemmPlan& p, const RowInfo& ri, int col, const float (&v)[CH],
@@ -339,21 +335,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmPlan& p, int m_tile, int
   }
 }
 
-
-// GELU with packed half2 math (mode 1): 0.5*(1+tanh.approx.f16x2(x*(c0+c1*x^2))) evaluated for two
-// elements per instruction, multiplied by the fp32 x.  ~5 instructions and 0.5 MUFU per element.
-__device__ __forceinline__ uint32_t gelu_pack2_f16(float a, float b) {
-  const __half2 h = __floats2half2_rn(a, b);
-  const __half2 x2 = __hmul2(h, h);
-  const __half2 pl = __hfma2(x2, __float2half2_rn(0.0356774f), __float2half2_rn(0.7978846f));
-  const __half2 q = __hmul2(h, pl);
-  uint32_t qi = *reinterpret_cast<const uint32_t*>(&q), ti;
-  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ti) : "r"(qi));
-  const __half2 t = *reinterpret_cast<const __half2*>(&ti);
-  const __half2 phi = __hfma2(t, __float2half2_rn(0.5f), __float2half2_rn(0.5f));
-  const float2 pf = __half22float2(phi);
-  return pack_bf16(a * pf.x, b * pf.y);
-}
 
 // GELU mode 2: fp32 tanh form with the hardware tanh.approx.f32 (1 MUFU / element):
 // 0.5*x*(1 + tanh(x*(c0 + c1*x^2 + c2*x^4))) with (c0,c1,c2) fitted to the erf form (tools/fit_gelu.py).

@@ -552,7 +552,7 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
       p.gn_stats = stat_slot(0); p.gn_groups = 32; p.gn_cpg = 8;
       RCP(0, gemm_tc_launch(p, 256, st));
     }
-  RCP(2, launch_gn_gelu(w.R, 0, stat_slot(0), w.gn_mr, m->gn_w[0], m->gn_b[0], w.P, B, 16, 16, 256, 32, 1e-5f, 1, st));
+  RCP(2, launch_gn_gelu(w.R, 0, stat_slot(0), w.gn_mr, m->gn_w[0], m->gn_b[0], w.P, B, 16, 16, 256, 32, 1e-5f, st));
   __nv_bfloat16* cur = w.P;
   __nv_bfloat16* nxt = w.Q;
   int hres = 16;
@@ -570,8 +570,15 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
       p.gn_stats = stat_slot(li + 1); p.gn_groups = 32; p.gn_cpg = 8;
       RCP(0, gemm_tc_launch(p, 256, st));
       const int up = (j == 1 && blk < 2) ? 2 : 1;
-      RCP(2, launch_gn_gelu(w.R, 0, stat_slot(li + 1), w.gn_mr, m->gn_w[li + 1], m->gn_b[li + 1], nxt, B, hres, hres, 256, 32, 1e-5f,
-                        up, st));
+      if (up == 1) {
+        RCP(2, launch_gn_gelu(w.R, 0, stat_slot(li + 1), w.gn_mr, m->gn_w[li + 1], m->gn_b[li + 1], nxt, B, hres, hres, 256, 32,
+                              1e-5f, st));
+      } else {
+        // GN + GELU at the low resolution into `cur` (the conv's input, dead now), then bilinear x2 into `nxt`
+        RCP(2, launch_gn_gelu(w.R, 0, stat_slot(li + 1), w.gn_mr, m->gn_w[li + 1], m->gn_b[li + 1], cur, B, hres, hres, 256, 32,
+                              1e-5f, st));
+        RCP(2, launch_upsample2x(cur, nxt, B, hres, hres, 256, st));
+      }
       std::swap(cur, nxt);
       hres *= up;
     }
@@ -620,7 +627,7 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
       p.OH = ores; p.OW = ores; p.osy = 1; p.osx = 1;
       p.gn_stats = stat_slot(7 + i); p.gn_groups = 32; p.gn_cpg = 4;
       RCP(0, gemm_tc_launch(p, 128, st));
-      RCP(2, launch_gn_gelu(w.pR, 0, stat_slot(7 + i), w.gn_mr, m->pgn_w[i], m->pgn_b[i], w.pP, B, ores, ores, 128, 32, 1e-5f, 1, st));
+      RCP(2, launch_gn_gelu(w.pR, 0, stat_slot(7 + i), w.gn_mr, m->pgn_w[i], m->pgn_b[i], w.pP, B, ores, ores, 128, 32, 1e-5f, st));
       // ping-pong between pP and a second buffer is unnecessary: the conv reads pP (or pnp_in) and writes pR
       in = w.pP;
       ires = ores;
