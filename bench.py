@@ -54,7 +54,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -91,6 +91,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    """CPU threads this process may actually use (cgroup / affinity aware), capped at 64 for the torch CPU path."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 64))
+
+
 def run_cpu_path(n_rois, threads, arch="convnext_base"):
     """The CPU restatement (oracle port) of the forward on `n_rois` ROIs; returns seconds."""
     from gdrnpp_bop2022_b200.synthetic import make_batch, make_state_dict
@@ -115,9 +124,9 @@ def bench_reference(args, rank):
     from gdrnpp_bop2022_b200.synthetic import make_batch, make_state_dict
     from oracle import gdrn_model_oracle as O
 
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     torch.set_num_threads(threads)
-    n = 4  # ROIs per step: a bounded sample of the 64-ROI workload
+    n = 1  # ROIs per step: a bounded sample of the 64-ROI workload (the CPU path needs seconds per ROI)
     sd = make_state_dict()
     batches = [make_batch(B=n, seed=20 + i) for i in range(2)]
     with torch.no_grad():
@@ -354,8 +363,8 @@ def main():
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            n_cpu = 8
+            threads = host_threads()
+            n_cpu = 4
             dt = run_cpu_path(n_cpu, threads)
             cpu = {"value": n_cpu / dt, "unit": "ROIs/s", "cores": threads, "kind": "port",
                    "sample": "%d ROIs of the same synthetic workload, oracle forward (torch CPU fp32), %.1f s" % (n_cpu, dt)}
