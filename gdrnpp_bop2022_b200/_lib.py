@@ -34,6 +34,8 @@ _SIGNATURES = {
     "gdrn_model_set_profiling": (c_int, [c_void_p, c_int]),
     "gdrn_model_get_profile": (c_int, [c_void_p, c_void_p, c_void_p]),
     "gdrn_model_create": (c_int, [POINTER(c_void_p), c_char_p, c_int, c_int]),
+    "gdrn_model_create_ex": (c_int, [POINTER(c_void_p), c_char_p, c_int, c_int, c_int]),
+    "gdrn_model_precision": (c_int, [c_void_p]),
     "gdrn_model_destroy": (None, [c_void_p]),
     "gdrn_model_load_tensor": (c_int, [c_void_p, c_char_p, c_void_p, c_int64, c_void_p]),
     "gdrn_model_missing": (c_int, [c_void_p]),

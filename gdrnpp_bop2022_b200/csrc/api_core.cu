@@ -42,7 +42,7 @@ extern "C" int gdrn_gemm_bf16(const void* A, const void* W, const float* bias, c
   p.a_rank = 2;
   p.num_taps = 1;
   p.k_chunks = (K + 63) / 64;
-  p.b_tap_stride = 0;
+  p.taps[0] = {0, 0, 0, 0, 0};
   p.m_tiles = (M + 127) / 128;
   p.n_tiles = (N + block_n - 1) / block_n;
   p.M = M;

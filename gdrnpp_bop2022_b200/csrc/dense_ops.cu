@@ -15,6 +15,7 @@ namespace {
 
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_kernel(const float* __restrict__ src, void* __restrict__ dst, int dst_is_bf16, PackDesc d) {
+  // d.lo_delta > 0 (bf16 only): also write lo = bf16(v - float(bf16(v))) at offset + lo_delta (split-bf16 weights)
   const long long total = d.dims[0] * d.dims[1] * d.dims[2] * d.dims[3];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -25,15 +26,20 @@ __global__ void pack_kernel(const float* __restrict__ src, void* __restrict__ ds
     long long i0 = r;
     float v = src[d.soff + i0 * d.ss[0] + i1 * d.ss[1] + i2 * d.ss[2] + i3 * d.ss[3]];
     long long o = d.doff + i0 * d.ds[0] + i1 * d.ds[1] + i2 * d.ds[2] + i3 * d.ds[3];
-    if (dst_is_bf16) reinterpret_cast<__nv_bfloat16*>(dst)[o] = __float2bfloat16(v);
-    else reinterpret_cast<float*>(dst)[o] = v;
+    if (dst_is_bf16) {
+      const __nv_bfloat16 hi = __float2bfloat16(v);
+      reinterpret_cast<__nv_bfloat16*>(dst)[o] = hi;
+      if (d.lo_delta > 0) reinterpret_cast<__nv_bfloat16*>(dst)[o + d.lo_delta] = __float2bfloat16(v - __bfloat162float(hi));
+    } else {
+      reinterpret_cast<float*>(dst)[o] = v;
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // stem patchify: one thread per output pixel writes one 128-byte row.
 __global__ void stem_patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int H,
-                                     int W) {
+                                     int W, int split) {
   const int OW = W / 4, OH = H / 4;
   const long long total = (long long)B * OH * OW;
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -41,7 +47,7 @@ __global__ void stem_patchify_kernel(const float* __restrict__ img, __nv_bfloat1
   const int ox = (int)(m % OW);
   const int oy = (int)((m / OW) % OH);
   const int b = (int)(m / ((long long)OW * OH));
-  uint4* row = reinterpret_cast<uint4*>(out + m * 64);
+  uint4* row = reinterpret_cast<uint4*>(out + m * (split ? 128 : 64));
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     float v[16];
@@ -60,10 +66,19 @@ __global__ void stem_patchify_kernel(const float* __restrict__ img, __nv_bfloat1
       u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
       u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
       row[c * 2 + j] = u;
+      if (split) {
+        float l[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) l[k] = v[j * 8 + k] - __bfloat162float(__float2bfloat16(v[j * 8 + k]));
+        uint4 ul;
+        ul.x = pack_bf16(l[0], l[1]); ul.y = pack_bf16(l[2], l[3]); ul.z = pack_bf16(l[4], l[5]); ul.w = pack_bf16(l[6], l[7]);
+        row[8 + c * 2 + j] = ul;
+      }
     }
   }
   row[6] = make_uint4(0, 0, 0, 0);
   row[7] = make_uint4(0, 0, 0, 0);
+  if (split) { row[14] = make_uint4(0, 0, 0, 0); row[15] = make_uint4(0, 0, 0, 0); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -245,7 +260,7 @@ __global__ void __launch_bounds__(((TW == 16) ? 32 : 64) * TH, (TW == 16) ? 2 : 
 dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                          const float* __restrict__ bias, const float* __restrict__ ln_w,
                          const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out, int B, int H, int W, int C,
-                         float eps) {
+                         float eps, int split) {
   constexpr int CPC = (TW == 16) ? 64 : 128;  // channels per CTA
   constexpr int PAIRS = CPC / 2;              // channel pairs = threads per output row
   constexpr int IW = TW + 6;
@@ -356,13 +371,19 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
   // ---- normalise + affine, bf16x2 out (a warp writes 128 contiguous bytes per pixel) ----
   const float gw0 = __ldg(ln_w + c0 + cl), gw1 = __ldg(ln_w + c0 + cl + 1);
   const float gb0 = __ldg(ln_b + c0 + cl), gb1 = __ldg(ln_b + c0 + cl + 1);
-  __nv_bfloat16* orow = out + (((long long)b * H + (y0 + row)) * W + x0) * C + c0 + cl;
+  const int ldc = split ? 2 * C : C;  // split mode: rows are [hi C | lo C]
+  __nv_bfloat16* orow = out + (((long long)b * H + (y0 + row)) * W + x0) * ldc + c0 + cl;
 #pragma unroll
   for (int ox = 0; ox < TW; ++ox) {
     const float m = __shfl_sync(0xffffffffu, mean_p, ox * LPP);
     const float r = __shfl_sync(0xffffffffu, rstd_p, ox * LPP);
-    const __nv_bfloat162 o = __floats2bfloat162_rn(fmaf((ax[ox] - m) * r, gw0, gb0), fmaf((ay[ox] - m) * r, gw1, gb1));
-    *reinterpret_cast<__nv_bfloat162*>(orow + (long long)ox * C) = o;
+    const float o0 = fmaf((ax[ox] - m) * r, gw0, gb0), o1 = fmaf((ay[ox] - m) * r, gw1, gb1);
+    const __nv_bfloat162 o = __floats2bfloat162_rn(o0, o1);
+    *reinterpret_cast<__nv_bfloat162*>(orow + (long long)ox * ldc) = o;
+    if (split) {
+      const float2 of = __bfloat1622float2(o);
+      *reinterpret_cast<__nv_bfloat162*>(orow + (long long)ox * ldc + C) = __floats2bfloat162_rn(o0 - of.x, o1 - of.y);
+    }
   }
 }
 
@@ -370,7 +391,7 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
 // LayerNorm2d + 2x2 stride-2 patchify: one warp per source pixel.
 __global__ void __launch_bounds__(256)
 ln_patchify2_kernel(const float* __restrict__ x, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                    __nv_bfloat16* __restrict__ out, int B, int H, int W, int C, float eps) {
+                    __nv_bfloat16* __restrict__ out, int B, int H, int W, int C, float eps, int split) {
   const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const long long total = (long long)B * H * W;
   if (pix >= total) return;
@@ -398,17 +419,56 @@ ln_patchify2_kernel(const float* __restrict__ x, const float* __restrict__ ln_w,
   for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float r = rsqrtf(q / (float)C + eps);
   const long long m2 = ((long long)b * (H / 2) + (py >> 1)) * (W / 2) + (px >> 1);
-  __nv_bfloat16* dst = out + m2 * (4LL * C) + ((py & 1) * 2 + (px & 1)) * C;
+  __nv_bfloat16* dst = out + m2 * ((split ? 8LL : 4LL) * C) + ((py & 1) * 2 + (px & 1)) * C;
   for (int k = 0; k < nv; ++k) {
     const int c = (k * 32 + lane) * 4;
     const float4 gw = *reinterpret_cast<const float4*>(ln_w + c);
     const float4 gb = *reinterpret_cast<const float4*>(ln_b + c);
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaf((v[k].x - mean) * r, gw.x, gb.x), fmaf((v[k].y - mean) * r, gw.y, gb.y));
-    __nv_bfloat162 p1 = __floats2bfloat162_rn(fmaf((v[k].z - mean) * r, gw.z, gb.z), fmaf((v[k].w - mean) * r, gw.w, gb.w));
+    const float o0 = fmaf((v[k].x - mean) * r, gw.x, gb.x), o1 = fmaf((v[k].y - mean) * r, gw.y, gb.y);
+    const float o2 = fmaf((v[k].z - mean) * r, gw.z, gb.z), o3 = fmaf((v[k].w - mean) * r, gw.w, gb.w);
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1);
+    __nv_bfloat162 p1 = __floats2bfloat162_rn(o2, o3);
     uint2 u;
     u.x = *reinterpret_cast<uint32_t*>(&p0);
     u.y = *reinterpret_cast<uint32_t*>(&p1);
     *reinterpret_cast<uint2*>(dst + c) = u;
+    if (split) {
+      const float2 f0 = __bfloat1622float2(p0), f1 = __bfloat1622float2(p1);
+      uint2 ul;
+      ul.x = pack_bf16(o0 - f0.x, o1 - f0.y);
+      ul.y = pack_bf16(o2 - f1.x, o3 - f1.y);
+      *reinterpret_cast<uint2*>(dst + 4LL * C + c) = ul;   // lo half of the [hi 4C | lo 4C] row
+    }
+  }
+}
+
+__device__ __forceinline__ void load8(const void* raw, int is_f32, long long off, float (&v)[8]) {
+  if (is_f32) {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(raw) + off);
+    float4 a = p[0], b = p[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(raw) + off);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float2 f = __bfloat1622float2(h[k]);
+      v[2 * k] = f.x; v[2 * k + 1] = f.y;
+    }
+  }
+}
+
+// 8 consecutive channels -> bf16 (hi) at dst, and, in split mode, lo = bf16(v - hi) at dst + lo_off
+__device__ __forceinline__ void store8_split(__nv_bfloat16* dst, const float (&o)[8], int split, long long lo_off) {
+  uint4 u;
+  u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
+  *reinterpret_cast<uint4*>(dst) = u;
+  if (split) {
+    float l[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) l[k] = o[k] - __bfloat162float(__float2bfloat16(o[k]));
+    u.x = pack_bf16(l[0], l[1]); u.y = pack_bf16(l[2], l[3]); u.z = pack_bf16(l[4], l[5]); u.w = pack_bf16(l[6], l[7]);
+    *reinterpret_cast<uint4*>(dst + lo_off) = u;
   }
 }
 
@@ -428,6 +488,18 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
   }
 }
 
+// fp32 [rows, C] -> split bf16 [rows, 2C] = [hi C | lo C]
+__global__ void cast_split_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long rows, int C) {
+  const long long total = rows * (C / 8);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (C / 8);
+    const int c8 = (int)(i % (C / 8)) * 8;
+    float v[8];
+    load8(src, 1, r * C + c8, v);
+    store8_split(dst + r * 2 * C + c8, v, 1, C);
+  }
+}
+
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = __bfloat162float(src[i]);
@@ -435,22 +507,6 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, float*
 
 // ------------------------------------------------------------------------------------------------
 // GroupNorm apply + exact-erf GELU (+ bilinear x2, align_corners=True).  One thread per (output pixel, 8 channels).
-__device__ __forceinline__ void load8(const void* raw, int is_f32, long long off, float (&v)[8]) {
-  if (is_f32) {
-    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(raw) + off);
-    float4 a = p[0], b = p[1];
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-  } else {
-    uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(raw) + off);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float2 f = __bfloat1622float2(h[k]);
-      v[2 * k] = f.x; v[2 * k + 1] = f.y;
-    }
-  }
-}
-
 // per-(image, group) mean / rstd from the double sums accumulated by the conv epilogue
 __global__ void gn_finalize_kernel(const double* __restrict__ stats, float2* __restrict__ mr, int n_bg, double count,
                                    float eps) {
@@ -468,7 +524,7 @@ constexpr int GN_PPT = 4;
 __global__ void __launch_bounds__(256)
 gn_gelu_kernel(const void* __restrict__ raw, int raw_is_f32, const float2* __restrict__ mr,
                const float* __restrict__ gn_w, const float* __restrict__ gn_b, __nv_bfloat16* __restrict__ out, int B,
-               int hw, int C, int groups) {
+               int hw, int C, int groups, int split) {
   const int cv = C >> 3;
   const unsigned total = (unsigned)B * (hw / GN_PPT) * cv;  // < 2^31 (checked by the launcher)
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -497,6 +553,16 @@ gn_gelu_kernel(const void* __restrict__ raw, int raw_is_f32, const float2* __res
   float v[GN_PPT][8];
 #pragma unroll
   for (int i = 0; i < GN_PPT; ++i) load8(raw, raw_is_f32, (pix0 + i) * C + c8, v[i]);
+  if (split) {  // split-bf16 (x3) mode: exact-erf GELU, [hi C | lo C] rows
+#pragma unroll
+    for (int i = 0; i < GN_PPT; ++i) {
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = gelu_erf(fmaf(v[i][k], a[k], s[k]));
+      store8_split(out + (pix0 + i) * 2 * C + c8, o, 1, C);
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < GN_PPT; ++i) {
     uint4 u;
@@ -508,9 +574,46 @@ gn_gelu_kernel(const void* __restrict__ raw, int raw_is_f32, const float2* __res
   }
 }
 
+// GroupNorm apply + exact GELU -> fp32 (feeds the fp32 FC stack of the split-bf16 mode)
+__global__ void gn_gelu_f32_kernel(const float* __restrict__ raw, const float2* __restrict__ mr,
+                                   const float* __restrict__ gn_w, const float* __restrict__ gn_b,
+                                   float* __restrict__ out, int B, int hw, int C, int groups) {
+  const long long total = (long long)B * hw * C;
+  const int cpg = C / groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int b = (int)(i / ((long long)hw * C));
+    const float2 m = mr[(long long)b * groups + c / cpg];
+    out[i] = gelu_erf((raw[i] - m.x) * m.y * gn_w[c] + gn_b[c]);
+  }
+}
+
+// y[b, n] = act(sum_k x[b,k] * W[n,k] + bias[n]) in fp32 on the CUDA cores (Patch-PnP FC stack in split-bf16 mode:
+// 8.7 MMAC per ROI, irrelevant for throughput).  One warp per output element.
+__global__ void fc_f32_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
+                              float* __restrict__ y, int B, int N, int K, int ldy, int gelu) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B * N) return;
+  const int b = warp / N, n = warp % N;
+  const float* xr = x + (long long)b * K;
+  const float* wr = W + (long long)n * K;
+  float acc = 0.f;
+  for (int k = lane * 4; k < K; k += 128) {
+    const float4 xv = *reinterpret_cast<const float4*>(xr + k), wv = __ldg(reinterpret_cast<const float4*>(wr + k));
+    acc = fmaf(xv.x, wv.x, acc); acc = fmaf(xv.y, wv.y, acc); acc = fmaf(xv.z, wv.z, acc); acc = fmaf(xv.w, wv.w, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    acc += bias[n];
+    y[(long long)b * ldy + n] = gelu ? gelu_erf(acc) : acc;
+  }
+}
+
 // nn.UpsamplingBilinear2d(scale_factor=2) (align_corners=True) on NHWC bf16: src = dst * (in-1)/(out-1)
 __global__ void __launch_bounds__(256)
-upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int h, int w, int C) {
+upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int h, int w, int C,
+                  int split) {
   const int cv = C >> 3;
   const int oh = 2 * h, ow = 2 * w;
   const unsigned total = (unsigned)B * oh * ow * cv;
@@ -528,17 +631,31 @@ upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restric
   const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
   const float ly = fy - (float)y0, lx = fx - (float)x0;
   const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  const int ldc = split ? 2 * C : C;
   float v00[8], v01[8], v10[8], v11[8];
-  load8(in, 0, (((long long)b * h + y0) * w + x0) * C + c8, v00);
-  load8(in, 0, (((long long)b * h + y0) * w + x1) * C + c8, v01);
-  load8(in, 0, (((long long)b * h + y1) * w + x0) * C + c8, v10);
-  load8(in, 0, (((long long)b * h + y1) * w + x1) * C + c8, v11);
+  load8(in, 0, (((long long)b * h + y0) * w + x0) * ldc + c8, v00);
+  load8(in, 0, (((long long)b * h + y0) * w + x1) * ldc + c8, v01);
+  load8(in, 0, (((long long)b * h + y1) * w + x0) * ldc + c8, v10);
+  load8(in, 0, (((long long)b * h + y1) * w + x1) * ldc + c8, v11);
+  if (split) {  // value = hi + lo
+    float t[8];
+    load8(in, 0, (((long long)b * h + y0) * w + x0) * ldc + C + c8, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v00[k] += t[k];
+    load8(in, 0, (((long long)b * h + y0) * w + x1) * ldc + C + c8, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v01[k] += t[k];
+    load8(in, 0, (((long long)b * h + y1) * w + x0) * ldc + C + c8, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v10[k] += t[k];
+    load8(in, 0, (((long long)b * h + y1) * w + x1) * ldc + C + c8, t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v11[k] += t[k];
+  }
   float o[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) o[k] = w00 * v00[k] + w01 * v01[k] + w10 * v10[k] + w11 * v11[k];
-  uint4 u;
-  u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
-  *reinterpret_cast<uint4*>(out + (((long long)b * oh + oy) * ow + ox) * C + c8) = u;
+  store8_split(out + (((long long)b * oh + oy) * ow + ox) * ldc + c8, o, split, C);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -624,10 +741,10 @@ int launch_pack(const float* src, void* dst, int dst_is_bf16, const PackDesc& d,
   return GDRN_OK;
 }
 
-int launch_stem_patchify(const float* img, __nv_bfloat16* out, int B, int H, int W, cudaStream_t st) {
+int launch_stem_patchify(const float* img, __nv_bfloat16* out, int B, int H, int W, int split, cudaStream_t st) {
   GDRN_REQUIRE(H % 4 == 0 && W % 4 == 0, "stem: H, W must be multiples of 4");
   long long total = (long long)B * (H / 4) * (W / 4);
-  stem_patchify_kernel<<<(int)((total + 127) / 128), 128, 0, st>>>(img, out, B, H, W);
+  stem_patchify_kernel<<<(int)((total + 127) / 128), 128, 0, st>>>(img, out, B, H, W, split);
   GDRN_CHECK_CUDA(cudaGetLastError());
   gdrn_count_launch(1);
   return GDRN_OK;
@@ -636,7 +753,7 @@ int launch_stem_patchify(const float* img, __nv_bfloat16* out, int B, int H, int
 template <int TW, int TH>
 static int launch_dwconv_cluster(const float* x, const float* w49c, const float* bias, const float* ln_w,
                                  const float* ln_b, __nv_bfloat16* out, int B, int H, int W, int C, float eps,
-                                 cudaStream_t st) {
+                                 int split, cudaStream_t st) {
   constexpr int CPC = (TW == 16) ? 64 : 128;
   constexpr int IW = TW + 6, IH = TH + 6;
   constexpr int NPIX = TW * TH;
@@ -676,17 +793,18 @@ static int launch_dwconv_cluster(const float* x, const float* w49c, const float*
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  GDRN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kfn, tmap, tmap_w, bias, ln_w, ln_b, out, B, H, W, C, eps));
+  GDRN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kfn, tmap, tmap_w, bias, ln_w, ln_b, out, B, H, W, C, eps, split));
   gdrn_count_launch(1);
   return GDRN_OK;
 }
 
 int launch_dwconv_ln(const float* x, const float* w49c, const float* bias, const float* ln_w, const float* ln_b,
-                     __nv_bfloat16* out, int B, int H, int W, int C, float eps, cudaStream_t st) {
+                     __nv_bfloat16* out, int B, int H, int W, int C, float eps, int split, cudaStream_t st) {
   GDRN_REQUIRE(C % 128 == 0 && C <= 1024, "dwconv: C must be a multiple of 128 and <= 1024");
   // cluster kernel: 16x8 tiles x 64 channels (cluster C/64 <= 8) or 8x8 tiles x 128 channels (cluster C/128 <= 8)
-  if (H % 8 == 0 && W % 16 == 0 && C / 64 <= 8) return launch_dwconv_cluster<16, 8>(x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps, st);
-  if (H % 8 == 0 && W % 8 == 0 && C / 128 <= 8) return launch_dwconv_cluster<8, 8>(x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps, st);
+  if (H % 8 == 0 && W % 16 == 0 && C / 64 <= 8) return launch_dwconv_cluster<16, 8>(x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps, split, st);
+  if (H % 8 == 0 && W % 8 == 0 && C / 128 <= 8) return launch_dwconv_cluster<8, 8>(x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps, split, st);
+  GDRN_REQUIRE(!split, "dwconv: the non-cluster fallback kernel has no split-bf16 output");
   const int S = 256 / (C / 4);
   if (W % 16 == 0) {
     long long strips = (long long)B * H * (W / 16);
@@ -702,10 +820,10 @@ int launch_dwconv_ln(const float* x, const float* w49c, const float* bias, const
 }
 
 int launch_ln_patchify2(const float* x, const float* ln_w, const float* ln_b, __nv_bfloat16* out, int B, int H, int W,
-                        int C, float eps, cudaStream_t st) {
+                        int C, float eps, int split, cudaStream_t st) {
   GDRN_REQUIRE(C % 128 == 0 && C <= 512 && H % 2 == 0 && W % 2 == 0, "ln_patchify2: unsupported shape");
   long long total = (long long)B * H * W;
-  ln_patchify2_kernel<<<(int)((total + 7) / 8), 256, 0, st>>>(x, ln_w, ln_b, out, B, H, W, C, eps);
+  ln_patchify2_kernel<<<(int)((total + 7) / 8), 256, 0, st>>>(x, ln_w, ln_b, out, B, H, W, C, eps, split);
   GDRN_CHECK_CUDA(cudaGetLastError());
   gdrn_count_launch(1);
   return GDRN_OK;
@@ -731,7 +849,7 @@ int launch_bf16_to_f32(const __nv_bfloat16* src, float* dst, long long n, cudaSt
 }
 
 int launch_gn_gelu(const void* raw, int raw_is_f32, const double* stats, float* mean_rstd_scratch, const float* gn_w,
-                   const float* gn_b, __nv_bfloat16* out, int B, int h, int w, int C, int groups, float eps,
+                   const float* gn_b, __nv_bfloat16* out, int B, int h, int w, int C, int groups, float eps, int split,
                    cudaStream_t st) {
   GDRN_REQUIRE(C % 8 == 0 && (h * w) % GN_PPT == 0, "gn_gelu: unsupported shape");
   const int n_bg = B * groups;
@@ -740,17 +858,51 @@ int launch_gn_gelu(const void* raw, int raw_is_f32, const double* stats, float* 
   long long total = (long long)B * (h * w / GN_PPT) * (C / 8);
   GDRN_REQUIRE(total < (1LL << 31), "gn_gelu: tensor too large for 32-bit indexing");
   gn_gelu_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(raw, raw_is_f32, reinterpret_cast<const float2*>(mean_rstd_scratch),
-                                                            gn_w, gn_b, out, B, h * w, C, groups);
+                                                            gn_w, gn_b, out, B, h * w, C, groups, split);
   GDRN_CHECK_CUDA(cudaGetLastError());
   gdrn_count_launch(2);
   return GDRN_OK;
 }
 
-int launch_upsample2x(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int h, int w, int C, cudaStream_t st) {
+int launch_gn_gelu_f32(const float* raw, const double* stats, float* mean_rstd_scratch, const float* gn_w,
+                       const float* gn_b, float* out, int B, int h, int w, int C, int groups, float eps, cudaStream_t st) {
+  const int n_bg = B * groups;
+  gn_finalize_kernel<<<(n_bg + 127) / 128, 128, 0, st>>>(stats, reinterpret_cast<float2*>(mean_rstd_scratch), n_bg,
+                                                        (double)h * w * (C / groups), eps);
+  long long total = (long long)B * h * w * C;
+  gn_gelu_f32_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(raw, reinterpret_cast<const float2*>(mean_rstd_scratch), gn_w,
+                                                                gn_b, out, B, h * w, C, groups);
+  GDRN_CHECK_CUDA(cudaGetLastError());
+  gdrn_count_launch(2);
+  return GDRN_OK;
+}
+
+int launch_fc_f32(const float* x, const float* W, const float* bias, float* y, int B, int N, int K, int ldy, int gelu,
+                  cudaStream_t st) {
+  GDRN_REQUIRE(K % 128 == 0, "fc_f32: K must be a multiple of 128");
+  const long long warps = (long long)B * N;
+  fc_f32_kernel<<<(int)((warps * 32 + 255) / 256), 256, 0, st>>>(x, W, bias, y, B, N, K, ldy, gelu);
+  GDRN_CHECK_CUDA(cudaGetLastError());
+  gdrn_count_launch(1);
+  return GDRN_OK;
+}
+
+int launch_cast_split(const float* src, __nv_bfloat16* dst, long long rows, int C, cudaStream_t st) {
+  GDRN_REQUIRE(C % 8 == 0, "cast_split: C must be a multiple of 8");
+  long long total = rows * (C / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 8192) blocks = 8192;
+  cast_split_kernel<<<(int)blocks, 256, 0, st>>>(src, dst, rows, C);
+  GDRN_CHECK_CUDA(cudaGetLastError());
+  gdrn_count_launch(1);
+  return GDRN_OK;
+}
+
+int launch_upsample2x(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int h, int w, int C, int split, cudaStream_t st) {
   GDRN_REQUIRE(C % 8 == 0 && h > 1 && w > 1, "upsample2x: unsupported shape");
   long long total = (long long)B * 4 * h * w * (C / 8);
   GDRN_REQUIRE(total < (1LL << 31), "upsample2x: tensor too large for 32-bit indexing");
-  upsample2x_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(in, out, B, h, w, C);
+  upsample2x_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(in, out, B, h, w, C, split);
   GDRN_CHECK_CUDA(cudaGetLastError());
   gdrn_count_launch(1);
   return GDRN_OK;

@@ -10,21 +10,22 @@ struct PackDesc {
   long long ss[4];
   long long ds[4];
   long long soff, doff;
+  long long lo_delta;  // > 0 (bf16 dst): also write lo = bf16(v - float(hi)) at dst offset + lo_delta (split-bf16 weights)
 };
 int launch_pack(const float* src, void* dst, int dst_is_bf16, const PackDesc& d, cudaStream_t st);
 
 // stem: NCHW fp32 image -> bf16 patch rows [B*(H/4)*(W/4), 64] (k = c*16 + ky*4 + kx, 48..63 zero)
-int launch_stem_patchify(const float* img, __nv_bfloat16* out, int B, int H, int W, cudaStream_t st);
+int launch_stem_patchify(const float* img, __nv_bfloat16* out, int B, int H, int W, int split, cudaStream_t st);
 
 // ConvNeXt block front half: depthwise 7x7 (pad 3) + bias, LayerNorm over C (eps) -> bf16 [B*H*W, C]
 // x: fp32 NHWC; w: [49][C] (tap-major, repacked); all fp32.
 int launch_dwconv_ln(const float* x, const float* w49c, const float* bias, const float* ln_w, const float* ln_b,
-                     __nv_bfloat16* out, int B, int H, int W, int C, float eps, cudaStream_t st);
+                     __nv_bfloat16* out, int B, int H, int W, int C, float eps, int split, cudaStream_t st);
 
 // downsample front half: per-pixel LayerNorm over C then 2x2/s2 patchify -> bf16 [B*(H/2)*(W/2), 4*C]
 // (k = (ky*2+kx)*C + c)
 int launch_ln_patchify2(const float* x, const float* ln_w, const float* ln_b, __nv_bfloat16* out, int B, int H, int W,
-                        int C, float eps, cudaStream_t st);
+                        int C, float eps, int split, cudaStream_t st);
 
 int launch_cast_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t st);
 
@@ -32,9 +33,16 @@ int launch_cast_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStre
 // out bf16 [B,h,w,C].
 int launch_gn_gelu(const void* raw, int raw_is_f32, const double* stats, float* mean_rstd_scratch /*[B*groups*2]*/,
                    const float* gn_w, const float* gn_b, __nv_bfloat16* out, int B, int h, int w, int C, int groups, float eps,
-                   cudaStream_t st);
+                   int split, cudaStream_t st);
+int launch_gn_gelu_f32(const float* raw, const double* stats, float* mean_rstd_scratch, const float* gn_w,
+                       const float* gn_b, float* out, int B, int h, int w, int C, int groups, float eps, cudaStream_t st);
+// fp32 CUDA-core fully connected layer (split-bf16 mode FC stack): y[b,n] = act(x[b,:] . W[n,:] + bias[n])
+int launch_fc_f32(const float* x, const float* W, const float* bias, float* y, int B, int N, int K, int ldy, int gelu,
+                  cudaStream_t st);
+// fp32 [rows,C] -> split bf16 [rows,2C]
+int launch_cast_split(const float* src, __nv_bfloat16* dst, long long rows, int C, cudaStream_t st);
 // bilinear x2 (align_corners=True) on NHWC bf16: [B,h,w,C] -> [B,2h,2w,C]
-int launch_upsample2x(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int h, int w, int C, cudaStream_t st);
+int launch_upsample2x(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int h, int w, int C, int split, cudaStream_t st);
 
 // rot6d -> R_allo, centroid/z -> t, allocentric -> egocentric. raw: [B, ld] fp32 (rot6d at 0..5, t_ at 6..8)
 int launch_pose_lift(const float* raw, int ld, const float* cams, const float* centers, const float* whs,

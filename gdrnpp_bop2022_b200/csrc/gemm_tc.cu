@@ -306,7 +306,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmPlan& p, int m_tile, int
       for (int j = 7; j < 70; ++j) mx = fmaxf(mx, v[j]);
       float den = 0.f;
 #pragma unroll
-      for (int j = 6; j < 70; ++j) { v[j] = __expf(v[j] - mx); den += v[j]; }
+      if (p.split) {  // precise mode: full-accuracy exp
+#pragma unroll
+        for (int j = 6; j < 70; ++j) { v[j] = expf(v[j] - mx); den += v[j]; }
+      } else {
+#pragma unroll
+        for (int j = 6; j < 70; ++j) { v[j] = __expf(v[j] - mx); den += v[j]; }
+      }
       const float inv = 1.0f / den;
       const float ex = __ldg(p.roi_extents + b * 3 + 0), ey = __ldg(p.roi_extents + b * 3 + 1),
                   ez = __ldg(p.roi_extents + b * 3 + 2);
@@ -319,7 +325,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmPlan& p, int m_tile, int
 #pragma unroll
       for (int j = 0; j < 64; ++j) f[5 + j] = v[6 + j] * inv;
       f[69] = 0.f; f[70] = 0.f; f[71] = 0.f;
-      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.pnp_in) + ri.orow * 128);
+      const int pw = p.split ? 256 : 128;  // Patch-PnP input row width (split mode: [hi 128 | lo 128])
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.pnp_in) + ri.orow * pw);
 #pragma unroll
       for (int j = 0; j < 72; j += 8) {
         uint4 u;
@@ -331,6 +338,21 @@ __device__ __forceinline__ void epilogue_tile(const GemmPlan& p, int m_tile, int
       }
 #pragma unroll
       for (int j = 9; j < 16; ++j) dst[j] = make_uint4(0, 0, 0, 0);
+      if (p.split) {
+#pragma unroll
+        for (int j = 0; j < 72; ++j) f[j] = f[j] - __bfloat162float(__float2bfloat16(f[j]));
+#pragma unroll
+        for (int j = 0; j < 72; j += 8) {
+          uint4 u;
+          u.x = pack_bf16(f[j], f[j + 1]);
+          u.y = pack_bf16(f[j + 2], f[j + 3]);
+          u.z = pack_bf16(f[j + 4], f[j + 5]);
+          u.w = pack_bf16(f[j + 6], f[j + 7]);
+          dst[16 + (j >> 3)] = u;
+        }
+#pragma unroll
+        for (int j = 25; j < 32; ++j) dst[j] = make_uint4(0, 0, 0, 0);
+      }
     }
   }
 }
@@ -437,6 +459,7 @@ __device__ __forceinline__ void epilogue_tile_staged_t(const GemmPlan& p, int m_
       }
     }
     // ---- registers -> staging row ----
+    float lo[F32 ? 1 : CH];  // split mode: residual of the bf16 rounding, written in a second round
     if constexpr (F32) {
       float4* dst = reinterpret_cast<float4*>(my_row);
 #pragma unroll
@@ -453,7 +476,10 @@ __device__ __forceinline__ void epilogue_tile_staged_t(const GemmPlan& p, int m_
         }
       } else {
         if constexpr (EPI == EPI_GELU) {
-          if (p.gelu_mode == 2) {
+          if (p.gelu_mode == 3) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) v[j] = gelu_erf(v[j]);
+          } else if (p.gelu_mode == 2) {
 #pragma unroll
             for (int j = 0; j < CH; ++j) v[j] = gelu_tanh_f32(v[j]);
           } else {
@@ -467,6 +493,10 @@ __device__ __forceinline__ void epilogue_tile_staged_t(const GemmPlan& p, int m_
           w.x = pack_bf16(v[j], v[j + 1]); w.y = pack_bf16(v[j + 2], v[j + 3]);
           w.z = pack_bf16(v[j + 4], v[j + 5]); w.w = pack_bf16(v[j + 6], v[j + 7]);
           dst[j >> 3] = w;
+        }
+        if (p.split) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) lo[j] = v[j] - __bfloat162float(__float2bfloat16(v[j]));
         }
       }
     }
@@ -520,6 +550,28 @@ __device__ __forceinline__ void epilogue_tile_staged_t(const GemmPlan& p, int m_
             *reinterpret_cast<const uint4*>(stg + rr * EPI_STAGE_PITCH + fl_piece * 16);
     }
     __syncwarp();
+    if constexpr (!F32) {
+      if (p.split) {  // second round: the lo halves go to columns [N + col, ...)
+        uint4* dst = reinterpret_cast<uint4*>(my_row);
+#pragma unroll
+        for (int j = 0; j < CH; j += 8) {
+          uint4 w;
+          w.x = pack_bf16(lo[j], lo[j + 1]); w.y = pack_bf16(lo[j + 2], lo[j + 3]);
+          w.z = pack_bf16(lo[j + 4], lo[j + 5]); w.w = pack_bf16(lo[j + 6], lo[j + 7]);
+          dst[j >> 3] = w;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int pass = 0; pass < 32; pass += 8) {
+          const int rr = pass + fl_row;
+          const long long orow = s_orow[rr];
+          if (orow >= 0)
+            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + (orow * p.ldo + p.N + col) * ESZ + fl_piece * 16) =
+                *reinterpret_cast<const uint4*>(stg + rr * EPI_STAGE_PITCH + fl_piece * 16);
+        }
+        __syncwarp();
+      }
+    }
   }
 }
 
@@ -617,7 +669,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           ptx::mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
           const int k0 = kc * BLOCK_K;
           if (p.a_rank == 2) {
-            ptx::tma_load_2d(sa, &p.tmap_a, full_bar(stage), k0, m_tile * BLOCK_M);
+            ptx::tma_load_2d(sa, &p.tmap_a, full_bar(stage), k0 + tp.c0, m_tile * BLOCK_M + tp.d1);
             // A is streamed from HBM (it was written by the previous kernel): request it into L2 several
             // k-iterations ahead so the shared-memory ring only has to cover L2 latency, not DRAM latency.
             int pk = kc + PREFETCH_AHEAD, pm = m_tile;
@@ -626,13 +678,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
               const int nt = tile + gridDim.x;
               pm = (nt < total_tiles && (nt / p.n_tiles) != m_tile) ? nt / p.n_tiles : -1;
             }
-            if (pm >= 0 && pk < p.k_chunks) ptx::tma_prefetch_2d(&p.tmap_a, pk * BLOCK_K, pm * BLOCK_M);
+            if (pm >= 0 && pk < p.k_chunks && p.num_taps == 1) ptx::tma_prefetch_2d(&p.tmap_a, pk * BLOCK_K, pm * BLOCK_M);
           } else if (p.a_rank == 4) {
             ptx::tma_load_4d(sa, &p.tmap_a, full_bar(stage), k0 + tp.c0, x0 + tp.d1, y0 + tp.d2, b0);
           } else {
             ptx::tma_load_5d(sa, &p.tmap_a, full_bar(stage), k0 + tp.c0, x0 + tp.d1, tp.d2, y0 + tp.d3, b0);
           }
-          ptx::tma_load_2d(sb, &p.tmap_b, full_bar(stage), tap * p.b_tap_stride + k0, brow);
+          ptx::tma_load_2d(sb, &p.tmap_b, full_bar(stage), tp.b_off + k0, brow);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -745,7 +797,7 @@ int launch_inst(const GemmPlan& plan, cudaStream_t stream) {
 
 int gemm_tc_launch(const GemmPlan& plan, int block_n, cudaStream_t stream) {
   GDRN_REQUIRE(plan.a_rank == 2 || plan.a_rank == 4 || plan.a_rank == 5, "gemm: bad a_rank");
-  GDRN_REQUIRE(plan.num_taps >= 1 && plan.num_taps <= 9, "gemm: bad num_taps");
+  GDRN_REQUIRE(plan.num_taps >= 1 && plan.num_taps <= GEMM_MAX_TAPS, "gemm: bad num_taps");
 #define GDRN_GEMM_CASE(BN, E) \
   if (block_n == BN && plan.epi == E) return launch_inst<BN, E>(plan, stream);
   GDRN_GEMM_CASE(256, EPI_GELU)

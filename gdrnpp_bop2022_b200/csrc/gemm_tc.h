@@ -1,6 +1,6 @@
 // Internal C++ interface of the tcgen05/TMA implicit-GEMM kernel (gemm_tc.cu).
 //
-//   D[m, n] = sum_{tap} sum_{k} A_tap[m, k] * W[n, tap*b_tap_stride + k]      (bf16 x bf16 -> fp32 in TMEM)
+//   D[m, n] = sum_{tap} sum_{k} A_tap[m, k] * W[n, tap.b_off + k]      (bf16 x bf16 -> fp32 in TMEM)
 //
 // A rows are pixels of an NHWC activation tensor: a 128-row tile is a (bw x bh x bb) box of pixels
 // fetched by one TMA box load per (tap, 64-channel chunk); conv padding = TMA out-of-bounds zero fill.
@@ -19,11 +19,14 @@ enum GemmEpilogue : int {
 };
 
 struct GemmTap {
-  int c0;  // added to coordinate 0 (channel offset; e.g. x-parity * C for the stride-2 view)
-  int d1;  // added to coordinate 1 (x)
-  int d2;  // rank 4: added to y.  rank 5: absolute coordinate 2 (y parity)
-  int d3;  // rank 5: added to y (coordinate 3)
+  int c0;     // added to coordinate 0 (channel offset; e.g. x-parity * C for the stride-2 view, or the lo-half offset)
+  int d1;     // added to coordinate 1 (x; rank 2: row offset)
+  int d2;     // rank 4: added to y.  rank 5: absolute coordinate 2 (y parity)
+  int d3;     // rank 5: added to y (coordinate 3)
+  int b_off;  // K offset of this tap inside a row of W (elements)
 };
+
+constexpr int GEMM_MAX_TAPS = 27;  // 9 spatial taps x 3 split-bf16 products
 
 struct GemmPlan {
   // ---- A operand ----
@@ -32,11 +35,10 @@ struct GemmPlan {
   int lg_bw, lg_bh, lg_bb;  // log2 of the pixel box (bw*bh*bb == 128); rank 2 ignores them
   int tiles_x, tiles_y;     // tiles per image along x / y (rank 4/5)
   int num_taps;
-  GemmTap taps[9];
+  GemmTap taps[GEMM_MAX_TAPS];
   int k_chunks;         // ceil(K_per_tap / 64)
   // ---- B operand ----
   CUtensorMap tmap_b;   // 2D [rows][K_total] bf16, K-major
-  int b_tap_stride;     // elements between taps along K in W
   int b_rows_per_class; // EPI_OUTCONV: row offset multiplier for the ROI class (0 otherwise)
   // ---- problem ----
   int m_tiles, n_tiles;
@@ -45,7 +47,8 @@ struct GemmPlan {
   // ---- epilogue ----
   int epi;
   int out_f32;          // EPI_STORE / EPI_GNSTATS: 1 -> fp32 output, 0 -> bf16
-  int gelu_mode;        // EPI_GELU: 0 = fp32 ex2/rcp form (1.2e-5 of erf), 1 = packed half2 tanh.approx (faster, ~7e-4)
+  int gelu_mode;        // EPI_GELU: 0 = fp32 ex2/rcp form (1.2e-5 of erf), 1 = packed half2 tanh.approx, 2 = fp32 tanh.approx, 3 = erff
+  int split;            // bf16 outputs are written as [hi | lo] pairs (row width 2N, lo = bf16(v - hi)): split-bf16 (x3) mode
   void* out;            // [rows, ldo]
   long long ldo;        // output row stride (elements)
   int OH, OW, osy, osx, ooy, oox;  // rank 4/5: out row = (b*OH + y*osy+ooy)*OW + x*osx+oox

@@ -10,6 +10,12 @@
 //   P,Q   bf16  [B,64,64,256] post GN+GELU(+bilinear) activations (ping-pong)
 //   pnp_in bf16 [B,64,64,128] Patch-PnP input assembled by the out-conv epilogue
 // Weights: bf16 [N][taps*K] K-major per GEMM, fp32 vectors for bias / gamma / norm affine.
+//
+// Precision 1 ("bf16x3", split-bf16): every bf16 GEMM operand v is stored as the pair hi = bf16(v), lo = bf16(v - hi)
+// -- activations as rows [hi C | lo C], weights as rows [hi Ktot | lo Ktot] -- and every GEMM accumulates the three
+// products A_lo*W_hi + A_hi*W_lo + A_hi*W_hi in the same fp32 TMEM accumulator (operand error 2^-17 instead of
+// 2^-9).  Head conv outputs stay fp32 until GroupNorm, GELU is the exact erf form, and the Patch-PnP FC stack runs
+// in fp32 on the CUDA cores.  Used to meet the 1e-4 rad / 1e-3 parity bar of BASELINE.json against the fp32 oracle.
 #include <algorithm>
 #include <map>
 #include <string>
@@ -60,6 +66,7 @@ struct GdrnModel {
   int num_classes;
   int max_batch;
   int in_res = 256, out_res = 64;
+  int precise = 0;    // 0: bf16 operands (fast); 1: split-bf16 x3 products, fp32 FC stack, erf GELU
   int gelu_mode = 1;  // fc1 epilogue GELU: 1 = packed-half2 tanh.approx (default, fastest), 0 = fp32 ex2/rcp form, 2 = fp32 tanh.approx; env GDRN_GELU_MODE
   // ---- weights (device) ----
   std::vector<void*> allocs;
@@ -82,6 +89,7 @@ struct GdrnModel {
   float* pfc2_b;
   __nv_bfloat16* pfcrt_w;      // [16][256]: rows 0-5 fc_r, 6-8 fc_t, rest 0
   float* pfcrt_b;              // [16]
+  float *pfc1_wf = nullptr, *pfc2_wf = nullptr, *pfcrt_wf = nullptr;  // precise mode: fp32 copies (same layouts)
   // ---- loader ----
   std::map<std::string, std::vector<LoadOp>> loaders;
   std::map<std::string, bool> loaded;
@@ -119,32 +127,34 @@ void add_loader(GdrnModel* m, const std::string& key, void* dst, int is_bf16, Pa
 
 PackDesc pd(long long d0, long long d1, long long d2, long long d3, long long s0, long long s1, long long s2,
             long long s3, long long t0, long long t1, long long t2, long long t3, long long soff = 0,
-            long long doff = 0) {
+            long long doff = 0, long long lo = 0) {
   PackDesc d;
   d.dims[0] = d0; d.dims[1] = d1; d.dims[2] = d2; d.dims[3] = d3;
   d.ss[0] = s0; d.ss[1] = s1; d.ss[2] = s2; d.ss[3] = s3;
   d.ds[0] = t0; d.ds[1] = t1; d.ds[2] = t2; d.ds[3] = t3;
-  d.soff = soff; d.doff = doff;
+  d.soff = soff; d.doff = doff; d.lo_delta = lo;
   return d;
 }
 
 // plain copy of a vector / matrix [r][c] -> [r][ldc]
 void add_copy(GdrnModel* m, const std::string& key, void* dst, int is_bf16, long long rows, long long cols,
-              long long ld_dst, long long doff = 0) {
-  add_loader(m, key, dst, is_bf16, pd(1, 1, rows, cols, 0, 0, cols, 1, 0, 0, ld_dst, 1, 0, doff), rows * cols);
+              long long ld_dst, long long doff = 0, long long lo = 0) {
+  add_loader(m, key, dst, is_bf16, pd(1, 1, rows, cols, 0, 0, cols, 1, 0, 0, ld_dst, 1, 0, doff, lo), rows * cols);
 }
 
 bool build_weights(GdrnModel* m) {
   const Arch& a = m->arch;
   const int C0 = a.dims[0], C3 = a.dims[3];
   const int nc = m->num_classes;
+  const int S = m->precise ? 2 : 1;  // bf16 weight rows are [hi Ktot | lo Ktot] in precise mode
+  auto LO = [&](long long ktot) { return S == 2 ? ktot : 0LL; };
   bool ok = true;
 #define ALLOC(ptr, T, n) ok = ok && ((ptr = dalloc<T>(m, (n))) != nullptr)
   // ---- stem ----
-  ALLOC(m->stem_w, __nv_bfloat16, (size_t)C0 * 64);
+  ALLOC(m->stem_w, __nv_bfloat16, (size_t)S * C0 * 64);
   ALLOC(m->stem_b, float, C0); ALLOC(m->stem_ln_w, float, C0); ALLOC(m->stem_ln_b, float, C0);
   if (!ok) return false;
-  add_copy(m, "backbone.stem_0.weight", m->stem_w, 1, C0, 48, 64);
+  add_copy(m, "backbone.stem_0.weight", m->stem_w, 1, C0, 48, S * 64, 0, LO(64));
   add_copy(m, "backbone.stem_0.bias", m->stem_b, 0, 1, C0, C0);
   add_copy(m, "backbone.stem_1.weight", m->stem_ln_w, 0, 1, C0, C0);
   add_copy(m, "backbone.stem_1.bias", m->stem_ln_b, 0, 1, C0, C0);
@@ -154,22 +164,22 @@ bool build_weights(GdrnModel* m) {
     if (s > 0) {
       const int Ci = a.dims[s - 1];
       ALLOC(m->down[s].ln_w, float, Ci); ALLOC(m->down[s].ln_b, float, Ci);
-      ALLOC(m->down[s].w, __nv_bfloat16, (size_t)C * 4 * Ci);
+      ALLOC(m->down[s].w, __nv_bfloat16, (size_t)S * C * 4 * Ci);
       ALLOC(m->down[s].b, float, C);
       if (!ok) return false;
       snprintf(buf, sizeof(buf), "backbone.stages_%d.downsample.0.weight", s); add_copy(m, buf, m->down[s].ln_w, 0, 1, Ci, Ci);
       snprintf(buf, sizeof(buf), "backbone.stages_%d.downsample.0.bias", s); add_copy(m, buf, m->down[s].ln_b, 0, 1, Ci, Ci);
       // [C][Ci][2][2] -> [C][tap][Ci]
       snprintf(buf, sizeof(buf), "backbone.stages_%d.downsample.1.weight", s);
-      add_loader(m, buf, m->down[s].w, 1, pd(1, C, 4, Ci, 0, (long long)Ci * 4, 1, 4, 0, (long long)4 * Ci, Ci, 1), (long long)C * Ci * 4);
+      add_loader(m, buf, m->down[s].w, 1, pd(1, C, 4, Ci, 0, (long long)Ci * 4, 1, 4, 0, (long long)S * 4 * Ci, Ci, 1, 0, 0, LO(4 * Ci)), (long long)C * Ci * 4);
       snprintf(buf, sizeof(buf), "backbone.stages_%d.downsample.1.bias", s); add_copy(m, buf, m->down[s].b, 0, 1, C, C);
     }
     m->blocks[s].resize(a.depths[s]);
     for (int i = 0; i < a.depths[s]; ++i) {
       BlockW& w = m->blocks[s][i];
       ALLOC(w.dw_w, float, (size_t)49 * C); ALLOC(w.dw_b, float, C); ALLOC(w.ln_w, float, C); ALLOC(w.ln_b, float, C);
-      ALLOC(w.fc1_w, __nv_bfloat16, (size_t)4 * C * C); ALLOC(w.fc1_b, float, 4 * C);
-      ALLOC(w.fc2_w, __nv_bfloat16, (size_t)4 * C * C); ALLOC(w.fc2_b, float, C); ALLOC(w.gamma, float, C);
+      ALLOC(w.fc1_w, __nv_bfloat16, (size_t)S * 4 * C * C); ALLOC(w.fc1_b, float, 4 * C);
+      ALLOC(w.fc2_w, __nv_bfloat16, (size_t)S * 4 * C * C); ALLOC(w.fc2_b, float, C); ALLOC(w.gamma, float, C);
       if (!ok) return false;
       std::string p = "backbone.stages_" + std::to_string(s) + ".blocks." + std::to_string(i) + ".";
       // conv_dw.weight [C][1][7][7] -> [49][C]
@@ -177,9 +187,9 @@ bool build_weights(GdrnModel* m) {
       add_copy(m, p + "conv_dw.bias", w.dw_b, 0, 1, C, C);
       add_copy(m, p + "norm.weight", w.ln_w, 0, 1, C, C);
       add_copy(m, p + "norm.bias", w.ln_b, 0, 1, C, C);
-      add_copy(m, p + "mlp.fc1.weight", w.fc1_w, 1, 4 * C, C, C);
+      add_copy(m, p + "mlp.fc1.weight", w.fc1_w, 1, 4 * C, C, S * C, 0, LO(C));
       add_copy(m, p + "mlp.fc1.bias", w.fc1_b, 0, 1, 4 * C, 4 * C);
-      add_copy(m, p + "mlp.fc2.weight", w.fc2_w, 1, C, 4 * C, 4 * C);
+      add_copy(m, p + "mlp.fc2.weight", w.fc2_w, 1, C, 4 * C, S * 4 * C, 0, LO(4 * C));
       add_copy(m, p + "mlp.fc2.bias", w.fc2_b, 0, 1, C, C);
       add_copy(m, p + "gamma", w.gamma, 0, 1, C, C);
     }
@@ -190,12 +200,13 @@ bool build_weights(GdrnModel* m) {
     for (int px = 0; px < 2; ++px) {
       const int nty = py ? 2 : 1, ntx = px ? 2 : 1;
       const int par = py * 2 + px;
-      ALLOC(m->deconv_w[par], __nv_bfloat16, (size_t)256 * nty * ntx * C3);
+      ALLOC(m->deconv_w[par], __nv_bfloat16, (size_t)S * 256 * nty * ntx * C3);
       if (!ok) return false;
       // dst [o][jy][jx][i]; src index = i*256*9 + o*9 + (ky*3+kx), ky = py ? 2*jy : 1, kx = px ? 2*jx : 1
       const long long soff = (py ? 0 : 3) + (px ? 0 : 1);
       // dims (o, jy, jx, i)
-      PackDesc d = pd(256, nty, ntx, C3, 9, 6, 2, (long long)256 * 9, (long long)nty * ntx * C3, (long long)ntx * C3, C3, 1, soff, 0);
+      PackDesc d = pd(256, nty, ntx, C3, 9, 6, 2, (long long)256 * 9, (long long)S * nty * ntx * C3, (long long)ntx * C3, C3, 1, soff, 0,
+                      LO((long long)nty * ntx * C3));
       add_loader(m, "geo_head_net.features.0.weight", m->deconv_w[par], 1, d, (long long)C3 * 256 * 9);
     }
   const char* gn_names[7] = {"features.1", "features.3.gn", "features.4.gn", "features.6.gn",
@@ -208,20 +219,20 @@ bool build_weights(GdrnModel* m) {
   }
   const int conv_ids[6] = {3, 4, 6, 7, 9, 10};
   for (int i = 0; i < 6; ++i) {
-    ALLOC(m->hconv_w[i], __nv_bfloat16, (size_t)256 * 9 * 256);
+    ALLOC(m->hconv_w[i], __nv_bfloat16, (size_t)S * 256 * 9 * 256);
     if (!ok) return false;
     // [O][I][3][3] -> [O][tap][I]
     add_loader(m, "geo_head_net.features." + std::to_string(conv_ids[i]) + ".conv.weight", m->hconv_w[i], 1,
-               pd(1, 256, 9, 256, 0, 256 * 9, 1, 9, 0, 9 * 256, 256, 1), 256LL * 256 * 9);
+               pd(1, 256, 9, 256, 0, 256 * 9, 1, 9, 0, S * 9 * 256, 256, 1, 0, 0, LO(9 * 256)), 256LL * 256 * 9);
   }
   // out layer: [nc*70][256] -> gathered [nc][80][256], rows: vis c | full nc+c | x 2nc+c | y 3nc+c | z 4nc+c | region 5nc+65c+j
-  ALLOC(m->out_w, __nv_bfloat16, (size_t)nc * 80 * 256);
+  ALLOC(m->out_w, __nv_bfloat16, (size_t)S * nc * 80 * 256);
   ALLOC(m->out_b, float, (size_t)nc * 80);
   if (!ok) return false;
   add_loader(m, "geo_head_net.out_layer.weight", m->out_w, 1,
-             pd(1, nc, 5, 256, 0, 256, (long long)nc * 256, 1, 0, 80 * 256, 256, 1), (long long)nc * 70 * 256);
+             pd(1, nc, 5, 256, 0, 256, (long long)nc * 256, 1, 0, S * 80 * 256, S * 256, 1, 0, 0, LO(256)), (long long)nc * 70 * 256);
   add_loader(m, "geo_head_net.out_layer.weight", m->out_w, 1,
-             pd(1, nc, 65, 256, 0, 65 * 256, 256, 1, 0, 80 * 256, 256, 1, (long long)5 * nc * 256, 5 * 256),
+             pd(1, nc, 65, 256, 0, 65 * 256, 256, 1, 0, S * 80 * 256, S * 256, 1, (long long)5 * nc * 256, S * 5 * 256, LO(256)),
              (long long)nc * 70 * 256);
   add_loader(m, "geo_head_net.out_layer.bias", m->out_b, 0, pd(1, 1, nc, 5, 0, 0, 1, nc, 0, 0, 80, 1), (long long)nc * 70);
   add_loader(m, "geo_head_net.out_layer.bias", m->out_b, 0, pd(1, 1, nc, 65, 0, 0, 65, 1, 0, 0, 80, 1, 5LL * nc, 5),
@@ -229,11 +240,11 @@ bool build_weights(GdrnModel* m) {
   // ---- Patch-PnP ----
   for (int i = 0; i < 3; ++i) {
     const int cin = i == 0 ? 69 : 128;
-    ALLOC(m->pconv_w[i], __nv_bfloat16, (size_t)128 * 9 * 128);
+    ALLOC(m->pconv_w[i], __nv_bfloat16, (size_t)S * 128 * 9 * 128);
     ALLOC(m->pgn_w[i], float, 128); ALLOC(m->pgn_b[i], float, 128);
     if (!ok) return false;
     add_loader(m, "pnp_net.features." + std::to_string(i * 3) + ".weight", m->pconv_w[i], 1,
-               pd(1, 128, 9, cin, 0, (long long)cin * 9, 1, 9, 0, 9 * 128, 128, 1), 128LL * cin * 9);
+               pd(1, 128, 9, cin, 0, (long long)cin * 9, 1, 9, 0, S * 9 * 128, 128, 1, 0, 0, LO(9 * 128)), 128LL * cin * 9);
     add_copy(m, "pnp_net.features." + std::to_string(i * 3 + 1) + ".weight", m->pgn_w[i], 0, 1, 128, 128);
     add_copy(m, "pnp_net.features." + std::to_string(i * 3 + 1) + ".bias", m->pgn_b[i], 0, 1, 128, 128);
   }
@@ -250,6 +261,15 @@ bool build_weights(GdrnModel* m) {
   add_copy(m, "pnp_net.fc_t.weight", m->pfcrt_w, 1, 3, 256, 256, 6 * 256);
   add_copy(m, "pnp_net.fc_r.bias", m->pfcrt_b, 0, 1, 6, 6, 0);
   add_copy(m, "pnp_net.fc_t.bias", m->pfcrt_b, 0, 1, 3, 3, 6);
+  if (m->precise) {  // fp32 FC stack
+    ALLOC(m->pfc1_wf, float, (size_t)1024 * 8192); ALLOC(m->pfc2_wf, float, (size_t)256 * 1024);
+    ALLOC(m->pfcrt_wf, float, (size_t)16 * 256);
+    if (!ok) return false;
+    add_loader(m, "pnp_net.fc1.weight", m->pfc1_wf, 0, pd(1, 1024, 64, 128, 0, 8192, 1, 64, 0, 8192, 128, 1), 1024LL * 8192);
+    add_copy(m, "pnp_net.fc2.weight", m->pfc2_wf, 0, 256, 1024, 1024);
+    add_copy(m, "pnp_net.fc_r.weight", m->pfcrt_wf, 0, 6, 256, 256, 0);
+    add_copy(m, "pnp_net.fc_t.weight", m->pfcrt_wf, 0, 3, 256, 256, 6 * 256);
+  }
 #undef ALLOC
   return ok;
 }
@@ -264,6 +284,7 @@ struct Workspace {
   __nv_bfloat16* pnp_in;
   __nv_bfloat16 *pR, *pP;
   __nv_bfloat16 *f1, *f2;
+  float *pF, *f1f, *f2f;  // precise mode: fp32 Patch-PnP feature [B,8192] and FC activations
   float* fout;      // [B][16]
   double* gn_stats; // [10][B][32][2]
   float* gn_mr;     // [B][32][2] mean / rstd scratch of the layer being applied
@@ -279,6 +300,7 @@ Workspace carve(const GdrnModel* m, int B, void* base) {
   size_t off = 0;
   auto take = [&](size_t bytes) { uint8_t* r = p ? p + off : nullptr; off += align_up(bytes); return r; };
   const size_t M0 = (size_t)B * 64 * 64;
+  const size_t S = m->precise ? 2 : 1;  // split-bf16 rows are twice as wide
   size_t x_el = 0, a_el = M0 * 64, h_el = 0;
   for (int s = 0; s < 4; ++s) {
     size_t Ms = M0 >> (2 * s);
@@ -287,15 +309,18 @@ Workspace carve(const GdrnModel* m, int B, void* base) {
     h_el = std::max(h_el, Ms * a.dims[s] * 4);
   }
   w.X = reinterpret_cast<float*>(take(x_el * 4));
-  w.A = reinterpret_cast<__nv_bfloat16*>(take(a_el * 2));
-  w.Hb = reinterpret_cast<__nv_bfloat16*>(take(h_el * 2));
-  w.feat = reinterpret_cast<__nv_bfloat16*>(take((size_t)B * 64 * a.dims[3] * 2));
-  w.R = reinterpret_cast<__nv_bfloat16*>(take(M0 * 256 * 2));
-  w.P = reinterpret_cast<__nv_bfloat16*>(take(M0 * 256 * 2));
-  w.Q = reinterpret_cast<__nv_bfloat16*>(take(M0 * 256 * 2));
-  w.pnp_in = reinterpret_cast<__nv_bfloat16*>(take(M0 * 128 * 2));
-  w.pR = reinterpret_cast<__nv_bfloat16*>(take((size_t)B * 32 * 32 * 128 * 2));
-  w.pP = reinterpret_cast<__nv_bfloat16*>(take((size_t)B * 32 * 32 * 128 * 2));
+  w.A = reinterpret_cast<__nv_bfloat16*>(take(S * a_el * 2));
+  w.Hb = reinterpret_cast<__nv_bfloat16*>(take(S * h_el * 2));
+  w.feat = reinterpret_cast<__nv_bfloat16*>(take(S * B * 64 * a.dims[3] * 2));
+  w.R = reinterpret_cast<__nv_bfloat16*>(take(S * M0 * 256 * 2));  // precise: fp32 [M0,256]
+  w.P = reinterpret_cast<__nv_bfloat16*>(take(S * M0 * 256 * 2));
+  w.Q = reinterpret_cast<__nv_bfloat16*>(take(S * M0 * 256 * 2));
+  w.pnp_in = reinterpret_cast<__nv_bfloat16*>(take(S * M0 * 128 * 2));
+  w.pR = reinterpret_cast<__nv_bfloat16*>(take(S * B * 32 * 32 * 128 * 2));  // precise: fp32
+  w.pP = reinterpret_cast<__nv_bfloat16*>(take(S * B * 32 * 32 * 128 * 2));
+  w.pF = reinterpret_cast<float*>(take(m->precise ? (size_t)B * 8192 * 4 : 0));
+  w.f1f = reinterpret_cast<float*>(take(m->precise ? (size_t)B * 1024 * 4 : 0));
+  w.f2f = reinterpret_cast<float*>(take(m->precise ? (size_t)B * 256 * 4 : 0));
   w.f1 = reinterpret_cast<__nv_bfloat16*>(take((size_t)B * 1024 * 2));
   w.f2 = reinterpret_cast<__nv_bfloat16*>(take((size_t)B * 256 * 2));
   w.fout = reinterpret_cast<float*>(take((size_t)B * 16 * 4));
@@ -308,22 +333,23 @@ Workspace carve(const GdrnModel* m, int B, void* base) {
 int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 // A = plain [M,K] rows
-int plan_a2d(GemmPlan& p, const void* A, long long M, int K) {
-  uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
-  uint64_t str[1] = {(uint64_t)K * 2};
+// S = 2: rows are [hi K | lo K] (split-bf16); the tap list is expanded by expand_x3() afterwards
+int plan_a2d(GemmPlan& p, const void* A, long long M, int K, int S = 1) {
+  uint64_t dims[2] = {(uint64_t)S * K, (uint64_t)M};
+  uint64_t str[1] = {(uint64_t)S * K * 2};
   uint32_t box[2] = {64, 128};
   p.a_rank = 2;
   p.num_taps = 1;
-  p.taps[0] = {0, 0, 0, 0};
+  p.taps[0] = {0, 0, 0, 0, 0};
   p.k_chunks = (K + 63) / 64;
   p.m_tiles = (int)((M + 127) / 128);
   p.M = (int)M;
   return make_tmap_bf16(&p.tmap_a, A, 2, dims, str, box);
 }
 
-int plan_b(GemmPlan& p, const void* W, long long rows, long long Ktot, int block_n, int N) {
-  uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)rows};
-  uint64_t str[1] = {(uint64_t)Ktot * 2};
+int plan_b(GemmPlan& p, const void* W, long long rows, long long Ktot, int block_n, int N, int S = 1) {
+  uint64_t dims[2] = {(uint64_t)S * Ktot, (uint64_t)rows};
+  uint64_t str[1] = {(uint64_t)S * Ktot * 2};
   uint32_t box[2] = {64, (uint32_t)block_n};
   p.N = N;
   p.n_tiles = (N + block_n - 1) / block_n;
@@ -331,12 +357,13 @@ int plan_b(GemmPlan& p, const void* W, long long rows, long long Ktot, int block
 }
 
 // A = NHWC [B,H,W,C] pixel boxes; output grid OHxOW = (H*osy, W*osx) handled by the caller's mapping fields
-int plan_a4d(GemmPlan& p, const void* act, int B, int H, int W, int C) {
+int plan_a4d(GemmPlan& p, const void* act, int B, int H, int W, int C, int S = 1) {
   int bw = W >= 128 ? 128 : W;
   int bh = 128 / bw; if (bh > H) bh = H;
   int bb = 128 / (bw * bh);
-  uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-  uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+  const uint64_t RC_ = (uint64_t)S * C;  // row (pixel) width in elements
+  uint64_t dims[4] = {RC_, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  uint64_t str[3] = {RC_ * 2, (uint64_t)W * RC_ * 2, (uint64_t)H * W * RC_ * 2};
   uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb};
   p.a_rank = 4;
   p.lg_bw = ilog2(bw); p.lg_bh = ilog2(bh); p.lg_bb = ilog2(bb);
@@ -348,13 +375,14 @@ int plan_a4d(GemmPlan& p, const void* act, int B, int H, int W, int C) {
 }
 
 // stride-2 view of NHWC [B,H,W,C]: (2C, W/2, 2, H/2, B); output grid (H/2 x W/2)
-int plan_a5d_s2(GemmPlan& p, const void* act, int B, int H, int W, int C) {
+int plan_a5d_s2(GemmPlan& p, const void* act, int B, int H, int W, int C, int S = 1) {
   const int OW = W / 2, OH = H / 2;
   int bw = OW >= 128 ? 128 : OW;
   int bh = 128 / bw; if (bh > OH) bh = OH;
   int bb = 128 / (bw * bh);
-  uint64_t dims[5] = {(uint64_t)2 * C, (uint64_t)OW, 2, (uint64_t)OH, (uint64_t)B};
-  uint64_t str[4] = {(uint64_t)2 * C * 2, (uint64_t)W * C * 2, (uint64_t)2 * W * C * 2, (uint64_t)H * W * C * 2};
+  const uint64_t RC_ = (uint64_t)S * C;
+  uint64_t dims[5] = {2 * RC_, (uint64_t)OW, 2, (uint64_t)OH, (uint64_t)B};
+  uint64_t str[4] = {2 * RC_ * 2, (uint64_t)W * RC_ * 2, (uint64_t)2 * W * RC_ * 2, (uint64_t)H * W * RC_ * 2};
   uint32_t box[5] = {64, (uint32_t)bw, 1, (uint32_t)bh, (uint32_t)bb};
   p.a_rank = 5;
   p.lg_bw = ilog2(bw); p.lg_bh = ilog2(bh); p.lg_bb = ilog2(bb);
@@ -363,6 +391,19 @@ int plan_a5d_s2(GemmPlan& p, const void* act, int B, int H, int W, int C) {
   p.m_tiles = p.tiles_x * p.tiles_y * ((B + bb - 1) / bb);
   p.M = B;
   return make_tmap_bf16(&p.tmap_a, act, 5, dims, str, box);
+}
+
+// split-bf16: every tap becomes the three products (A lo, W hi) + (A hi, W lo) + (A hi, W hi), small terms first
+void expand_x3(GemmPlan& p, int a_lo_c0, int b_lo_off) {
+  const int n = p.num_taps;
+  for (int t = n - 1; t >= 0; --t) {
+    const GemmTap h = p.taps[t];
+    GemmTap al = h; al.c0 += a_lo_c0;
+    GemmTap bl = h; bl.b_off += b_lo_off;
+    p.taps[t] = al; p.taps[n + t] = bl; p.taps[2 * n + t] = h;
+  }
+  p.num_taps = 3 * n;
+  p.split = 1;
 }
 
 #define RC(expr) do { int _rc = (expr); if (_rc != GDRN_OK) return _rc; } while (0)
@@ -387,7 +428,16 @@ void prof_end(GdrnModel* m, cudaStream_t st) {
 
 // ================================================================================================
 extern "C" int gdrn_model_create(GdrnModel** out, const char* arch, int num_classes, int max_batch) {
+  int precision = 0;
+  if (const char* e = getenv("GDRN_PRECISION")) precision = atoi(e);
+  return gdrn_model_create_ex(out, arch, num_classes, max_batch, precision);
+}
+
+extern "C" int gdrn_model_precision(const GdrnModel* m) { return m ? m->precise : -1; }
+
+extern "C" int gdrn_model_create_ex(GdrnModel** out, const char* arch, int num_classes, int max_batch, int precision) {
   GDRN_REQUIRE(out != nullptr && arch != nullptr, "model_create: null argument");
+  GDRN_REQUIRE(precision == 0 || precision == 1, "model_create: precision must be 0 (bf16) or 1 (split-bf16 x3)");
   Arch a;
   GDRN_REQUIRE(get_arch(arch, &a), "model_create: unknown arch (convnext_base | convnext_small | convnext_tiny)");
   GDRN_REQUIRE(num_classes >= 1 && num_classes <= 64 && max_batch >= 1, "model_create: bad num_classes / max_batch");
@@ -395,6 +445,7 @@ extern "C" int gdrn_model_create(GdrnModel** out, const char* arch, int num_clas
   m->arch = a;
   m->num_classes = num_classes;
   m->max_batch = max_batch;
+  m->precise = precision;
   if (const char* e = getenv("GDRN_GELU_MODE")) m->gelu_mode = atoi(e);
   if (!build_weights(m)) {
     gdrn_model_destroy(m);
@@ -475,16 +526,20 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
 
   GemmPlan p;
   auto reset = [&]() { memset(&p, 0, sizeof(p)); p.ldo = 0; };
+  const int PR = m->precise;
+  const int S = PR ? 2 : 1;
+  const int gelu_mode = PR ? 3 : m->gelu_mode;
 
   // ---------------- stem: 4x4/s4 conv as GEMM (K=48 padded to 64) + bias + LayerNorm2d in the epilogue ----------------
   const long long M0 = (long long)B * 64 * 64;
-  RCP(2, launch_stem_patchify(roi_img, w.A, B, 256, 256, st));
+  RCP(2, launch_stem_patchify(roi_img, w.A, B, 256, 256, PR, st));
   {
     const int C0 = a.dims[0];
     reset();
-    RC(plan_a2d(p, w.A, M0, 64));
+    RC(plan_a2d(p, w.A, M0, 64, S));
     if (C0 == 128) {
-      RC(plan_b(p, m->stem_w, C0, 64, 128, C0));
+      RC(plan_b(p, m->stem_w, C0, 64, 128, C0, S));
+      if (PR) expand_x3(p, 64, 64);
       p.epi = EPI_BIAS_LN; p.out = w.X; p.ldo = C0; p.bias = m->stem_b;
       p.ln_w = m->stem_ln_w; p.ln_b = m->stem_ln_b; p.ln_eps = 1e-6f;
       RCP(0, gemm_tc_launch(p, 128, st));
@@ -499,35 +554,39 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
     const int C = a.dims[s];
     if (s > 0) {
       const int Ci = a.dims[s - 1];
-      RCP(2, launch_ln_patchify2(w.X, m->down[s].ln_w, m->down[s].ln_b, w.A, B, res, res, Ci, 1e-6f, st));
+      RCP(2, launch_ln_patchify2(w.X, m->down[s].ln_w, m->down[s].ln_b, w.A, B, res, res, Ci, 1e-6f, PR, st));
       res /= 2;
       const long long M = (long long)B * res * res;
       reset();
-      RC(plan_a2d(p, w.A, M, 4 * Ci));
+      RC(plan_a2d(p, w.A, M, 4 * Ci, S));
       const int bn = 256;
-      RC(plan_b(p, m->down[s].w, C, 4 * Ci, bn, C));
+      RC(plan_b(p, m->down[s].w, C, 4 * Ci, bn, C, S));
+      if (PR) expand_x3(p, 4 * Ci, 4 * Ci);
       p.epi = EPI_STORE; p.out_f32 = 1; p.out = w.X; p.ldo = C; p.bias = m->down[s].b;
       RCP(0, gemm_tc_launch(p, bn, st));
     }
     const long long M = (long long)B * res * res;
     for (int i = 0; i < a.depths[s]; ++i) {
       const BlockW& bw = m->blocks[s][i];
-      RCP(1, launch_dwconv_ln(w.X, bw.dw_w, bw.dw_b, bw.ln_w, bw.ln_b, w.A, B, res, res, C, 1e-6f, st));
+      RCP(1, launch_dwconv_ln(w.X, bw.dw_w, bw.dw_b, bw.ln_w, bw.ln_b, w.A, B, res, res, C, 1e-6f, PR, st));
       reset();
-      RC(plan_a2d(p, w.A, M, C));
-      RC(plan_b(p, bw.fc1_w, 4 * C, C, 256, 4 * C));
-      p.epi = EPI_GELU; p.gelu_mode = m->gelu_mode; p.out = w.Hb; p.ldo = 4 * C; p.bias = bw.fc1_b;
+      RC(plan_a2d(p, w.A, M, C, S));
+      RC(plan_b(p, bw.fc1_w, 4 * C, C, 256, 4 * C, S));
+      if (PR) expand_x3(p, C, C);
+      p.epi = EPI_GELU; p.gelu_mode = gelu_mode; p.out = w.Hb; p.ldo = S * 4 * C; p.bias = bw.fc1_b;
       RCP(0, gemm_tc_launch(p, 256, st));
       reset();
-      RC(plan_a2d(p, w.Hb, M, 4 * C));
+      RC(plan_a2d(p, w.Hb, M, 4 * C, S));
       const int bn2 = C >= 256 ? 256 : 128;
-      RC(plan_b(p, bw.fc2_w, C, 4 * C, bn2, C));
+      RC(plan_b(p, bw.fc2_w, C, 4 * C, bn2, C, S));
+      if (PR) expand_x3(p, 4 * C, 4 * C);
       p.epi = EPI_RESID; p.out_f32 = 1; p.out = w.X; p.resid = w.X; p.ldo = C; p.bias = bw.fc2_b; p.gamma = bw.gamma;
       RCP(0, gemm_tc_launch(p, bn2, st));
     }
   }
   const int C3 = a.dims[3];
-  RCP(2, launch_cast_bf16(w.X, w.feat, (long long)B * 64 * C3, st));
+  if (PR) RCP(2, launch_cast_split(w.X, w.feat, (long long)B * 64, C3, st));
+  else RCP(2, launch_cast_bf16(w.X, w.feat, (long long)B * 64 * C3, st));
 
   // ---------------- geometry head ----------------
   double* stats = w.gn_stats;
@@ -536,23 +595,24 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
   for (int py = 0; py < 2; ++py)
     for (int px = 0; px < 2; ++px) {
       reset();
-      RC(plan_a4d(p, w.feat, B, 8, 8, C3));
+      RC(plan_a4d(p, w.feat, B, 8, 8, C3, S));
       int nt = 0;
       for (int jy = 0; jy < (py ? 2 : 1); ++jy)
         for (int jx = 0; jx < (px ? 2 : 1); ++jx) {
           // ky = py ? 2*jy : 1 -> iy = a + (ky == 0 ? 1 : 0)
           const int dy = (py && jy == 0) ? 1 : 0, dx = (px && jx == 0) ? 1 : 0;
-          p.taps[nt++] = {0, dx, dy, 0};
+          p.taps[nt] = {0, dx, dy, 0, nt * C3};
+          ++nt;
         }
       p.num_taps = nt;
-      p.b_tap_stride = C3;
-      RC(plan_b(p, m->deconv_w[py * 2 + px], 256, (long long)nt * C3, 256, 256));
-      p.epi = EPI_GNSTATS; p.out_f32 = 0; p.out = w.R; p.ldo = 256;
+      RC(plan_b(p, m->deconv_w[py * 2 + px], 256, (long long)nt * C3, 256, 256, S));
+      if (PR) expand_x3(p, C3, nt * C3);
+      p.epi = EPI_GNSTATS; p.out_f32 = PR; p.out = w.R; p.ldo = 256;
       p.OH = 16; p.OW = 16; p.osy = 2; p.osx = 2; p.ooy = py; p.oox = px;
       p.gn_stats = stat_slot(0); p.gn_groups = 32; p.gn_cpg = 8;
       RCP(0, gemm_tc_launch(p, 256, st));
     }
-  RCP(2, launch_gn_gelu(w.R, 0, stat_slot(0), w.gn_mr, m->gn_w[0], m->gn_b[0], w.P, B, 16, 16, 256, 32, 1e-5f, st));
+  RCP(2, launch_gn_gelu(w.R, PR, stat_slot(0), w.gn_mr, m->gn_w[0], m->gn_b[0], w.P, B, 16, 16, 256, 32, 1e-5f, PR, st));
   __nv_bfloat16* cur = w.P;
   __nv_bfloat16* nxt = w.Q;
   int hres = 16;
@@ -560,24 +620,24 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
     for (int j = 0; j < 2; ++j) {
       const int li = blk * 2 + j;  // conv index 0..5, gn index li+1
       reset();
-      RC(plan_a4d(p, cur, B, hres, hres, 256));
-      for (int t = 0; t < 9; ++t) p.taps[t] = {0, t % 3 - 1, t / 3 - 1, 0};
+      RC(plan_a4d(p, cur, B, hres, hres, 256, S));
+      for (int t = 0; t < 9; ++t) p.taps[t] = {0, t % 3 - 1, t / 3 - 1, 0, t * 256};
       p.num_taps = 9;
-      p.b_tap_stride = 256;
-      RC(plan_b(p, m->hconv_w[li], 256, 9 * 256, 256, 256));
-      p.epi = EPI_GNSTATS; p.out_f32 = 0; p.out = w.R; p.ldo = 256;
+      RC(plan_b(p, m->hconv_w[li], 256, 9 * 256, 256, 256, S));
+      if (PR) expand_x3(p, 256, 9 * 256);
+      p.epi = EPI_GNSTATS; p.out_f32 = PR; p.out = w.R; p.ldo = 256;
       p.OH = hres; p.OW = hres; p.osy = 1; p.osx = 1; p.ooy = 0; p.oox = 0;
       p.gn_stats = stat_slot(li + 1); p.gn_groups = 32; p.gn_cpg = 8;
       RCP(0, gemm_tc_launch(p, 256, st));
       const int up = (j == 1 && blk < 2) ? 2 : 1;
       if (up == 1) {
-        RCP(2, launch_gn_gelu(w.R, 0, stat_slot(li + 1), w.gn_mr, m->gn_w[li + 1], m->gn_b[li + 1], nxt, B, hres, hres, 256, 32,
-                              1e-5f, st));
+        RCP(2, launch_gn_gelu(w.R, PR, stat_slot(li + 1), w.gn_mr, m->gn_w[li + 1], m->gn_b[li + 1], nxt, B, hres, hres, 256, 32,
+                              1e-5f, PR, st));
       } else {
         // GN + GELU at the low resolution into `cur` (the conv's input, dead now), then bilinear x2 into `nxt`
-        RCP(2, launch_gn_gelu(w.R, 0, stat_slot(li + 1), w.gn_mr, m->gn_w[li + 1], m->gn_b[li + 1], cur, B, hres, hres, 256, 32,
-                              1e-5f, st));
-        RCP(2, launch_upsample2x(cur, nxt, B, hres, hres, 256, st));
+        RCP(2, launch_gn_gelu(w.R, PR, stat_slot(li + 1), w.gn_mr, m->gn_w[li + 1], m->gn_b[li + 1], cur, B, hres, hres, 256, 32,
+                              1e-5f, PR, st));
+        RCP(2, launch_upsample2x(cur, nxt, B, hres, hres, 256, PR, st));
       }
       std::swap(cur, nxt);
       hres *= up;
@@ -585,8 +645,9 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
   }
   // out conv (class gathered) + Patch-PnP input assembly
   reset();
-  RC(plan_a2d(p, cur, M0, 256));
-  RC(plan_b(p, m->out_w, (long long)m->num_classes * 80, 256, 80, 80));
+  RC(plan_a2d(p, cur, M0, 256, S));
+  RC(plan_b(p, m->out_w, (long long)m->num_classes * 80, 256, 80, 80, S));
+  if (PR) expand_x3(p, 256, 256);
   p.n_tiles = 1;
   p.b_rows_per_class = 80;
   p.epi = EPI_OUTCONV;
@@ -612,42 +673,53 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
     for (int i = 0; i < 3; ++i) {
       const int ores = ires / 2;
       reset();
-      RC(plan_a5d_s2(p, in, B, ires, ires, 128));
+      RC(plan_a5d_s2(p, in, B, ires, ires, 128, S));
       // input (2*o + k - 1): k=0 -> parity 1, half index o-1; k=1 -> parity 0, o; k=2 -> parity 1, o
       for (int t = 0; t < 9; ++t) {
         const int ky = t / 3, kx = t % 3;
         const int pyy = (ky == 1) ? 0 : 1, dyy = (ky == 0) ? -1 : 0;
         const int pxx = (kx == 1) ? 0 : 1, dxx = (kx == 0) ? -1 : 0;
-        p.taps[t] = {pxx * 128, dxx, pyy, dyy};
+        p.taps[t] = {pxx * S * 128, dxx, pyy, dyy, t * 128};
       }
       p.num_taps = 9;
-      p.b_tap_stride = 128;
-      RC(plan_b(p, m->pconv_w[i], 128, 9 * 128, 128, 128));
-      p.epi = EPI_GNSTATS; p.out_f32 = 0; p.out = w.pR; p.ldo = 128;
+      RC(plan_b(p, m->pconv_w[i], 128, 9 * 128, 128, 128, S));
+      if (PR) expand_x3(p, 128, 9 * 128);
+      p.epi = EPI_GNSTATS; p.out_f32 = PR; p.out = w.pR; p.ldo = 128;
       p.OH = ores; p.OW = ores; p.osy = 1; p.osx = 1;
       p.gn_stats = stat_slot(7 + i); p.gn_groups = 32; p.gn_cpg = 4;
       RCP(0, gemm_tc_launch(p, 128, st));
-      RCP(2, launch_gn_gelu(w.pR, 0, stat_slot(7 + i), w.gn_mr, m->pgn_w[i], m->pgn_b[i], w.pP, B, ores, ores, 128, 32, 1e-5f, st));
+      if (PR && i == 2) {  // last feature map feeds the fp32 FC stack
+        RCP(2, launch_gn_gelu_f32(reinterpret_cast<const float*>(w.pR), stat_slot(7 + i), w.gn_mr, m->pgn_w[i], m->pgn_b[i], w.pF, B,
+                                  ores, ores, 128, 32, 1e-5f, st));
+      } else {
+        RCP(2, launch_gn_gelu(w.pR, PR, stat_slot(7 + i), w.gn_mr, m->pgn_w[i], m->pgn_b[i], w.pP, B, ores, ores, 128, 32, 1e-5f, PR, st));
+      }
       // ping-pong between pP and a second buffer is unnecessary: the conv reads pP (or pnp_in) and writes pR
       in = w.pP;
       ires = ores;
     }
     // FC stack: [B,8192] -> 1024 -> 256 -> 9
+    if (PR) {
+      RCP(2, launch_fc_f32(w.pF, m->pfc1_wf, m->pfc1_b, w.f1f, B, 1024, 8192, 1024, 1, st));
+      RCP(2, launch_fc_f32(w.f1f, m->pfc2_wf, m->pfc2_b, w.f2f, B, 256, 1024, 256, 1, st));
+      RCP(2, launch_fc_f32(w.f2f, m->pfcrt_wf, m->pfcrt_b, w.fout, B, 16, 256, 16, 0, st));
+    } else {
     reset();
     RC(plan_a2d(p, w.pP, B, 8192));
     RC(plan_b(p, m->pfc1_w, 1024, 8192, 64, 1024));
-    p.epi = EPI_GELU; p.out = w.f1; p.ldo = 1024; p.bias = m->pfc1_b;
+    p.epi = EPI_GELU; p.gelu_mode = 0; p.out = w.f1; p.ldo = 1024; p.bias = m->pfc1_b;
     RCP(0, gemm_tc_launch(p, 64, st));
     reset();
     RC(plan_a2d(p, w.f1, B, 1024));
     RC(plan_b(p, m->pfc2_w, 256, 1024, 64, 256));
-    p.epi = EPI_GELU; p.out = w.f2; p.ldo = 256; p.bias = m->pfc2_b;
+    p.epi = EPI_GELU; p.gelu_mode = 0; p.out = w.f2; p.ldo = 256; p.bias = m->pfc2_b;
     RCP(0, gemm_tc_launch(p, 64, st));
     reset();
     RC(plan_a2d(p, w.f2, B, 256));
     RC(plan_b(p, m->pfcrt_w, 16, 256, 16, 16));
     p.epi = EPI_STORE; p.out_f32 = 1; p.out = w.fout; p.ldo = 16; p.bias = m->pfcrt_b;
     RCP(0, gemm_tc_launch(p, 16, st));
+    }
   }
   RCP(2, launch_pose_lift(w.fout, 16, roi_cams, roi_centers, roi_whs, resize_ratios, out_rot, out_trans, out_raw, B, st));
   return GDRN_OK;
@@ -683,6 +755,10 @@ extern "C" int64_t gdrn_model_debug_read(GdrnModel* m, const char* name, int bat
   cudaStream_t st = (cudaStream_t)stream;
   const int C3 = m->arch.dims[3];
   long long n = 0;
+  if (m->precise && strcmp(name, "stage3_x") && strcmp(name, "fc_out")) {
+    gdrn_set_last_error(__FILE__, __LINE__, "debug_read: only stage3_x / fc_out are readable in split-bf16 mode");
+    return GDRN_ERR_INVALID;
+  }
   if (!strcmp(name, "conv_feat")) {
     n = (long long)batch * 64 * C3;
     if (launch_bf16_to_f32(w.feat, dst, n, st)) return GDRN_ERR_CUDA;

@@ -14,6 +14,7 @@ include/gdrn_b200.h).  There is no PyTorch/CPU fallback: without the library or 
 forward raises.
 """
 import ctypes
+import os
 from types import SimpleNamespace
 
 import torch
@@ -71,7 +72,10 @@ def _build_param_tree(root, shapes):
 
 
 class GDRN_DoubleMask(nn.Module):
-    def __init__(self, cfg, arch="convnext_base", max_batch=64):
+    def __init__(self, cfg, arch="convnext_base", max_batch=64, precision=None):
+        """precision: "bf16" (default; tensor-core bf16 operands, the reference's AMP regime) or "bf16x3"
+        (split-bf16 GEMMs + fp32 FC stack: reproduces the reference's fp32 forward, see include/gdrn_b200.h).
+        None -> cfg.MODEL.POSE_NET.PRECISION if present, else the GDRN_PRECISION environment variable, else bf16."""
         super().__init__()
         net_cfg = cfg.MODEL.POSE_NET
         assert net_cfg.NAME == "GDRN_double_mask", net_cfg.NAME
@@ -79,6 +83,13 @@ class GDRN_DoubleMask(nn.Module):
         self.arch = arch
         self.num_classes = int(net_cfg.NUM_CLASSES)
         self.max_batch = max_batch
+        if precision is None:
+            precision = getattr(net_cfg, "PRECISION", None)
+        if precision is None:
+            precision = {"0": "bf16", "1": "bf16x3"}.get(os.environ.get("GDRN_PRECISION", "0"), "bf16")
+        if precision not in ("bf16", "bf16x3"):
+            raise ValueError(f"precision must be 'bf16' or 'bf16x3', got {precision!r}")
+        self.precision = precision
         self.neck = None
         if arch not in CONVNEXT_ARCH:
             raise ValueError(f"unknown backbone {arch}")
@@ -111,8 +122,8 @@ class GDRN_DoubleMask(nn.Module):
         L = _lib.lib()
         if self._handle is None:
             h = ctypes.c_void_p()
-            _lib.check(L.gdrn_model_create(ctypes.byref(h), self.arch.encode(), self.num_classes, self.max_batch),
-                       "gdrn_model_create")
+            _lib.check(L.gdrn_model_create_ex(ctypes.byref(h), self.arch.encode(), self.num_classes, self.max_batch,
+                                              1 if self.precision == "bf16x3" else 0), "gdrn_model_create_ex")
             self._handle = h
         if self._loaded_version != self._param_version:
             st = _lib.current_stream()

@@ -41,6 +41,14 @@ typedef struct GdrnModel GdrnModel;
 
 /* arch: "convnext_base" | "convnext_small" | "convnext_tiny"; num_classes: class-aware head size (21). */
 int gdrn_model_create(GdrnModel** out, const char* arch, int num_classes, int max_batch);
+/* precision: 0 = bf16 tensor-core operands, fp32 accumulate / residual stream (the throughput mode; what the
+ *               reference's AMP test path does, engine_utils.py autocast);
+ *            1 = split-bf16 ("bf16x3"): every GEMM operand is the pair (hi, lo) of bf16 values and every GEMM
+ *               accumulates A_lo*W_hi + A_hi*W_lo + A_hi*W_hi in fp32; exact-erf GELU; fp32 Patch-PnP FC stack.
+ *               Reproduces the reference's fp32 forward to ~1e-5 relative (the BASELINE.json parity bar).
+ * gdrn_model_create() uses precision 0 unless the environment variable GDRN_PRECISION says otherwise. */
+int gdrn_model_create_ex(GdrnModel** out, const char* arch, int num_classes, int max_batch, int precision);
+int gdrn_model_precision(const GdrnModel* m);
 void gdrn_model_destroy(GdrnModel* m);
 
 /* Feed one fp32 tensor of a reference checkpoint (state_dict key names, e.g.

@@ -71,13 +71,19 @@ def test_gemm_gelu_modes(dev, lib, mode, monkeypatch):
 
 
 # ----------------------------------------------------------------------------------------------- model
-def _run_model(dev, B, seed, with_maps=True):
+def _run_model(dev, B, seed, with_maps=True, precision="bf16", trained_like_rot=False):
     from gdrnpp_bop2022_b200.gdrn_model import GDRN_DoubleMask, default_cfg
     from gdrnpp_bop2022_b200.synthetic import make_batch, make_state_dict
 
     sd = make_state_dict()
+    if trained_like_rot:
+        # The reference initialises fc_r with std 0.01 (conv_pnp_net.py:109-110), so a random-init head emits 6-D
+        # rotation vectors of norm ~0.05 and the Gram-Schmidt normalisation (rot_reps.py:34-55) amplifies any
+        # difference ~20x.  A trained head emits O(1) vectors: give fc_r an O(1) bias so the rotation error is
+        # measured at the conditioning the 1e-4 rad bar is meant for.  Oracle and device get the same weights.
+        sd["pnp_net.fc_r.bias"] = torch.tensor([0.9, 0.2, -0.35, -0.15, 0.8, 0.45])
     batch = make_batch(B=B, seed=seed)
-    model = GDRN_DoubleMask(default_cfg(with_maps=with_maps), max_batch=max(B, 2))
+    model = GDRN_DoubleMask(default_cfg(with_maps=with_maps), max_batch=max(B, 2), precision=precision)
     model.load_state_dict(sd)
     model.to(dev)
     gb = {k: v.to(dev) for k, v in batch.items()}
@@ -113,6 +119,37 @@ def test_forward_vs_oracle_bf16(dev, B):
     assert (raw[:, 6:] - ref["t_"]).abs().max().item() < 0.02
     assert _rot_err(out["rot"].cpu(), ref["rot"]).max().item() < 0.1
     assert (out["trans"].cpu() - ref["trans"]).abs().max().item() < 1e-2
+
+
+@pytest.mark.parametrize("B", [1, 5, 16])
+def test_forward_vs_oracle_north_star_tolerance(dev, B):
+    """BASELINE.json north_star parity bar, met by the split-bf16 ("bf16x3") precision mode: R within 1e-4 rad and
+    t within 1e-3 of the fp32 oracle (= the reference's fp32 forward, pinned by tests/golden/ref_heads.npz), with the
+    maps and the raw Patch-PnP output at fp32-class tolerances."""
+    sd, batch, model, out = _run_model(dev, B, seed=60 + B, precision="bf16x3", trained_like_rot=True)
+    with torch.no_grad():
+        ref = O.gdrn_forward(sd, batch, return_maps=True, return_intermediate=True)
+    x3 = model.debug_read("stage3_x", B, B * 64 * 1024).reshape(B, 8, 8, 1024).permute(0, 3, 1, 2).cpu()
+    rel = ((x3 - ref["conv_feat"]).norm() / ref["conv_feat"].norm()).item()
+    assert rel < 1e-4, rel
+    for k in ("mask", "full_mask", "coor_x", "coor_y", "coor_z", "region"):
+        assert (out[k].cpu() - ref[k]).abs().max().item() < 2e-3, k
+    raw = out["raw"].cpu()
+    assert (raw[:, :6] - ref["rot6d"]).abs().max().item() < 1e-4
+    assert (raw[:, 6:] - ref["t_"]).abs().max().item() < 1e-4
+    rerr = _rot_err(out["rot"].cpu(), ref["rot"]).max().item()
+    terr = (out["trans"].cpu() - ref["trans"]).abs().max().item()
+    assert rerr < 1e-4, rerr   # north_star: R within 1e-4 rad
+    assert terr < 1e-3, terr   # north_star: t within 1e-3
+
+
+def test_precisions_agree_and_report(dev):
+    """The throughput mode (bf16) stays within its documented distance of the precise mode on the same inputs."""
+    _, _, m1, o1 = _run_model(dev, 4, seed=9, precision="bf16")
+    _, _, m2, o2 = _run_model(dev, 4, seed=9, precision="bf16x3")
+    assert m1.precision == "bf16" and m2.precision == "bf16x3"
+    assert _rot_err(o1["rot"].cpu(), o2["rot"].cpu()).max().item() < 0.1
+    assert (o1["trans"] - o2["trans"]).abs().max().item() < 1e-2
 
 
 def test_pose_lift_exact_given_head_output(dev):
