@@ -3,6 +3,8 @@
 #include <string.h>
 #include <atomic>
 
+#include <stdio.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "gemm_tc.h"
 
@@ -55,5 +57,21 @@ extern "C" int gdrn_gemm_bf16(const void* A, const void* W, const float* bias, c
   p.bias = bias;
   p.gamma = gamma;
   p.resid = resid;
-  return gemm_tc_launch(p, block_n, (cudaStream_t)stream);
+  static int trace_on = -1;
+  if (trace_on < 0) trace_on = getenv("GDRN_GEMM_TRACE") ? 1 : 0;
+  if (!trace_on) return gemm_tc_launch(p, block_n, (cudaStream_t)stream);
+  // debug: cycle accounting of CTA 0, printed to stderr (synchronises the stream)
+  static long long* d_trace = nullptr;
+  if (!d_trace) GDRN_CHECK_CUDA(cudaMalloc(&d_trace, 16 * sizeof(long long)));
+  GDRN_CHECK_CUDA(cudaMemsetAsync(d_trace, 0, 16 * sizeof(long long), (cudaStream_t)stream));
+  p.trace = d_trace;
+  rc = gemm_tc_launch(p, block_n, (cudaStream_t)stream);
+  if (rc != GDRN_OK) return rc;
+  long long h[16];
+  GDRN_CHECK_CUDA(cudaMemcpyAsync(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  GDRN_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  fprintf(stderr, "[gemm trace] M=%lld N=%d K=%d epi=%d bn=%d: cta0 cycles=%lld tiles=%lld | producer empty-wait=%lld | "
+                  "mma full-wait=%lld acc-wait=%lld | epi0 acc-wait=%lld busy=%lld (tmem-ld=%lld compute=%lld flush=%lld)\n",
+          (long long)M, N, K, epi, block_n, h[6], h[7], h[0], h[1], h[2], h[3], h[4], h[8], h[9], h[10]);
+  return GDRN_OK;
 }

@@ -12,6 +12,7 @@
 // head (heads/top_down_doublemask_xyz_region_head.py:177-211: ConvTranspose2d, six 3x3 convs, 1x1 out
 // conv) and by ConvPnPNet (heads/conv_pnp_net.py:120-183: three 3x3 s2 convs and four Linear layers).
 #include "common.cuh"
+#include <stdlib.h>
 #include "gemm_tc.h"
 
 namespace {
@@ -23,7 +24,9 @@ constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int NUM_THREADS = 384;              // 4 control warps + 8 epilogue warps
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int EPI_STAGE_PITCH = 80;           // 64-byte row segment + 16 B pad (conflict-free 16-byte accesses)
-constexpr int EPI_STAGE_BYTES = 32 * EPI_STAGE_PITCH + 256 + 1024;  // per epilogue warp: 32 rows + 32 x int64 row map + bias/gamma (2 x 128 f32)
+// per epilogue warp: either the TMA-store staging tile (32 rows x 128 B, 128B-swizzled, 1024-aligned) or, for the
+// gather-store path, 32 rows x 80 B + 32 x int64 row map + bias/gamma (2 x 128 f32) = 3840 B
+constexpr int EPI_STAGE_BYTES = 4096;
 constexpr int SMEM_BUDGET = 227 * 1024 - NUM_EPI_WARPS * EPI_STAGE_BYTES - 1024 - 256;
 
 template <int BLOCK_N>
@@ -396,6 +399,8 @@ __device__ __forceinline__ void epilogue_tile_staged_t(const GemmPlan& p, int m_
   uint8_t* my_row = stg + lane * EPI_STAGE_PITCH;
   const int cpg = p.gn_cpg;
   const int fl_row = lane >> 2, fl_piece = lane & 3;  // flush / prefetch mapping: 8 rows x 4 pieces per pass
+  const bool trc = (p.trace != nullptr) && blockIdx.x == 0 && ew == 0;
+  long long tq_tmem = 0, tq_comp = 0, tq_flush = 0;
   uint4 rres[4];
   if constexpr (EPI == EPI_RESID) {
     if (n0 < p.N) {
@@ -428,7 +433,9 @@ __device__ __forceinline__ void epilogue_tile_staged_t(const GemmPlan& p, int m_
       __syncwarp();
     }
     float v[CH];
+    long long tq0 = trc ? clock64() : 0;
     tmem_load_chunk<CH>(tmem_row + c, v);
+    if (trc) { const long long t = clock64(); tq_tmem += t - tq0; tq0 = t; }
     if constexpr (EPI == EPI_STORE || EPI == EPI_GELU) {
       const float4* sb = reinterpret_cast<const float4*>(s_bias + c);  // warp-wide broadcast reads
 #pragma unroll
@@ -487,12 +494,22 @@ __device__ __forceinline__ void epilogue_tile_staged_t(const GemmPlan& p, int m_
             for (int j = 0; j < CH; ++j) v[j] = gelu_fast(v[j]);
           }
         }
+        if (p.split) {  // hi must be exactly the cvt.rn value the lo halves are computed against
 #pragma unroll
-        for (int j = 0; j < CH; j += 8) {
-          uint4 w;
-          w.x = pack_bf16(v[j], v[j + 1]); w.y = pack_bf16(v[j + 2], v[j + 3]);
-          w.z = pack_bf16(v[j + 4], v[j + 5]); w.w = pack_bf16(v[j + 6], v[j + 7]);
-          dst[j >> 3] = w;
+          for (int j = 0; j < CH; j += 8) {
+            uint4 w;
+            w.x = pack_bf16(v[j], v[j + 1]); w.y = pack_bf16(v[j + 2], v[j + 3]);
+            w.z = pack_bf16(v[j + 4], v[j + 5]); w.w = pack_bf16(v[j + 6], v[j + 7]);
+            dst[j >> 3] = w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < CH; j += 8) {
+            uint4 w;
+            w.x = pack_bf16(v[j], v[j + 1]); w.y = pack_bf16(v[j + 2], v[j + 3]);
+            w.z = pack_bf16(v[j + 4], v[j + 5]); w.w = pack_bf16(v[j + 6], v[j + 7]);
+            dst[j >> 3] = w;
+          }
         }
         if (p.split) {
 #pragma unroll
@@ -540,6 +557,7 @@ __device__ __forceinline__ void epilogue_tile_staged_t(const GemmPlan& p, int m_
       }
     }
     __syncwarp();
+    if (trc) { const long long t = clock64(); tq_comp += t - tq0; tq0 = t; }
     // ---- coalesced flush of the 32 row segments ----
 #pragma unroll
     for (int pass = 0; pass < 32; pass += 8) {
@@ -550,6 +568,7 @@ __device__ __forceinline__ void epilogue_tile_staged_t(const GemmPlan& p, int m_
             *reinterpret_cast<const uint4*>(stg + rr * EPI_STAGE_PITCH + fl_piece * 16);
     }
     __syncwarp();
+    if (trc) { const long long t = clock64(); tq_flush += t - tq0; tq0 = t; }
     if constexpr (!F32) {
       if (p.split) {  // second round: the lo halves go to columns [N + col, ...)
         uint4* dst = reinterpret_cast<uint4*>(my_row);
@@ -573,11 +592,163 @@ __device__ __forceinline__ void epilogue_tile_staged_t(const GemmPlan& p, int m_
       }
     }
   }
+  if (trc && lane == 0) { p.trace[8] += tq_tmem; p.trace[9] += tq_comp; p.trace[10] += tq_flush; }
+}
+
+
+// Epilogue for rank-2 outputs (EPI_STORE / EPI_GELU / EPI_RESID) with TMA stores.
+// Eight warps as above.  A thread owns one accumulator row; it writes 128-byte row segments (64 bf16 or 32 fp32
+// columns, produced as two 64-byte halves = two tcgen05.ld) into the warp's 32 x 128 B staging tile in the
+// SWIZZLE_128B layout (16-byte piece j of row r at piece j ^ (r & 7): conflict-free row-wise STS.128), and one lane
+// issues a single cp.async.bulk.tensor store per tile.  No address arithmetic, LDS or STG in the flush; rows beyond
+// M are clipped by the tensor map.  The residual of EPI_RESID is read by its owner thread (64 contiguous bytes per
+// half, register-prefetched one half ahead).
+template <int BLOCK_N, int EPI, bool F32>
+__device__ __forceinline__ void epilogue_tile_tma(const GemmPlan& p, int m_tile, int n_tile, uint32_t tmem_acc, int ew,
+                                                  int lane, uint8_t* stg) {
+  static_assert(BLOCK_N >= 128, "TMA-store epilogue needs BLOCK_N >= 128");
+  constexpr int CPW = BLOCK_N / 2;      // columns per warp
+  constexpr int CH = F32 ? 16 : 32;     // columns per 64-byte half row (one tcgen05.ld)
+  constexpr int GW = 2 * CH;            // columns per staged 128-byte row (one TMA store)
+  const int q = ew & 3, half = ew >> 2;
+  const long long grow = (long long)m_tile * BLOCK_M + q * 32 + lane;
+  const bool rvalid = grow < p.M;
+  const int n0 = n_tile * BLOCK_N + half * CPW;
+  const uint32_t tmem_row = tmem_acc + ((uint32_t)(q * 32) << 16) + half * CPW;
+  const uint32_t stg_u32 = ptx::smem_u32(stg);
+  uint8_t* my_row = stg + lane * 128;
+  const int sw = lane & 7;
+  const bool trc = (p.trace != nullptr) && blockIdx.x == 0 && ew == 0;
+  long long tq_tmem = 0, tq_comp = 0, tq_flush = 0;
+
+  uint4 rres[4];
+  const float* rrow = nullptr;
+  const bool red = (EPI == EPI_RESID) && p.resid_reduce;  // launch-uniform: out += gamma*(acc+bias) by TMA reduce-add
+  if constexpr (EPI == EPI_RESID) {
+    rrow = p.resid + grow * p.ldo + n0;
+    if (rvalid && n0 < p.N && !red) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rres[k] = *reinterpret_cast<const uint4*>(rrow + 4 * k);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rres[k] = make_uint4(0, 0, 0, 0);
+    }
+  }
+
+#pragma unroll 1
+  for (int g = 0; g < CPW; g += GW) {
+    const int gcol = n0 + g;
+    if (gcol >= p.N) break;  // warp-uniform
+    long long tq0 = trc ? clock64() : 0;
+    // the previous store of this warp must have finished reading the staging tile
+    if (lane == 0) ptx::bulk_wait_read0();
+    __syncwarp();
+    if (trc) { const long long t = clock64(); tq_flush += t - tq0; tq0 = t; }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = g + h * CH;
+      const int col = n0 + c;
+      float bias[CH];
+#pragma unroll
+      for (int j = 0; j < CH; j += 4) {
+        const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        bias[j] = b4.x; bias[j + 1] = b4.y; bias[j + 2] = b4.z; bias[j + 3] = b4.w;
+      }
+      float x[EPI == EPI_RESID ? CH : 1], gm[EPI == EPI_RESID ? CH : 1];
+      if constexpr (EPI == EPI_RESID) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          x[4 * k] = __uint_as_float(rres[k].x); x[4 * k + 1] = __uint_as_float(rres[k].y);
+          x[4 * k + 2] = __uint_as_float(rres[k].z); x[4 * k + 3] = __uint_as_float(rres[k].w);
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + col + 4 * k));
+          gm[4 * k] = g4.x; gm[4 * k + 1] = g4.y; gm[4 * k + 2] = g4.z; gm[4 * k + 3] = g4.w;
+        }
+        // next half's residual: in flight while this half is processed
+        if (rvalid && !red && c + CH < CPW && col + CH < p.N) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) rres[k] = *reinterpret_cast<const uint4*>(rrow + c + CH + 4 * k);
+        }
+      }
+      float v[CH];
+      long long tq1 = trc ? clock64() : 0;
+      tmem_load_chunk<CH>(tmem_row + c, v);
+      if (trc) { const long long t = clock64(); tq_tmem += t - tq1; }
+      uint4* dst = reinterpret_cast<uint4*>(my_row);
+      if constexpr (F32) {
+        if constexpr (EPI == EPI_RESID) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] = fmaf(gm[j], v[j] + bias[j], x[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] += bias[j];
+        }
+#pragma unroll
+        for (int j = 0; j < CH; j += 4)
+          dst[(h * 4 + (j >> 2)) ^ sw] = make_uint4(__float_as_uint(v[j]), __float_as_uint(v[j + 1]),
+                                                    __float_as_uint(v[j + 2]), __float_as_uint(v[j + 3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] += bias[j];
+        if (EPI == EPI_GELU && p.gelu_mode == 1) {
+#pragma unroll
+          for (int j = 0; j < CH; j += 8) {
+            uint4 w;
+            w.x = gelu_pack2_f16(v[j], v[j + 1]); w.y = gelu_pack2_f16(v[j + 2], v[j + 3]);
+            w.z = gelu_pack2_f16(v[j + 4], v[j + 5]); w.w = gelu_pack2_f16(v[j + 6], v[j + 7]);
+            dst[(h * 4 + (j >> 3)) ^ sw] = w;
+          }
+        } else {
+          if constexpr (EPI == EPI_GELU) {
+            if (p.gelu_mode == 3) {
+#pragma unroll
+              for (int j = 0; j < CH; ++j) v[j] = gelu_erf(v[j]);
+            } else if (p.gelu_mode == 2) {
+#pragma unroll
+              for (int j = 0; j < CH; ++j) v[j] = gelu_tanh_f32(v[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < CH; ++j) v[j] = gelu_fast(v[j]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < CH; j += 8) {
+            uint4 w;
+            w.x = pack_bf16(v[j], v[j + 1]); w.y = pack_bf16(v[j + 2], v[j + 3]);
+            w.z = pack_bf16(v[j + 4], v[j + 5]); w.w = pack_bf16(v[j + 6], v[j + 7]);
+            dst[(h * 4 + (j >> 3)) ^ sw] = w;
+          }
+        }
+      }
+    }
+    if (trc) { const long long t = clock64(); tq_comp += t - tq0; tq0 = t; }
+    ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+    __syncwarp();
+    if (lane == 0) {
+      if (red) ptx::tma_reduce_add_2d(&p.tmap_out, stg_u32, gcol, m_tile * BLOCK_M + q * 32);
+      else ptx::tma_store_2d(&p.tmap_out, stg_u32, gcol, m_tile * BLOCK_M + q * 32);
+      ptx::bulk_commit();
+    }
+    if (trc) { const long long t = clock64(); tq_flush += t - tq0; }
+  }
+  if (trc && lane == 0) { p.trace[8] += tq_tmem; p.trace[9] += tq_comp; p.trace[10] += tq_flush; }
 }
 
 template <int BLOCK_N, int EPI>
 __device__ __forceinline__ void epilogue_tile_staged(const GemmPlan& p, int m_tile, int n_tile, uint32_t tmem_acc,
                                                      int ew, int lane, uint8_t* stg) {
+  if constexpr (BLOCK_N >= 128 && (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_RESID)) {
+    if (p.use_tma_store) {  // launch-uniform
+      if constexpr (EPI == EPI_RESID) {
+        epilogue_tile_tma<BLOCK_N, EPI, true>(p, m_tile, n_tile, tmem_acc, ew, lane, stg);
+      } else if constexpr (EPI == EPI_GELU) {
+        epilogue_tile_tma<BLOCK_N, EPI, false>(p, m_tile, n_tile, tmem_acc, ew, lane, stg);
+      } else {
+        if (p.out_f32) epilogue_tile_tma<BLOCK_N, EPI, true>(p, m_tile, n_tile, tmem_acc, ew, lane, stg);
+        else epilogue_tile_tma<BLOCK_N, EPI, false>(p, m_tile, n_tile, tmem_acc, ew, lane, stg);
+      }
+      return;
+    }
+  }
   if constexpr (EPI == EPI_RESID) {
     epilogue_tile_staged_t<BLOCK_N, EPI, true>(p, m_tile, n_tile, tmem_acc, ew, lane, stg);
   } else if constexpr (EPI == EPI_GELU) {
@@ -594,21 +765,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by SWIZZLE_128B
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + C::STAGES * C::STAGE_BYTES +
-                                                                            8 * (2 * C::STAGES + 4));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(
+      smem_gen + C::STAGES * C::STAGE_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES + 8 * (2 * C::STAGES + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   // epilogues that need the whole row in one thread (LayerNorm, out-conv) or tiny N keep 4 warps + direct stores
   constexpr bool kStaged = (BLOCK_N >= 64) && (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_RESID || EPI == EPI_GNSTATS);
-  uint8_t* stage_base = smem_gen + C::STAGES * C::STAGE_BYTES + 256;
+  uint8_t* stage_base = smem_gen + C::STAGES * C::STAGE_BYTES;  // 1024-aligned (TMA-store tiles are 128B-swizzled)
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.tmap_a);
@@ -636,14 +807,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int k_iters = p.num_taps * p.k_chunks;
+  // optional cycle accounting of CTA 0 (GDRN_GEMM_TRACE, api_core.cu): who waits for whom
+  const bool tr = (p.trace != nullptr) && blockIdx.x == 0;
+  long long tr_acc0 = 0, tr_acc1 = 0;
+  const long long tr_start = tr ? clock64() : 0;
 
   if (warp == 0 && lane == 0) {
     // ================= TMA producer =================
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles;
-      const int m_tile = tile / p.n_tiles;
+      const int n_tile = p.n_major ? tile / p.m_tiles : tile % p.n_tiles;
+      const int m_tile = p.n_major ? tile % p.m_tiles : tile / p.n_tiles;
       int x0 = 0, y0 = 0, b0 = 0;
       if (p.a_rank != 2) {
         int tx = m_tile % p.tiles_x;
@@ -663,7 +838,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       for (int tap = 0; tap < p.num_taps; ++tap) {
         const GemmTap tp = p.taps[tap];
         for (int kc = 0; kc < p.k_chunks; ++kc) {
-          ptx::mbar_wait(empty_bar(stage), phase ^ 1);
+          { const long long t0 = tr ? clock64() : 0; ptx::mbar_wait(empty_bar(stage), phase ^ 1); if (tr) tr_acc0 += clock64() - t0; }
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
           const uint32_t sb = sa + A_STAGE_BYTES;
           ptx::mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
@@ -676,7 +851,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             if (pk >= p.k_chunks) {
               pk -= p.k_chunks;
               const int nt = tile + gridDim.x;
-              pm = (nt < total_tiles && (nt / p.n_tiles) != m_tile) ? nt / p.n_tiles : -1;
+              const int nm = p.n_major ? nt % p.m_tiles : nt / p.n_tiles;
+              pm = (nt < total_tiles && nm != m_tile) ? nm : -1;
             }
             if (pm >= 0 && pk < p.k_chunks && p.num_taps == 1) ptx::tma_prefetch_2d(&p.tmap_a, pk * BLOCK_K, pm * BLOCK_M);
           } else if (p.a_rank == 4) {
@@ -698,11 +874,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      ptx::mbar_wait(tempty_bar(as), aphase ^ 1);
+      { const long long t0 = tr ? clock64() : 0; ptx::mbar_wait(tempty_bar(as), aphase ^ 1); if (tr) tr_acc1 += clock64() - t0; }
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * C::ACC_COLS;
       for (int k = 0; k < k_iters; ++k) {
-        ptx::mbar_wait(full_bar(stage), phase);
+        { const long long t0 = tr ? clock64() : 0; ptx::mbar_wait(full_bar(stage), phase); if (tr) tr_acc0 += clock64() - t0; }
         ptx::tc_fence_after();
         const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
         const uint32_t sb = sa + A_STAGE_BYTES;
@@ -723,11 +899,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     const int ew = warp - 4;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int n_tile = tile % p.n_tiles;
-      const int m_tile = tile / p.n_tiles;
+      const int n_tile = p.n_major ? tile / p.m_tiles : tile % p.n_tiles;
+      const int m_tile = p.n_major ? tile % p.m_tiles : tile / p.n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      if constexpr (kStaged && EPI != EPI_GNSTATS) {
+      if (kStaged && EPI != EPI_GNSTATS && !p.use_tma_store) {
         // this warp's bias (and layer-scale gamma) segment -> its shared-memory slot, before the accumulator wait
         float* sbw = reinterpret_cast<float*>(stage_base + ew * EPI_STAGE_BYTES + 32 * EPI_STAGE_PITCH + 256);
         const int cb = n_tile * BLOCK_N + (ew >> 2) * (BLOCK_N / 2) + lane * 4;
@@ -742,7 +918,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         }
         __syncwarp();
       }
-      if constexpr (kStaged && EPI == EPI_RESID) {
+      if (kStaged && EPI == EPI_RESID && !p.resid_reduce) {
         // the residual rows of this tile are not produced by the MMAs: pull them into L2 while the mainloop runs
         const RowInfo pri = map_row(p, m_tile, (ew & 3) * 32 + lane);
         if (pri.valid) {
@@ -752,7 +928,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const uint8_t*>(rp) + b));
         }
       }
+      long long t0 = tr ? clock64() : 0;
       ptx::mbar_wait(tfull_bar(as), aphase);
+      if (tr) { const long long t1 = clock64(); tr_acc0 += t1 - t0; t0 = t1; }
       ptx::tc_fence_after();
       if constexpr (kStaged) {
         epilogue_tile_staged<BLOCK_N, EPI>(p, m_tile, n_tile, tmem_base + as * C::ACC_COLS, ew, lane,
@@ -764,7 +942,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+      if (tr) tr_acc1 += clock64() - t0;
     }
+    if (tr && ew == 0 && lane == 0) { p.trace[3] = tr_acc0; p.trace[4] = tr_acc1; }
+    if (lane == 0) ptx::bulk_wait0();  // outstanding TMA stores (no-op when none were issued)
+  }
+  if (tr && lane == 0) {
+    if (warp == 0) { p.trace[0] = tr_acc0; p.trace[6] = clock64() - tr_start; p.trace[7] = (total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1; }
+    if (warp == 1) { p.trace[1] = tr_acc0; p.trace[2] = tr_acc1; }
   }
 
   ptx::tc_fence_before();
@@ -795,8 +980,35 @@ int launch_inst(const GemmPlan& plan, cudaStream_t stream) {
 
 }  // namespace
 
-int gemm_tc_launch(const GemmPlan& plan, int block_n, cudaStream_t stream) {
+int gemm_tc_launch(const GemmPlan& plan_in, int block_n, cudaStream_t stream) {
+  GemmPlan plan = plan_in;
+  {  // experiment knob: GDRN_TILE_ORDER=0/1 forces the tile order of every multi-n-tile GEMM
+    static int order = -2;
+    if (order == -2) { const char* e = getenv("GDRN_TILE_ORDER"); order = e ? atoi(e) : -1; }
+    if (order >= 0) plan.n_major = order;
+  }
   GDRN_REQUIRE(plan.a_rank == 2 || plan.a_rank == 4 || plan.a_rank == 5, "gemm: bad a_rank");
+  plan.use_tma_store = 0;
+  plan.resid_reduce = 0;
+  {
+    static int tma_epi = -1;  // GDRN_TMA_STORE=0 falls back to the gather-store epilogue (A/B experiments)
+    if (tma_epi < 0) { const char* e = getenv("GDRN_TMA_STORE"); tma_epi = e ? atoi(e) : 1; }
+    const bool f32 = plan.epi == EPI_RESID || (plan.epi == EPI_STORE && plan.out_f32);
+    if (tma_epi && plan.a_rank == 2 && !plan.split && block_n >= 128 && plan.N % 64 == 0 &&
+        (plan.epi == EPI_STORE || plan.epi == EPI_GELU || plan.epi == EPI_RESID) &&
+        ((uintptr_t)plan.out % 16 == 0) && ((plan.ldo * (f32 ? 4 : 2)) % 16 == 0) &&
+        (plan.epi != EPI_RESID || ((uintptr_t)plan.resid % 16 == 0))) {
+      const uint64_t dims[2] = {(uint64_t)plan.ldo, (uint64_t)plan.M};
+      const uint64_t str[1] = {(uint64_t)plan.ldo * (f32 ? 4 : 2)};
+      const uint32_t box[2] = {f32 ? 32u : 64u, 32u};
+      int rc = make_tmap_store(&plan.tmap_out, plan.out, f32 ? 1 : 0, dims, str, box);
+      if (rc != GDRN_OK) return rc;
+      plan.use_tma_store = 1;
+      static int red = -1;  // GDRN_RESID_REDUCE=0: read-modify-write in the SM instead of the L2 reduce-add
+      if (red < 0) { const char* e = getenv("GDRN_RESID_REDUCE"); red = e ? atoi(e) : 1; }
+      plan.resid_reduce = (red && plan.epi == EPI_RESID && plan.resid == plan.out) ? 1 : 0;
+    }
+  }
   GDRN_REQUIRE(plan.num_taps >= 1 && plan.num_taps <= GEMM_MAX_TAPS, "gemm: bad num_taps");
 #define GDRN_GEMM_CASE(BN, E) \
   if (block_n == BN && plan.epi == E) return launch_inst<BN, E>(plan, stream);
@@ -858,6 +1070,28 @@ int make_tmap_f32_plain(CUtensorMap* out, const void* base, int rank, const uint
   if (r != CUDA_SUCCESS) {
     char msg[160];
     snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled(f32) failed: CUresult %d", (int)r);
+    gdrn_set_last_error(__FILE__, __LINE__, msg);
+    return GDRN_ERR_CUDA;
+  }
+  return GDRN_OK;
+}
+
+// rank-2 output map for the TMA-store epilogue: 128-byte rows, SWIZZLE_128B
+int make_tmap_store(CUtensorMap* out, const void* base, int is_f32, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box) {
+  PFN_encodeTiled fn = get_encode_fn();
+  GDRN_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  cuuint64_t gdim[2] = {dims[0], dims[1]};
+  cuuint64_t gstr[1] = {strides_bytes[0]};
+  cuuint32_t bx[2] = {box[0], box[1]};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(out, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled(store) failed: CUresult %d (dims %llu,%llu)", (int)r,
+             (unsigned long long)dims[0], (unsigned long long)dims[1]);
     gdrn_set_last_error(__FILE__, __LINE__, msg);
     return GDRN_ERR_CUDA;
   }

@@ -42,6 +42,7 @@ struct GemmPlan {
   int b_rows_per_class; // EPI_OUTCONV: row offset multiplier for the ROI class (0 otherwise)
   // ---- problem ----
   int m_tiles, n_tiles;
+  int n_major;          // tile order: 0 = consecutive CTAs share an A tile (m-major), 1 = they share a B tile (n-major)
   int M;                // valid rows (rank 2) ; rank 4/5: number of images B
   int N;                // valid output columns
   // ---- epilogue ----
@@ -50,6 +51,9 @@ struct GemmPlan {
   int gelu_mode;        // EPI_GELU: 0 = fp32 ex2/rcp form (1.2e-5 of erf), 1 = packed half2 tanh.approx, 2 = fp32 tanh.approx, 3 = erff
   int split;            // bf16 outputs are written as [hi | lo] pairs (row width 2N, lo = bf16(v - hi)): split-bf16 (x3) mode
   void* out;            // [rows, ldo]
+  CUtensorMap tmap_out; // rank-2 outputs: store map (filled by gemm_tc_launch when use_tma_store)
+  int use_tma_store;    // set by gemm_tc_launch
+  int resid_reduce;     // set by gemm_tc_launch: EPI_RESID in place -> TMA reduce-add (x += gamma*(acc+bias)), x is never read by the SM
   long long ldo;        // output row stride (elements)
   int OH, OW, osy, osx, ooy, oox;  // rank 4/5: out row = (b*OH + y*osy+ooy)*OW + x*osx+oox
   const float* bias;    // [N] or null
@@ -66,6 +70,9 @@ struct GemmPlan {
   const float* roi_extents;      // [B,3]
   const float* roi_coord_2d;     // [B,2,64,64] fp32 NCHW
   void* pnp_in;                  // bf16 [B*4096, 128]
+  // debug: CTA 0 writes [0] producer empty-wait, [1] MMA full-wait, [2] MMA accumulator-wait, [3] epilogue warp 0
+  // accumulator-wait, [4] epilogue warp 0 busy, [6] CTA cycles, [7] tiles of CTA 0 (clock64 cycles)
+  long long* trace;
   float* map_mask; float* map_full; float* map_x; float* map_y; float* map_z; float* map_region;  // NCHW or null
 };
 
@@ -76,5 +83,7 @@ int gemm_tc_launch(const GemmPlan& plan, int block_n, cudaStream_t stream);
 // fp32, no swizzle, zero OOB fill (dense [..][box0] shared-memory image)
 int make_tmap_f32_plain(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                         const uint64_t* strides_bytes, const uint32_t* box);
+int make_tmap_store(CUtensorMap* out, const void* base, int is_f32, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box);
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box);

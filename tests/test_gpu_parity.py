@@ -49,6 +49,26 @@ def test_gemm_vs_torch(dev, lib, M, N, K, bn, epi, f32):
     assert err < (2e-4 if is_f32 else 0.04), err
 
 
+@pytest.mark.parametrize("M,N,K,bn", [(4096, 256, 1024, 256), (1000, 128, 512, 128), (300, 512, 128, 256)])
+def test_gemm_residual_in_place(dev, lib, M, N, K, bn):
+    """EPI_RESID with out == resid (how the model calls it): the epilogue turns into a TMA reduce-add
+    (x += gamma*(acc+bias) performed by the L2).  M not a multiple of 128 checks the tensor-map row clipping."""
+    L = _lib()
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(dev).bfloat16()
+    W = (torch.randn(N, K, generator=g) / np.sqrt(K)).to(dev).bfloat16()
+    bias, gamma = torch.randn(N, generator=g).to(dev), torch.rand(N, generator=g).to(dev)
+    pad = torch.full((M + 256, N), 7.0, device=dev)      # canary rows behind the matrix must stay untouched
+    x = torch.randn(M, N, generator=g).to(dev)
+    pad[:M] = x
+    ref = x + gamma * (A.float() @ W.float().t() + bias)
+    L.check(lib.gdrn_gemm_bf16(L.ptr(A), L.ptr(W), L.ptr(bias), L.ptr(gamma), L.ptr(pad), L.ptr(pad), M, N, K, 2, 1, bn,
+                               L.current_stream()), "gemm")
+    torch.cuda.synchronize()
+    assert (pad[:M] - ref).abs().max().item() < 2e-4
+    assert torch.equal(pad[M:], torch.full((256, N), 7.0, device=dev))
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_gemm_gelu_modes(dev, lib, mode, monkeypatch):
     """The three epilogue GELU evaluations (fp32 ex2/rcp, packed half2 tanh.approx, fp32 tanh.approx) vs erf-GELU."""
