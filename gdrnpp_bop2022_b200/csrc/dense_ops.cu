@@ -4,6 +4,8 @@
 // heads/conv_pnp_net.py, core/utils/rot_reps.py:34-55, models/pose_from_pred_centroid_z.py:56-154,
 // core/utils/utils.py:31-88.
 #include <cooperative_groups.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "dense_ops.h"
@@ -255,20 +257,31 @@ __device__ __forceinline__ float lane_transpose_reduce(float (&a)[N], int lane) 
   return a[0];
 }
 
-template <int TW, int TH>
-__global__ void __launch_bounds__(((TW == 16) ? 32 : 64) * TH, (TW == 16) ? 2 : 1)
+// Depthwise 7x7 + bias + LayerNorm(C) -> bf16 GEMM operand.  One CTA = (TW x TH pixel tile) x CPC channels of one
+// image; the CTAs of a cluster hold the C / CPC channel slices of the same tile.  A thread owns one channel PAIR
+// (packed fma.rn.f32x2) and R consecutive output rows x TW pixels.  It walks the R + 6 input rows once: each row is
+// loaded from shared memory a single time (TW + 6 LDS.64) and applied to every output row it contributes to, and
+// the filter row fetched for output row r is kept in registers for output row r + 1 of the next step, so that one
+// step costs TW + 6 + 7 shared-memory loads for R * 7 * TW packed FMAs (R = 2: 0.13 loads per FMA instead of 0.26;
+// the R = 1 form was co-limited by shared-memory bandwidth, see profiles/).
+template <int TW, int TH, int CPC, int R, int MINB>
+__global__ void __launch_bounds__((CPC / 2) * TH / R, MINB)
 dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                          const float* __restrict__ bias, const float* __restrict__ ln_w,
                          const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out, int B, int H, int W, int C,
-                         float eps, int split) {
-  constexpr int CPC = (TW == 16) ? 64 : 128;  // channels per CTA
-  constexpr int PAIRS = CPC / 2;              // channel pairs = threads per output row
+                         float eps, int split, long long* trace) {
+  static_assert(R == 1 || R == 2, "rows per thread");
+  const bool trc = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == B / 2 && threadIdx.x == 0;
+  long long tt[6];
+  if (trc) tt[0] = clock64();
+  constexpr int PAIRS = CPC / 2;              // channel pairs = threads per thread-row (CPC = channels per CTA)
   constexpr int IW = TW + 6;
   constexpr int IH = TH + 6;
   constexpr int NPIX = TW * TH;
-  constexpr int NTHREADS = PAIRS * TH;
-  constexpr int WPR = PAIRS / 32;             // warps per output row
-  constexpr int LPP = 32 / TW;                // lanes per pixel after the transposing reduction (2 or 4)
+  constexpr int WPR = PAIRS / 32;             // warps per thread-row
+  constexpr int NV = R * TW;                  // pixels per thread
+  constexpr int LPP = 32 / NV;                // lanes per pixel after the transposing reduction (1, 2 or 4)
+  static_assert(NV == 8 || NV == 16 || NV == 32, "pixels per thread");
   extern __shared__ __align__(1024) float smem_dw[];   // TMA destination first: 128-byte aligned
   float* tile = smem_dw;                      // [IH][IW][CPC]
   float* wsm = tile + IH * IW * CPC;          // [49][CPC]
@@ -284,7 +297,7 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
   const int b = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31;
   const int pair = tid % PAIRS;
-  const int row = tid / PAIRS;                // output row of the tile
+  const int row0 = (tid / PAIRS) * R;         // first output row of this thread
   const int wc = (tid >> 5) % WPR;            // which 64-channel group of the CTA this warp holds
   const int cl = 2 * pair;                    // first channel of the pair (CTA-local)
 
@@ -299,52 +312,73 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
     ptx::tma_load_2d(ptx::smem_u32(wsm), &tmap_w, bar, c0, 0);          // this CTA's 49 x CPC filter taps
     ptx::tma_load_4d(ptx::smem_u32(tile), &tmap_x, bar, c0, x0 - 3, y0 - 3, b);
   }
-  f32x2_t acc[TW];
+  f32x2_t acc[R][TW];
   {
     const f32x2_t bv = f2_pack(__ldg(bias + c0 + cl), __ldg(bias + c0 + cl + 1));
 #pragma unroll
-    for (int i = 0; i < TW; ++i) acc[i] = bv;
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int i = 0; i < TW; ++i) acc[r][i] = bv;
   }
   ptx::mbar_wait(bar, 0);    // filter taps + input tile landed
+  if (trc) tt[1] = clock64();
 
-  // ---- convolution: one output row x TW pixels for a channel pair, 7 input rows ----
+  // ---- convolution: input row i feeds output row r with filter row ky = i - r ----
+  {
+    f32x2_t wprev[7];
 #pragma unroll
-  for (int ky = 0; ky < 7; ++ky) {
-    f32x2_t v[IW], wk[7];
-    const float* rowp = tile + ((row + ky) * IW) * CPC + cl;
+    for (int i = 0; i < R + 6; ++i) {
+      f32x2_t v[IW], wk[7];
+      const float* rowp = tile + ((row0 + i) * IW) * CPC + cl;
 #pragma unroll
-    for (int j = 0; j < IW; ++j) v[j] = *reinterpret_cast<const f32x2_t*>(rowp + j * CPC);
+      for (int j = 0; j < IW; ++j) v[j] = *reinterpret_cast<const f32x2_t*>(rowp + j * CPC);
+      if (i < 7) {
 #pragma unroll
-    for (int kx = 0; kx < 7; ++kx) wk[kx] = *reinterpret_cast<const f32x2_t*>(wsm + (ky * 7 + kx) * CPC + cl);
+        for (int kx = 0; kx < 7; ++kx) wk[kx] = *reinterpret_cast<const f32x2_t*>(wsm + (i * 7 + kx) * CPC + cl);
 #pragma unroll
-    for (int kx = 0; kx < 7; ++kx)
+        for (int kx = 0; kx < 7; ++kx)
 #pragma unroll
-      for (int ox = 0; ox < TW; ++ox) acc[ox] = f2_fma(v[ox + kx], wk[kx], acc[ox]);
+          for (int ox = 0; ox < TW; ++ox) acc[0][ox] = f2_fma(v[ox + kx], wk[kx], acc[0][ox]);
+      }
+      if (R == 2 && i >= 1) {
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx)
+#pragma unroll
+          for (int ox = 0; ox < TW; ++ox) acc[R - 1][ox] = f2_fma(v[ox + kx], wprev[kx], acc[R - 1][ox]);
+      }
+      if (R == 2 && i < 7) {
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) wprev[kx] = wk[kx];
+      }
+    }
   }
-  float ax[TW], ay[TW];
+  if (trc) tt[2] = clock64();
+  float ax[NV], ay[NV];
 #pragma unroll
-  for (int i = 0; i < TW; ++i) { const float2 t = f2_unpack(acc[i]); ax[i] = t.x; ay[i] = t.y; }
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int i = 0; i < TW; ++i) { const float2 t = f2_unpack(acc[r][i]); ax[r * TW + i] = t.x; ay[r * TW + i] = t.y; }
 
   // ---- LayerNorm over all C channels of each pixel ----
-  // A warp holds 64 channels of its row's TW pixels: it computes (sum, M2 about its own mean) per pixel with
+  // A warp holds 64 channels of its NV pixels: it computes (sum, M2 about its own mean) per pixel with
   // shuffles only, PUSHES that partial into every CTA of the cluster (distributed shared memory stores), and after
   // ONE cluster barrier each warp combines the C/64 partials with Chan's parallel-variance formula.  No block-level
   // barrier, no remote loads, and nothing remote is touched after the barrier (so no exit barrier is needed).
   constexpr float INV_W = 1.0f / 64.0f;  // channels per warp = 64
-  const int pix = row * TW + lane / LPP;
+  const int pix = row0 * TW + lane / LPP;   // the thread's R rows are contiguous in the row-major tile
   float s_loc, m2_loc;
   {
-    float a[TW];
+    float a[NV];
 #pragma unroll
-    for (int i = 0; i < TW; ++i) a[i] = ax[i] + ay[i];
-    s_loc = lane_transpose_reduce<TW>(a, lane);           // lane L: pixel L / LPP of this row
+    for (int i = 0; i < NV; ++i) a[i] = ax[i] + ay[i];
+    s_loc = lane_transpose_reduce<NV>(a, lane);           // lane L: pixel L / LPP of this thread-row
 #pragma unroll
-    for (int i = 0; i < TW; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const float m = __shfl_sync(0xffffffffu, s_loc, i * LPP) * INV_W;
       const float dx = ax[i] - m, dy = ay[i] - m;
       a[i] = fmaf(dx, dx, dy * dy);
     }
-    m2_loc = lane_transpose_reduce<TW>(a, lane);
+    m2_loc = lane_transpose_reduce<NV>(a, lane);
   }
   const int nparts = nrank * WPR;
   {
@@ -354,7 +388,9 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
       for (int rk = 0; rk < nrank; ++rk) cluster.map_shared_rank(s_parts, rk)[part * NPIX + pix] = v;
     }
   }
+  if (trc) tt[3] = clock64();
   cluster.sync();
+  if (trc) tt[4] = clock64();
   float mean_p, rstd_p;
   {
     float tot = 0.f;
@@ -372,18 +408,26 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
   const float gw0 = __ldg(ln_w + c0 + cl), gw1 = __ldg(ln_w + c0 + cl + 1);
   const float gb0 = __ldg(ln_b + c0 + cl), gb1 = __ldg(ln_b + c0 + cl + 1);
   const int ldc = split ? 2 * C : C;  // split mode: rows are [hi C | lo C]
-  __nv_bfloat16* orow = out + (((long long)b * H + (y0 + row)) * W + x0) * ldc + c0 + cl;
 #pragma unroll
-  for (int ox = 0; ox < TW; ++ox) {
-    const float m = __shfl_sync(0xffffffffu, mean_p, ox * LPP);
-    const float r = __shfl_sync(0xffffffffu, rstd_p, ox * LPP);
-    const float o0 = fmaf((ax[ox] - m) * r, gw0, gb0), o1 = fmaf((ay[ox] - m) * r, gw1, gb1);
-    const __nv_bfloat162 o = __floats2bfloat162_rn(o0, o1);
-    *reinterpret_cast<__nv_bfloat162*>(orow + (long long)ox * ldc) = o;
-    if (split) {
-      const float2 of = __bfloat1622float2(o);
-      *reinterpret_cast<__nv_bfloat162*>(orow + (long long)ox * ldc + C) = __floats2bfloat162_rn(o0 - of.x, o1 - of.y);
+  for (int r = 0; r < R; ++r) {
+    __nv_bfloat16* orow = out + (((long long)b * H + (y0 + row0 + r)) * W + x0) * ldc + c0 + cl;
+#pragma unroll
+    for (int ox = 0; ox < TW; ++ox) {
+      const int i = r * TW + ox;
+      const float m = __shfl_sync(0xffffffffu, mean_p, i * LPP);
+      const float rs = __shfl_sync(0xffffffffu, rstd_p, i * LPP);
+      const float o0 = fmaf((ax[i] - m) * rs, gw0, gb0), o1 = fmaf((ay[i] - m) * rs, gw1, gb1);
+      const __nv_bfloat162 o = __floats2bfloat162_rn(o0, o1);
+      *reinterpret_cast<__nv_bfloat162*>(orow + (long long)ox * ldc) = o;
+      if (split) {
+        const float2 of = __bfloat1622float2(o);
+        *reinterpret_cast<__nv_bfloat162*>(orow + (long long)ox * ldc + C) = __floats2bfloat162_rn(o0 - of.x, o1 - of.y);
+      }
     }
+  }
+  if (trc) {
+    tt[5] = clock64();
+    for (int i = 0; i < 5; ++i) trace[i] = tt[i + 1] - tt[i];
   }
 }
 
@@ -750,16 +794,15 @@ int launch_stem_patchify(const float* img, __nv_bfloat16* out, int B, int H, int
   return GDRN_OK;
 }
 
-template <int TW, int TH>
+template <int TW, int TH, int CPC, int R, int MINB>
 static int launch_dwconv_cluster(const float* x, const float* w49c, const float* bias, const float* ln_w,
                                  const float* ln_b, __nv_bfloat16* out, int B, int H, int W, int C, float eps,
                                  int split, cudaStream_t st) {
-  constexpr int CPC = (TW == 16) ? 64 : 128;
   constexpr int IW = TW + 6, IH = TH + 6;
   constexpr int NPIX = TW * TH;
-  constexpr int NTHREADS = (CPC / 2) * TH;
+  constexpr int NTHREADS = (CPC / 2) * TH / R;
   const size_t smem = (size_t)(IH * IW * CPC + 49 * CPC + 2 * 8 * (CPC / 64) * NPIX) * sizeof(float) + 16;
-  auto kfn = dwconv_ln_cluster_kernel<TW, TH>;
+  auto kfn = dwconv_ln_cluster_kernel<TW, TH, CPC, R, MINB>;
   static bool configured = false;
   if (!configured) {
     GDRN_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -793,8 +836,20 @@ static int launch_dwconv_cluster(const float* x, const float* w49c, const float*
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  GDRN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kfn, tmap, tmap_w, bias, ln_w, ln_b, out, B, H, W, C, eps, split));
+  static int trace_on = -1;  // GDRN_DW_TRACE=1: phase cycle counts of one mid-grid CTA on stderr (synchronises)
+  if (trace_on < 0) trace_on = getenv("GDRN_DW_TRACE") ? 1 : 0;
+  static long long* d_trace = nullptr;
+  if (trace_on && !d_trace) GDRN_CHECK_CUDA(cudaMalloc(&d_trace, 8 * sizeof(long long)));
+  long long* trp = trace_on ? d_trace : nullptr;
+  GDRN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kfn, tmap, tmap_w, bias, ln_w, ln_b, out, B, H, W, C, eps, split, trp));
   gdrn_count_launch(1);
+  if (trace_on) {
+    long long h[5];
+    GDRN_CHECK_CUDA(cudaMemcpyAsync(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost, st));
+    GDRN_CHECK_CUDA(cudaStreamSynchronize(st));
+    fprintf(stderr, "[dwconv trace] %dx%d C=%d tile %dx%d R=%d: load-wait=%lld conv=%lld ln-local=%lld cluster-sync=%lld finish=%lld\n",
+            H, W, C, TW, TH, R, h[0], h[1], h[2], h[3], h[4]);
+  }
   return GDRN_OK;
 }
 
@@ -802,8 +857,20 @@ int launch_dwconv_ln(const float* x, const float* w49c, const float* bias, const
                      __nv_bfloat16* out, int B, int H, int W, int C, float eps, int split, cudaStream_t st) {
   GDRN_REQUIRE(C % 128 == 0 && C <= 1024, "dwconv: C must be a multiple of 128 and <= 1024");
   // cluster kernel: 16x8 tiles x 64 channels (cluster C/64 <= 8) or 8x8 tiles x 128 channels (cluster C/128 <= 8)
-  if (H % 8 == 0 && W % 16 == 0 && C / 64 <= 8) return launch_dwconv_cluster<16, 8>(x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps, split, st);
-  if (H % 8 == 0 && W % 8 == 0 && C / 128 <= 8) return launch_dwconv_cluster<8, 8>(x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps, split, st);
+  static int rows = -1;  // GDRN_DW_ROWS=1: one output row per thread (A/B experiments)
+  if (rows < 0) { const char* e = getenv("GDRN_DW_ROWS"); rows = (e && atoi(e) == 1) ? 1 : 2; }
+  static int var = -1;   // GDRN_DW_VARIANT: tile-shape experiments
+  if (var < 0) { const char* e = getenv("GDRN_DW_VARIANT"); var = e ? atoi(e) : 0; }
+#define DW_ARGS x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps, split, st
+  if (H % 8 == 0 && W % 16 == 0 && C / 64 <= 8) {
+    if (var == 1) return launch_dwconv_cluster<16, 4, 64, 1, 3>(DW_ARGS);   // 73 KB: 3 CTAs / SM, 128 threads
+    if (var == 2) return launch_dwconv_cluster<8, 8, 64, 1, 3>(DW_ARGS);    // 67 KB: 3 CTAs / SM, 256 threads
+    if (var == 3) return launch_dwconv_cluster<8, 4, 64, 1, 4>(DW_ARGS);    // 50 KB: 4 CTAs / SM, 128 threads
+    return rows == 2 ? launch_dwconv_cluster<16, 8, 64, 2, 2>(DW_ARGS) : launch_dwconv_cluster<16, 8, 64, 1, 2>(DW_ARGS);
+  }
+  if (H % 8 == 0 && W % 8 == 0 && C / 128 <= 8)
+    return rows == 2 ? launch_dwconv_cluster<8, 8, 128, 2, 1>(DW_ARGS) : launch_dwconv_cluster<8, 8, 128, 1, 1>(DW_ARGS);
+#undef DW_ARGS
   GDRN_REQUIRE(!split, "dwconv: the non-cluster fallback kernel has no split-bf16 output");
   const int S = 256 / (C / 4);
   if (W % 16 == 0) {
