@@ -432,56 +432,77 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
 }
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm2d + 2x2 stride-2 patchify: one warp per source pixel.
+// LayerNorm2d + 2x2 stride-2 patchify (ConvNeXt downsample front half).  One warp per OUTPUT pixel: it loads the four
+// source pixels of the 2x2 patch up front (4 x C fp32 in flight per warp -- the one-pixel-per-warp form was latency
+// bound at 1.4 TB/s), normalises each over its C channels with interleaved shuffle reductions, and writes the
+// patch row [p00 C | p01 C | p10 C | p11 C] (bf16, plus the lo halves in split mode).  C = 128 * NV.
+template <int NV>
 __global__ void __launch_bounds__(256)
 ln_patchify2_kernel(const float* __restrict__ x, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                    __nv_bfloat16* __restrict__ out, int B, int H, int W, int C, float eps, int split) {
-  const long long pix = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const long long total = (long long)B * H * W;
-  if (pix >= total) return;
+                    __nv_bfloat16* __restrict__ out, int B, int H, int W, float eps, int split) {
+  constexpr int C = 128 * NV;
+  const int OW = W / 2, OH = H / 2;
+  const long long m2 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (m2 >= (long long)B * OH * OW) return;
   const int lane = threadIdx.x & 31;
-  const int px = (int)(pix % W);
-  const int py = (int)((pix / W) % H);
-  const int b = (int)(pix / ((long long)W * H));
-  const float* src = x + pix * C;
-  const int nv = C >> 7;  // float4 per lane: C/128 (1, 2, 4)
-  float4 v[4];
-  float s = 0.f;
-  for (int k = 0; k < nv; ++k) {
-    v[k] = *reinterpret_cast<const float4*>(src + (k * 32 + lane) * 4);
-    s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  const int ox = (int)(m2 % OW);
+  const int oy = (int)((m2 / OW) % OH);
+  const int b = (int)(m2 / ((long long)OW * OH));
+  float4 v[4][NV];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const float* src = x + (((long long)b * H + (2 * oy + (p >> 1))) * W + (2 * ox + (p & 1))) * C;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[p][k] = *reinterpret_cast<const float4*>(src + (k * 32 + lane) * 4);
+  }
+  float s[4], q[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    s[p] = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) s[p] += (v[p][k].x + v[p][k].y) + (v[p][k].z + v[p][k].w);
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / (float)C;
-  float q = 0.f;
-  for (int k = 0; k < nv; ++k) {
-    float dx = v[k].x - mean, dy = v[k].y - mean, dz = v[k].z - mean, dw = v[k].w - mean;
-    q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int p = 0; p < 4; ++p) s[p] += __shfl_xor_sync(0xffffffffu, s[p], o);
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    s[p] = s[p] / (float)C;   // mean
+    q[p] = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const float dx = v[p][k].x - s[p], dy = v[p][k].y - s[p], dz = v[p][k].z - s[p], dw = v[p][k].w - s[p];
+      q[p] += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float r = rsqrtf(q / (float)C + eps);
-  const long long m2 = ((long long)b * (H / 2) + (py >> 1)) * (W / 2) + (px >> 1);
-  __nv_bfloat16* dst = out + m2 * ((split ? 8LL : 4LL) * C) + ((py & 1) * 2 + (px & 1)) * C;
-  for (int k = 0; k < nv; ++k) {
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int p = 0; p < 4; ++p) q[p] += __shfl_xor_sync(0xffffffffu, q[p], o);
+  __nv_bfloat16* dst = out + m2 * ((split ? 8LL : 4LL) * C);
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
     const int c = (k * 32 + lane) * 4;
     const float4 gw = *reinterpret_cast<const float4*>(ln_w + c);
     const float4 gb = *reinterpret_cast<const float4*>(ln_b + c);
-    const float o0 = fmaf((v[k].x - mean) * r, gw.x, gb.x), o1 = fmaf((v[k].y - mean) * r, gw.y, gb.y);
-    const float o2 = fmaf((v[k].z - mean) * r, gw.z, gb.z), o3 = fmaf((v[k].w - mean) * r, gw.w, gb.w);
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1);
-    __nv_bfloat162 p1 = __floats2bfloat162_rn(o2, o3);
-    uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&p0);
-    u.y = *reinterpret_cast<uint32_t*>(&p1);
-    *reinterpret_cast<uint2*>(dst + c) = u;
-    if (split) {
-      const float2 f0 = __bfloat1622float2(p0), f1 = __bfloat1622float2(p1);
-      uint2 ul;
-      ul.x = pack_bf16(o0 - f0.x, o1 - f0.y);
-      ul.y = pack_bf16(o2 - f1.x, o3 - f1.y);
-      *reinterpret_cast<uint2*>(dst + 4LL * C + c) = ul;   // lo half of the [hi 4C | lo 4C] row
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const float r = rsqrtf(q[p] / (float)C + eps);
+      const float o0 = fmaf((v[p][k].x - s[p]) * r, gw.x, gb.x), o1 = fmaf((v[p][k].y - s[p]) * r, gw.y, gb.y);
+      const float o2 = fmaf((v[p][k].z - s[p]) * r, gw.z, gb.z), o3 = fmaf((v[p][k].w - s[p]) * r, gw.w, gb.w);
+      const __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
+      uint2 u;
+      u.x = *reinterpret_cast<const uint32_t*>(&p0);
+      u.y = *reinterpret_cast<const uint32_t*>(&p1);
+      *reinterpret_cast<uint2*>(dst + p * C + c) = u;
+      if (split) {
+        const float2 f0 = __bfloat1622float2(p0), f1 = __bfloat1622float2(p1);
+        uint2 ul;
+        ul.x = pack_bf16(o0 - f0.x, o1 - f0.y);
+        ul.y = pack_bf16(o2 - f1.x, o3 - f1.y);
+        *reinterpret_cast<uint2*>(dst + 4LL * C + p * C + c) = ul;   // lo half of the [hi 4C | lo 4C] row
+      }
     }
   }
 }
@@ -889,8 +910,12 @@ int launch_dwconv_ln(const float* x, const float* w49c, const float* bias, const
 int launch_ln_patchify2(const float* x, const float* ln_w, const float* ln_b, __nv_bfloat16* out, int B, int H, int W,
                         int C, float eps, int split, cudaStream_t st) {
   GDRN_REQUIRE(C % 128 == 0 && C <= 512 && H % 2 == 0 && W % 2 == 0, "ln_patchify2: unsupported shape");
-  long long total = (long long)B * H * W;
-  ln_patchify2_kernel<<<(int)((total + 7) / 8), 256, 0, st>>>(x, ln_w, ln_b, out, B, H, W, C, eps, split);
+  const long long total = (long long)B * (H / 2) * (W / 2);
+  const int blocks = (int)((total + 7) / 8);
+  if (C == 128) ln_patchify2_kernel<1><<<blocks, 256, 0, st>>>(x, ln_w, ln_b, out, B, H, W, eps, split);
+  else if (C == 256) ln_patchify2_kernel<2><<<blocks, 256, 0, st>>>(x, ln_w, ln_b, out, B, H, W, eps, split);
+  else if (C == 384) ln_patchify2_kernel<3><<<blocks, 256, 0, st>>>(x, ln_w, ln_b, out, B, H, W, eps, split);
+  else ln_patchify2_kernel<4><<<blocks, 256, 0, st>>>(x, ln_w, ln_b, out, B, H, W, eps, split);
   GDRN_CHECK_CUDA(cudaGetLastError());
   gdrn_count_launch(1);
   return GDRN_OK;

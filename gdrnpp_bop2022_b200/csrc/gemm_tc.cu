@@ -149,7 +149,8 @@ __device__ __forceinline__ void tmem_load_chunk(uint32_t taddr, float (&v)[CH]) 
 // Epilogues.  Each of the 128 epilogue threads owns one accumulator row (TMEM lane).
 // ------------------------------------------------------------------------------------------------
 template <int BLOCK_N, int EPI>
-__device__ __forceinline__ void epilogue_tile(const GemmPlan& p, int m_tile, int n_tile, uint32_t tmem_row, int lane) {
+__device__ __forceinline__ void epilogue_tile(const GemmPlan& p, int m_tile, int n_tile, uint32_t tmem_row, int lane,
+                                              uint8_t* stg) {
   constexpr int CH = BLOCK_N >= 32 ? 32 : 16;
   const int r = ((threadIdx.x >> 5) & 3) * 32 + lane;
   const RowInfo ri = map_row(p, m_tile, r);
@@ -263,6 +264,25 @@ __device__ __forceinline__ void epilogue_tile(const GemmPlan& p, int m_tile, int
       load_vec<CH>(p.ln_b, c, p.N, bb);
 #pragma unroll
       for (int j = 0; j < CH; ++j) v[j] = fmaf((v[j] + bias[j] - mean) * rstd, w[j], bb[j]);
+      if constexpr (CH == 32) {
+        if (p.use_tma_store) {  // 32 rows x 128 B staging tile (SWIZZLE_128B) -> one TMA store, rows >= M clipped
+          if (lane == 0) ptx::bulk_wait_read0();
+          __syncwarp();
+          uint4* dst = reinterpret_cast<uint4*>(stg + lane * 128);
+          const int sw = lane & 7;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j ^ sw] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                                     __float_as_uint(v[4 * j + 3]));
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&p.tmap_out, ptx::smem_u32(stg), c, m_tile * BLOCK_M + (int)((threadIdx.x >> 5) & 3) * 32);
+            ptx::bulk_commit();
+          }
+          continue;
+        }
+      }
       if (ri.valid) store_row_chunk<CH>(p, ri, c, v, true);
     }
   } else if constexpr (EPI == EPI_OUTCONV) {
@@ -937,7 +957,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                                            stage_base + ew * EPI_STAGE_BYTES);
       } else {
         const uint32_t tmem_row = tmem_base + ((uint32_t)((ew & 3) * 32) << 16) + as * C::ACC_COLS;
-        epilogue_tile<BLOCK_N, EPI>(p, m_tile, n_tile, tmem_row, lane);
+        epilogue_tile<BLOCK_N, EPI>(p, m_tile, n_tile, tmem_row, lane, stage_base + (ew & 3) * EPI_STAGE_BYTES);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -993,9 +1013,9 @@ int gemm_tc_launch(const GemmPlan& plan_in, int block_n, cudaStream_t stream) {
   {
     static int tma_epi = -1;  // GDRN_TMA_STORE=0 falls back to the gather-store epilogue (A/B experiments)
     if (tma_epi < 0) { const char* e = getenv("GDRN_TMA_STORE"); tma_epi = e ? atoi(e) : 1; }
-    const bool f32 = plan.epi == EPI_RESID || (plan.epi == EPI_STORE && plan.out_f32);
+    const bool f32 = plan.epi == EPI_RESID || plan.epi == EPI_BIAS_LN || (plan.epi == EPI_STORE && plan.out_f32);
     if (tma_epi && plan.a_rank == 2 && !plan.split && block_n >= 128 && plan.N % 64 == 0 &&
-        (plan.epi == EPI_STORE || plan.epi == EPI_GELU || plan.epi == EPI_RESID) &&
+        (plan.epi == EPI_STORE || plan.epi == EPI_GELU || plan.epi == EPI_RESID || plan.epi == EPI_BIAS_LN) &&
         ((uintptr_t)plan.out % 16 == 0) && ((plan.ldo * (f32 ? 4 : 2)) % 16 == 0) &&
         (plan.epi != EPI_RESID || ((uintptr_t)plan.resid % 16 == 0))) {
       const uint64_t dims[2] = {(uint64_t)plan.ldo, (uint64_t)plan.M};

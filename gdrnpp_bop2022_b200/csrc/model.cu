@@ -605,12 +605,14 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
           ++nt;
         }
       p.num_taps = nt;
-      RC(plan_b(p, m->deconv_w[py * 2 + px], 256, (long long)nt * C3, 256, 256, S));
+      // only B/2 row tiles (8x8 inputs): narrow N tiles so that the launch still covers the SMs
+      const int dbn = p.m_tiles >= 96 ? 256 : 64;
+      RC(plan_b(p, m->deconv_w[py * 2 + px], 256, (long long)nt * C3, dbn, 256, S));
       if (PR) expand_x3(p, C3, nt * C3);
       p.epi = EPI_GNSTATS; p.out_f32 = PR; p.out = w.R; p.ldo = 256;
       p.OH = 16; p.OW = 16; p.osy = 2; p.osx = 2; p.ooy = py; p.oox = px;
       p.gn_stats = stat_slot(0); p.gn_groups = 32; p.gn_cpg = 8;
-      RCP(0, gemm_tc_launch(p, 256, st));
+      RCP(0, gemm_tc_launch(p, dbn, st));
     }
   RCP(2, launch_gn_gelu(w.R, PR, stat_slot(0), w.gn_mr, m->gn_w[0], m->gn_b[0], w.P, B, 16, 16, 256, 32, 1e-5f, PR, st));
   __nv_bfloat16* cur = w.P;
