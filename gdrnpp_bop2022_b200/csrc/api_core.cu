@@ -41,6 +41,7 @@ extern "C" int gdrn_gemm_bf16(const void* A, const void* W, const float* bias, c
   uint32_t box_b[2] = {64, (uint32_t)block_n};
   rc = make_tmap_bf16(&p.tmap_b, W, 2, dims_b, str_b, box_b);
   if (rc) return rc;
+  p.b_ptr = W; p.b_rows = N; p.b_ktot = K;
   p.a_rank = 2;
   p.num_taps = 1;
   p.k_chunks = (K + 63) / 64;

@@ -40,6 +40,8 @@ struct GemmPlan {
   // ---- B operand ----
   CUtensorMap tmap_b;   // 2D [rows][K_total] bf16, K-major
   int b_rows_per_class; // EPI_OUTCONV: row offset multiplier for the ROI class (0 otherwise)
+  const void* b_ptr;    // W base / rows / row length (elements): lets gemm_tc_launch re-tile W for the CTA-pair kernel
+  long long b_rows, b_ktot;
   // ---- problem ----
   int m_tiles, n_tiles;
   int n_major;          // tile order: 0 = consecutive CTAs share an A tile (m-major), 1 = they share a B tile (n-major)

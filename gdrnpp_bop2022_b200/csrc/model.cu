@@ -353,6 +353,7 @@ int plan_b(GemmPlan& p, const void* W, long long rows, long long Ktot, int block
   uint32_t box[2] = {64, (uint32_t)block_n};
   p.N = N;
   p.n_tiles = (N + block_n - 1) / block_n;
+  p.b_ptr = W; p.b_rows = rows; p.b_ktot = (long long)S * Ktot;
   return make_tmap_bf16(&p.tmap_b, W, 2, dims, str, box);
 }
 
