@@ -349,11 +349,26 @@ def main():
         gemm_n = n3[0]
     L.gdrn_model_set_profiling(model._handle, 0)
     gemm_tflops = BATCH * GEMM_GFLOP_PER_ROI_EXECUTED / gemm_ms if gemm_ms > 0 else 0.0  # GFLOP / ms = TFLOP/s
+    # DRAM bytes per GEMM launch from the committed ncu capture of this same command (profiles/, tools/make_traffic.py)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            fams = json.load(open(tpath))["families"]
+            fam = [v for k, v in fams.items() if k.startswith("gemm")]
+            if fam:
+                traffic = fam[0]["dram_bytes_per_launch"]
+                traffic_src = "profiles/r01_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean over the %d " \
+                              "tcgen05 GEMM launches of one step)" % fam[0]["launches"]
+        except Exception:  # noqa: BLE001
+            traffic = None
     step_ms = ms_total / args.steps
     roofline = {
-        "bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05/TMA implicit GEMM, all %d launches of a step)" % gemm_n,
+        "bound": "tensor", "kernel": "gemm_tc_kernel + gemm_pair_kernel (tcgen05/TMA implicit GEMM, all %d launches of a step)" % gemm_n,
         "achieved": gemm_tflops, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-        "frac": gemm_tflops / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+        "frac": gemm_tflops / peaks["bf16_tflops"], "traffic": traffic, "traffic_source": traffic_src,
+        "algorithmic_flop_per_launch": BATCH * GEMM_GFLOP_PER_ROI_EXECUTED * 1e9 / max(gemm_n, 1),
+        "avg_launch_us": gemm_ms * 1e3 / max(gemm_n, 1), "peak_source": peaks["source"],
         "gemm_ms_per_step": gemm_ms, "dwconv_ms_per_step": dw_ms, "other_ms_per_step": other_ms,
         "whole_step_tflops_reference_flops": BATCH * GFLOP_PER_ROI_REFERENCE / step_ms,
         "whole_step_frac_reference_flops": BATCH * GFLOP_PER_ROI_REFERENCE / step_ms / peaks["bf16_tflops"],

@@ -39,7 +39,7 @@ assert len(st) >= 2, "need at least one full step in the capture"
 step = [per[k] for k in ids[st[0]:st[1]]]
 agg = collections.defaultdict(lambda: {"launches": 0, "dram_read": 0.0, "dram_write": 0.0, "us": 0.0})
 for k in step:
-    fam = "gemm_tc_kernel" if k["name"].startswith("gemm_tc_kernel") else k["name"]
+    fam = "gemm (gemm_tc_kernel + gemm_pair_kernel, all tcgen05 launches)" if k["name"].startswith(("gemm_tc_kernel", "gemm_pair_kernel")) else k["name"]
     a = agg[fam]
     a["launches"] += 1
     a["dram_read"] += k.get("dram__bytes_read.sum", 0)

@@ -43,6 +43,8 @@ def launch_summary(path):
             data.append(dict(zip(hdr, r)))
     agg = collections.defaultdict(lambda: [0, 0.0])
     for d in data:
+        if not d["Metric Name"].startswith("gpu__time_duration"):
+            continue
         v = float(d["Metric Value"].replace(",", ""))
         if d["Metric Unit"] == "ns":
             v /= 1e3
@@ -50,7 +52,7 @@ def launch_summary(path):
         agg[k][0] += 1
         agg[k][1] += v
     tot = sum(v[1] for v in agg.values())
-    lines = [f"{len(data)} launches, {tot:.1f} us total (cold-cache, serialised: compare SHARES)"]
+    lines = [f"{sum(v[0] for v in agg.values())} launches, {tot:.1f} us total (cold-cache, serialised: compare SHARES)"]
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         lines.append(f"{t:10.1f} us {n:5d}x {100 * t / tot:5.1f}%  avg {t / n:8.1f} us  {k}")
     return "\n".join(lines)
