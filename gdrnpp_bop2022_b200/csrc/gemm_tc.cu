@@ -623,11 +623,12 @@ __device__ __forceinline__ void epilogue_tile_staged_t(const GemmPlan& p, int m_
 // issues a single cp.async.bulk.tensor store per tile.  No address arithmetic, LDS or STG in the flush; rows beyond
 // M are clipped by the tensor map.  The residual of EPI_RESID is read by its owner thread (64 contiguous bytes per
 // half, register-prefetched one half ahead).
-template <int BLOCK_N, int EPI, bool F32>
+template <int BLOCK_N, int EPI, bool F32, int NEW = NUM_EPI_WARPS>
 __device__ __forceinline__ void epilogue_tile_tma(const GemmPlan& p, int m_tile, int n_tile, uint32_t tmem_acc, int ew,
                                                   int lane, uint8_t* stg) {
   static_assert(BLOCK_N >= 128, "TMA-store epilogue needs BLOCK_N >= 128");
-  constexpr int CPW = BLOCK_N / 2;      // columns per warp
+  constexpr int CPW = BLOCK_N / (NEW / 4);  // columns per warp (NEW / 4 warps share one TMEM lane quarter)
+  static_assert(CPW * (F32 ? 4 : 2) >= 128, "a warp must own at least one 128-byte row segment");
   constexpr int CH = F32 ? 16 : 32;     // columns per 64-byte half row (one tcgen05.ld)
   constexpr int GW = 2 * CH;            // columns per staged 128-byte row (one TMA store)
   const int q = ew & 3, half = ew >> 2;
@@ -668,12 +669,11 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmPlan& p, int m_tile,
     for (int h = 0; h < 2; ++h) {
       const int c = g + h * CH;
       const int col = n0 + c;
-      float bias[CH];
-#pragma unroll
-      for (int j = 0; j < CH; j += 4) {
-        const float4 b4 = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        bias[j] = b4.x; bias[j + 1] = b4.y; bias[j + 2] = b4.z; bias[j + 3] = b4.w;
-      }
+      // bias is read four columns at a time right where it is consumed (keeps the live register set small
+      // enough for the 16-warp epilogue variant); the loads are warp-uniform L1 hits
+      auto bias4 = [&](int j) {
+        return p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
       float x[EPI == EPI_RESID ? CH : 1], gm[EPI == EPI_RESID ? CH : 1];
       if constexpr (EPI == EPI_RESID) {
 #pragma unroll
@@ -697,27 +697,40 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmPlan& p, int m_tile,
       if constexpr (F32) {
         if constexpr (EPI == EPI_RESID) {
 #pragma unroll
-          for (int j = 0; j < CH; ++j) v[j] = fmaf(gm[j], v[j] + bias[j], x[j]);
+          for (int j = 0; j < CH; j += 4) {
+            const float4 b4 = bias4(j);
+            v[j] = fmaf(gm[j], v[j] + b4.x, x[j]); v[j + 1] = fmaf(gm[j + 1], v[j + 1] + b4.y, x[j + 1]);
+            v[j + 2] = fmaf(gm[j + 2], v[j + 2] + b4.z, x[j + 2]); v[j + 3] = fmaf(gm[j + 3], v[j + 3] + b4.w, x[j + 3]);
+          }
         } else {
 #pragma unroll
-          for (int j = 0; j < CH; ++j) v[j] += bias[j];
+          for (int j = 0; j < CH; j += 4) {
+            const float4 b4 = bias4(j);
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          }
         }
 #pragma unroll
         for (int j = 0; j < CH; j += 4)
           dst[(h * 4 + (j >> 2)) ^ sw] = make_uint4(__float_as_uint(v[j]), __float_as_uint(v[j + 1]),
                                                     __float_as_uint(v[j + 2]), __float_as_uint(v[j + 3]));
       } else {
-#pragma unroll
-        for (int j = 0; j < CH; ++j) v[j] += bias[j];
         if (EPI == EPI_GELU && p.gelu_mode == 1) {
 #pragma unroll
           for (int j = 0; j < CH; j += 8) {
+            const float4 ba = bias4(j), bb = bias4(j + 4);
+            v[j] += ba.x; v[j + 1] += ba.y; v[j + 2] += ba.z; v[j + 3] += ba.w;
+            v[j + 4] += bb.x; v[j + 5] += bb.y; v[j + 6] += bb.z; v[j + 7] += bb.w;
             uint4 w;
             w.x = gelu_pack2_f16(v[j], v[j + 1]); w.y = gelu_pack2_f16(v[j + 2], v[j + 3]);
             w.z = gelu_pack2_f16(v[j + 4], v[j + 5]); w.w = gelu_pack2_f16(v[j + 6], v[j + 7]);
             dst[(h * 4 + (j >> 3)) ^ sw] = w;
           }
         } else {
+#pragma unroll
+          for (int j = 0; j < CH; j += 4) {
+            const float4 b4 = bias4(j);
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          }
           if constexpr (EPI == EPI_GELU) {
             if (p.gelu_mode == 3) {
 #pragma unroll
@@ -991,14 +1004,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 //   tfull[a]  (each CTA) <- tcgen05.commit multicast after the last k-chunk of a tile
 //   tempty[a] (leader)   <- the 8 epilogue warps of BOTH CTAs (remote mbarrier arrive from the peer)
 // ================================================================================================================
-constexpr int P2_STAGES = 6;
+// NEW = epilogue warps per CTA: 8 (6-stage ring) or 16 (4-stage ring; four warps per scheduler hide the latency of the
+// GELU epilogue, which with two warps per scheduler runs at ~0.5 IPC and bounds the short-K fc1 GEMMs).
 constexpr int P2_B_BYTES = 128 * BLOCK_K * 2;                 // this CTA's half of the 256 weight rows
 constexpr int P2_STAGE_BYTES = A_STAGE_BYTES + P2_B_BYTES;    // 32 KB
-constexpr int P2_SMEM_BYTES = P2_STAGES * P2_STAGE_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES + 256 + 1024;
+template <int NEW> struct P2Cfg {
+  static constexpr int STAGES = NEW == 16 ? 4 : 6;
+  static constexpr int THREADS = 128 + 32 * NEW;
+  static constexpr int SMEM_BYTES = STAGES * P2_STAGE_BYTES + NEW * EPI_STAGE_BYTES + 256 + 1024;
+};
 
-template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) gemm_pair_kernel(const __grid_constant__ GemmPlan p) {
+template <int EPI, int NEW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P2Cfg<NEW>::THREADS, 1) gemm_pair_kernel(const __grid_constant__ GemmPlan p) {
   constexpr int BLOCK_N = 256;
+  constexpr int P2_STAGES = P2Cfg<NEW>::STAGES;
+  constexpr int NUM_EPI_WARPS = NEW;   // shadows the file-scope constant inside this kernel
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
@@ -1095,8 +1115,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) gemm
       const uint32_t aphase = (it >> 1) & 1;
       ptx::mbar_wait(tfull_bar(as), aphase);
       ptx::tc_fence_after();
-      epilogue_tile_staged<BLOCK_N, EPI>(p, m_tile, n_tile, tmem_base + as * 256, ew, lane,
-                                         stage_base + ew * EPI_STAGE_BYTES);
+      constexpr bool kF32 = (EPI == EPI_RESID);
+      if constexpr (EPI == EPI_STORE) {
+        if (p.out_f32) epilogue_tile_tma<BLOCK_N, EPI, true, NEW>(p, m_tile, n_tile, tmem_base + as * 256, ew, lane, stage_base + ew * EPI_STAGE_BYTES);
+        else epilogue_tile_tma<BLOCK_N, EPI, false, NEW>(p, m_tile, n_tile, tmem_base + as * 256, ew, lane, stage_base + ew * EPI_STAGE_BYTES);
+      } else {
+        epilogue_tile_tma<BLOCK_N, EPI, kF32, NEW>(p, m_tile, n_tile, tmem_base + as * 256, ew, lane, stage_base + ew * EPI_STAGE_BYTES);
+      }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_shared(tempty_bar(as), 0));
@@ -1113,10 +1138,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) gemm
   }
 }
 
-template <int EPI>
+template <int EPI, int NEW>
 int launch_pair(const GemmPlan& plan, cudaStream_t stream) {
   static bool configured = false;
-  auto kfn = gemm_pair_kernel<EPI>;
+  auto kfn = gemm_pair_kernel<EPI, NEW>;
+  constexpr int P2_SMEM_BYTES = P2Cfg<NEW>::SMEM_BYTES;
+  constexpr int NUM_THREADS = P2Cfg<NEW>::THREADS;   // shadows the file-scope constant
   if (!configured) {
     GDRN_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
     configured = true;
@@ -1188,20 +1215,22 @@ int gemm_tc_launch(const GemmPlan& plan_in, int block_n, cudaStream_t stream) {
     if (pair_on < 0) { const char* e = getenv("GDRN_GEMM_PAIR"); pair_on = e ? atoi(e) : 1; }
     // measured (profiles/): the pair kernel wins when the mainloop dominates (K >= 1024: fc2, stage-3 fc1) and loses
     // a few % on short-K tiles whose time is the GELU epilogue plus per-tile pair handshakes
+    static int gelu16 = -1;   // GDRN_GELU16=0: GELU GEMMs keep the 8-warp epilogue (and the K threshold below)
+    if (gelu16 < 0) { const char* e = getenv("GDRN_GELU16"); gelu16 = e ? atoi(e) : 1; }
     static int pair_min_k = -1;
     if (pair_min_k < 0) { const char* e = getenv("GDRN_GEMM_PAIR_MIN_KCHUNKS"); pair_min_k = e ? atoi(e) : 16; }
     if (pair_on && plan.use_tma_store && block_n == 256 && plan.num_taps == 1 && plan.taps[0].c0 == 0 &&
         plan.taps[0].d1 == 0 && plan.taps[0].b_off == 0 && plan.b_ptr != nullptr && plan.N % 256 == 0 &&
         (plan.epi == EPI_GELU || plan.epi == EPI_RESID || plan.epi == EPI_STORE) && plan.M >= 256 * 16 &&
-        plan.k_chunks >= pair_min_k) {
+        (plan.k_chunks >= pair_min_k || (plan.epi == EPI_GELU && gelu16))) {
       const uint64_t dims[2] = {(uint64_t)plan.b_ktot, (uint64_t)plan.b_rows};
       const uint64_t str[1] = {(uint64_t)plan.b_ktot * 2};
       const uint32_t box[2] = {64, 128};
       int rc = make_tmap_bf16(&plan.tmap_b, plan.b_ptr, 2, dims, str, box);
       if (rc != GDRN_OK) return rc;
-      if (plan.epi == EPI_GELU) return launch_pair<EPI_GELU>(plan, stream);
-      if (plan.epi == EPI_RESID) return launch_pair<EPI_RESID>(plan, stream);
-      return launch_pair<EPI_STORE>(plan, stream);
+      if (plan.epi == EPI_GELU) return gelu16 ? launch_pair<EPI_GELU, 16>(plan, stream) : launch_pair<EPI_GELU, 8>(plan, stream);
+      if (plan.epi == EPI_RESID) return launch_pair<EPI_RESID, 8>(plan, stream);
+      return launch_pair<EPI_STORE, 8>(plan, stream);
     }
   }
 #define GDRN_GEMM_CASE(BN, E) \
