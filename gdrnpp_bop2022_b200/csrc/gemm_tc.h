@@ -81,6 +81,12 @@ struct GemmPlan {
 // block_n in {16, 64, 80, 128, 256}
 int gemm_tc_launch(const GemmPlan& plan, int block_n, cudaStream_t stream);
 
+// Fused ConvNeXt MLP block (C = 128): x += gamma * (W2 . gelu(W1 . A + b1) + b2), hidden activation kept on chip.
+// A bf16 [M, C]; W1 bf16 [4C, C]; W2 bf16 [C, 4C]; x fp32 [M, C] updated in place.
+int mlp_fused_supported(int C, long long M);
+int mlp_fused_launch(const void* A, const void* W1, const float* b1, const void* W2, const float* b2, const float* gamma,
+                     float* x, long long M, int C, cudaStream_t stream);
+
 // tensor-map builders (bf16). dims/strides innermost first; strides in BYTES for dims 1..rank-1.
 // fp32, no swizzle, zero OOB fill (dense [..][box0] shared-memory image)
 int make_tmap_f32_plain(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,

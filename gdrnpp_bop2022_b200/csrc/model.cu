@@ -66,6 +66,7 @@ struct GdrnModel {
   int num_classes;
   int max_batch;
   int in_res = 256, out_res = 64;
+  int fuse_mlp = 1;   // fused fc1->GELU->fc2 kernel where supported (env GDRN_MLP_FUSED=0 disables)
   int precise = 0;    // 0: bf16 operands (fast); 1: split-bf16 x3 products, fp32 FC stack, erf GELU
   int gelu_mode = 1;  // fc1 epilogue GELU: 1 = packed-half2 tanh.approx (default, fastest), 0 = fp32 ex2/rcp form, 2 = fp32 tanh.approx; env GDRN_GELU_MODE
   // ---- weights (device) ----
@@ -448,6 +449,7 @@ extern "C" int gdrn_model_create_ex(GdrnModel** out, const char* arch, int num_c
   m->max_batch = max_batch;
   m->precise = precision;
   if (const char* e = getenv("GDRN_GELU_MODE")) m->gelu_mode = atoi(e);
+  if (const char* e = getenv("GDRN_MLP_FUSED")) m->fuse_mlp = atoi(e);
   if (!build_weights(m)) {
     gdrn_model_destroy(m);
     gdrn_set_last_error(__FILE__, __LINE__, "model_create: cudaMalloc failed");
@@ -570,6 +572,11 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
     for (int i = 0; i < a.depths[s]; ++i) {
       const BlockW& bw = m->blocks[s][i];
       RCP(1, launch_dwconv_ln(w.X, bw.dw_w, bw.dw_b, bw.ln_w, bw.ln_b, w.A, B, res, res, C, 1e-6f, PR, st));
+      if (!PR && m->fuse_mlp && m->gelu_mode == 1 && mlp_fused_supported(C, M)) {
+        // stage 0: fc1 -> GELU -> fc2 -> residual in one kernel (no 4C-wide Hb round trip through HBM)
+        RCP(0, mlp_fused_launch(w.A, bw.fc1_w, bw.fc1_b, bw.fc2_w, bw.fc2_b, bw.gamma, w.X, M, C, st));
+        continue;
+      }
       reset();
       RC(plan_a2d(p, w.A, M, C, S));
       RC(plan_b(p, bw.fc1_w, 4 * C, C, 256, 4 * C, S));

@@ -1,6 +1,6 @@
 """Scratch: dwconv phase trace for one forward at B=64 (GDRN_DW_TRACE=1)."""
 import os, sys
-os.environ["GDRN_DW_TRACE"] = "1"
+os.environ.setdefault("GDRN_DW_TRACE", "1")
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
