@@ -214,6 +214,20 @@ def test_forward_is_deterministic_and_batch_invariant(dev):
     assert (o8["trans"][2:5] - o3["trans"]).abs().max().item() < 1e-4
 
 
+def test_fused_mlp_matches_unfused(dev, monkeypatch):
+    """Stage-0 blocks run fc1 -> GELU -> fc2 -> residual in one kernel when the batch is large enough (B >= 5); the
+    two-kernel path must give the same poses (same operands, same accumulation order; only scheduling differs)."""
+    outs = []
+    for fused in ("0", "1"):
+        monkeypatch.setenv("GDRN_MLP_FUSED", fused)
+        _, _, _, out = _run_model(dev, 8, seed=21)
+        outs.append(out)
+    assert _rot_err(outs[0]["rot"].cpu(), outs[1]["rot"].cpu()).max().item() < 1e-3
+    assert (outs[0]["trans"] - outs[1]["trans"]).abs().max().item() < 1e-4
+    for k in ("mask", "coor_x", "region"):
+        assert (outs[0][k] - outs[1][k]).abs().max().item() < 2e-2, k
+
+
 def test_forward_error_paths(dev, lib):
     from gdrnpp_bop2022_b200 import _lib as L
     from gdrnpp_bop2022_b200.gdrn_model import GDRN_DoubleMask, default_cfg
