@@ -91,6 +91,36 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Bounded cluster-scope acquire wait on a barrier of THIS CTA that peers complete with st.async transaction bytes.
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  long long t0 = 0;
+  int spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins == 64) t0 = clock64();
+    if (spins > 64 && (clock64() - t0) > 4000000000LL) {
+      printf("gdrn: cluster mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar,
+             parity);
+      __trap();
+    }
+  }
+}
+// 8-byte store into a peer CTA's shared memory that completes transaction bytes on a barrier of that peer:
+// data and signal travel together, no fence and no cluster-wide barrier on the sender side.
+__device__ __forceinline__ void st_async_f32x2(uint32_t remote_addr, float a, float b, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+               ::"r"(remote_addr), "f"(a), "f"(b), "r"(remote_bar)
+               : "memory");
+}
+
 // ---- TMA ------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");

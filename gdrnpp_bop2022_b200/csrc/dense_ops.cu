@@ -286,7 +286,7 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
   float* tile = smem_dw;                      // [IH][IW][CPC]
   float* wsm = tile + IH * IW * CPC;          // [49][CPC]
   float2* s_parts = reinterpret_cast<float2*>(wsm + 49 * CPC);  // [8 ranks * WPR][NPIX] (sum, M2) partials, pushed by peers
-  unsigned long long* tma_bar_p = reinterpret_cast<unsigned long long*>(s_parts + 8 * WPR * NPIX);
+  unsigned long long* tma_bar_p = reinterpret_cast<unsigned long long*>(s_parts + 8 * WPR * NPIX);   // [0] TMA, [1] partials
 
   cg::cluster_group cluster = cg::this_cluster();
   const int nrank = (int)cluster.num_blocks();
@@ -302,9 +302,13 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
   const int cl = 2 * pair;                    // first channel of the pair (CTA-local)
 
   const uint32_t bar = ptx::smem_u32(tma_bar_p);
+  const uint32_t parts_bar = bar + 8;
   if (tid == 0) {
     ptx::mbar_init(bar, 1);
+    ptx::mbar_init(parts_bar, 1);
     ptx::fence_barrier_init();
+    // every (rank, 64-channel warp group, pixel) partial of the cluster lands here as one 8-byte st.async
+    ptx::mbar_arrive_expect_tx(parts_bar, (uint32_t)(nrank * WPR * NPIX * sizeof(float2)));
   }
   __syncthreads();
   if (tid == 0) {
@@ -312,6 +316,9 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
     ptx::tma_load_2d(ptx::smem_u32(wsm), &tmap_w, bar, c0, 0);          // this CTA's 49 x CPC filter taps
     ptx::tma_load_4d(ptx::smem_u32(tile), &tmap_x, bar, c0, x0 - 3, y0 - 3, b);
   }
+  // split-phase cluster barrier: "my barriers exist" is announced here and only waited for right before the push
+  // (a conv later), so the start-up skew between the CTAs of a cluster is off the critical path
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
   f32x2_t acc[R][TW];
   {
     const f32x2_t bv = f2_pack(__ldg(bias + c0 + cl), __ldg(bias + c0 + cl + 1));
@@ -381,15 +388,19 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
     m2_loc = lane_transpose_reduce<NV>(a, lane);
   }
   const int nparts = nrank * WPR;
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");   // every peer has initialised its partials barrier
   {
     const int part = (int)cluster.block_rank() * WPR + wc;
     if ((lane % LPP) == 0) {
-      const float2 v = make_float2(s_loc, m2_loc);
-      for (int rk = 0; rk < nrank; ++rk) cluster.map_shared_rank(s_parts, rk)[part * NPIX + pix] = v;
+      // push with st.async: the 8 bytes complete transaction bytes on the peer's barrier, so there is no fence and no
+      // cluster-wide rendezvous -- a CTA continues as soon as ITS partials are in, stragglers only delay themselves
+      const uint32_t la = ptx::smem_u32(s_parts + part * NPIX + pix);
+      for (int rk = 0; rk < nrank; ++rk)
+        ptx::st_async_f32x2(ptx::mapa_shared(la, rk), s_loc, m2_loc, ptx::mapa_shared(parts_bar, rk));
     }
   }
   if (trc) tt[3] = clock64();
-  cluster.sync();
+  ptx::mbar_wait_cluster(parts_bar, 0);
   if (trc) tt[4] = clock64();
   float mean_p, rstd_p;
   {
@@ -822,7 +833,7 @@ static int launch_dwconv_cluster(const float* x, const float* w49c, const float*
   constexpr int IW = TW + 6, IH = TH + 6;
   constexpr int NPIX = TW * TH;
   constexpr int NTHREADS = (CPC / 2) * TH / R;
-  const size_t smem = (size_t)(IH * IW * CPC + 49 * CPC + 2 * 8 * (CPC / 64) * NPIX) * sizeof(float) + 16;
+  const size_t smem = (size_t)(IH * IW * CPC + 49 * CPC + 2 * 8 * (CPC / 64) * NPIX) * sizeof(float) + 32;
   auto kfn = dwconv_ln_cluster_kernel<TW, TH, CPC, R, MINB>;
   static bool configured = false;
   if (!configured) {
