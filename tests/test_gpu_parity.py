@@ -26,6 +26,9 @@ def _lib():
     (128, 128, 64, 128, 0, 1), (300, 128, 64, 128, 0, 0), (128, 256, 256, 256, 0, 1), (1000, 512, 128, 256, 1, 0),
     (4096, 128, 512, 128, 2, 1), (4096, 256, 1024, 256, 2, 1), (64, 1024, 8192, 64, 1, 0), (64, 9, 256, 16, 0, 1),
     (1, 256, 64, 256, 0, 1), (129, 512, 2048, 256, 1, 0),
+    # CTA-pair (cta_group::2) kernel: M >= 4096, BLOCK_N 256; ragged M (odd number of 128-row tiles + a partial tile),
+    # short K with the 16-warp GELU epilogue, fp32 and bf16 plain stores
+    (4296, 512, 1024, 256, 1, 0), (4224, 256, 128, 256, 1, 0), (8192, 256, 2048, 256, 0, 1), (4100, 256, 1024, 256, 0, 0),
 ])
 def test_gemm_vs_torch(dev, lib, M, N, K, bn, epi, f32):
     """tcgen05 kernel vs a plain fp32 torch reference of the same op (bf16 operands, fp32 accumulate)."""
@@ -49,7 +52,7 @@ def test_gemm_vs_torch(dev, lib, M, N, K, bn, epi, f32):
     assert err < (2e-4 if is_f32 else 0.04), err
 
 
-@pytest.mark.parametrize("M,N,K,bn", [(4096, 256, 1024, 256), (1000, 128, 512, 128), (300, 512, 128, 256)])
+@pytest.mark.parametrize("M,N,K,bn", [(4096, 256, 1024, 256), (4296, 256, 1024, 256), (1000, 128, 512, 128), (300, 512, 128, 256)])
 def test_gemm_residual_in_place(dev, lib, M, N, K, bn):
     """EPI_RESID with out == resid (how the model calls it): the epilogue turns into a TMA reduce-add
     (x += gamma*(acc+bias) performed by the L2).  M not a multiple of 128 checks the tensor-map row clipping."""
