@@ -67,6 +67,9 @@ _SIGNATURES = {
     ),
     "rast_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
     "gdrn_depth_refine_step": (c_int, [c_void_p] * 6 + [c_int, c_int, c_float, c_void_p]),
+    "gdrn_crop_resize_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                    c_void_p]),
+    "gdrn_crop_resize_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES.keys())

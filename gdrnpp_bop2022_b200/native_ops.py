@@ -349,3 +349,78 @@ def uncertainty_pnp_batched(pts2d, pts3d, wgt2d, K, init_rt):
     _lib.check(_lib.lib().upnp_batched(*[_lib.ptr(t) for t in ts], _lib.ptr(res), pn, n, _lib.current_stream()),
                "upnp_batched")
     return res
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ROI crop + resize (core/utils/data_utils.py:115-189: crop_resize_by_warp_affine, get_affine_transform)
+# ---------------------------------------------------------------------------------------------------------------
+def get_affine_transform(center, scale, rot, output_size, shift=(0.0, 0.0), inv=False):
+    """2x3 float64 forward matrix, same contract as the reference's get_affine_transform (data_utils.py:136-189):
+    the affine map taking (center, center + rotated (0, -scale_w/2), their perpendicular third point) onto
+    (out centre, out centre + (0, -out_w/2), third point).  The reference builds the three point pairs in float32
+    and solves with cv2.getAffineTransform; here the same float32 point pairs are solved in closed form in float64
+    (equal to 1e-12; the warp quantises coordinates to 1/32 pixel, so crops are identical)."""
+    center = np.asarray(center, np.float32)
+    if np.isscalar(scale):
+        scale = np.array([scale, scale], np.float32)
+    scale = np.asarray(scale, np.float32)
+    if np.isscalar(output_size):
+        output_size = (output_size, output_size)
+    shift = np.asarray(shift, np.float32)
+    src_w, dst_w, dst_h = scale[0], output_size[0], output_size[1]
+    rot_rad = np.pi * rot / 180
+    sn, cs = np.sin(rot_rad), np.cos(rot_rad)
+    src_dir = np.array([0 * cs - (src_w * -0.5) * sn, 0 * sn + (src_w * -0.5) * cs])
+    dst_dir = np.array([0, dst_w * -0.5], np.float32)
+    src = np.zeros((3, 2), np.float32)
+    dst = np.zeros((3, 2), np.float32)
+    src[0, :] = center + scale * shift
+    src[1, :] = center + src_dir + scale * shift
+    dst[0, :] = [dst_w * 0.5, dst_h * 0.5]
+    dst[1, :] = np.array([dst_w * 0.5, dst_h * 0.5], np.float32) + dst_dir
+
+    def third(a, b):
+        d = a - b
+        return b + np.array([-d[1], d[0]], np.float32)
+
+    src[2, :] = third(src[0], src[1])
+    dst[2, :] = third(dst[0], dst[1])
+    a, b = (dst, src) if inv else (src, dst)
+    A = np.concatenate([a.astype(np.float64), np.ones((3, 1))], axis=1)   # [3,3]: rows (x, y, 1)
+    return np.linalg.solve(A, b.astype(np.float64)).T.copy()               # [2,3]
+
+
+def _affine_batch(M, device):
+    M = np.ascontiguousarray(np.asarray(M, np.float64).reshape(-1, 6))
+    return torch.from_numpy(M).to(device), M.shape[0]
+
+
+def crop_resize_image(image, M, output_size, pixel_mean=(0.0, 0.0, 0.0), pixel_std=(255.0, 255.0, 255.0)):
+    """Batched cv2.warpAffine(image, M[i], (w, h), INTER_LINEAR) + normalize_image for an HxWxC uint8 CUDA image:
+    returns roi_img [n, C, h, w] float32 (predictor_gdrn.py:417-422).  M: [n,2,3] float64 forward transforms."""
+    _check_cuda_contig(image, "image")
+    assert image.dtype == torch.uint8 and image.dim() == 3
+    H, W, C = image.shape
+    ow, oh = (output_size, output_size) if np.isscalar(output_size) else output_size
+    Md, n = _affine_batch(M, image.device)
+    out = torch.empty((n, C, int(oh), int(ow)), dtype=torch.float32, device=image.device)
+    mean = (ctypes.c_double * C)(*[float(v) for v in list(pixel_mean)[:C]])
+    std = (ctypes.c_double * C)(*[float(v) for v in list(pixel_std)[:C]])
+    _lib.check(_lib.lib().gdrn_crop_resize_u8(_lib.ptr(image), H, W, C, _lib.ptr(Md), n, int(oh), int(ow), mean, std,
+                                              _lib.ptr(out), _lib.current_stream()), "gdrn_crop_resize_u8")
+    return out
+
+
+def crop_resize_float(src, M, output_size, nearest=False):
+    """Batched cv2.warpAffine on an HxW(xC) float32 CUDA array (INTER_LINEAR, or INTER_NEAREST for depth):
+    returns [n, C, h, w] float32 (roi_coord_2d / roi_depth, predictor_gdrn.py:425-438)."""
+    _check_cuda_contig(src, "src")
+    assert src.dtype == torch.float32 and src.dim() in (2, 3)
+    H, W = src.shape[:2]
+    C = 1 if src.dim() == 2 else src.shape[2]
+    ow, oh = (output_size, output_size) if np.isscalar(output_size) else output_size
+    Md, n = _affine_batch(M, src.device)
+    out = torch.empty((n, C, int(oh), int(ow)), dtype=torch.float32, device=src.device)
+    _lib.check(_lib.lib().gdrn_crop_resize_f32(_lib.ptr(src), H, W, C, _lib.ptr(Md), n, int(oh), int(ow), int(bool(nearest)),
+                                               _lib.ptr(out), _lib.current_stream()), "gdrn_crop_resize_f32")
+    return out

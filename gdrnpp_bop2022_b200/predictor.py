@@ -6,14 +6,14 @@ Same method names and data contracts: ``preprocessing(outputs, image, depth_img)
 ``process_depth_refine(data_dict, out_dict)``.  Differences that the absence of datasets/checkpoints forces:
 the constructor takes the already-loaded pieces (state_dict or checkpoint path, camera matrix, meshes, extents)
 instead of dataset paths.  ``inference`` and ``process_depth_refine`` run entirely in libgdrn_b200.so;
-``preprocessing`` (crop_resize_by_warp_affine, SURVEY.md §8f rank 1, "next") is a plain torch bilinear crop for
-now and is NOT part of the measured hot path.
+``preprocessing`` crops the ROIs with the batched GPU restatement of cv2.warpAffine (crop_resize_by_warp_affine,
+SURVEY.md §8f rank 1): bit-identical crops to the reference's per-ROI host loop.
 """
 import numpy as np
 import torch
-import torch.nn.functional as F
 
 from .gdrn_model import GDRN_DoubleMask, default_cfg
+from .native_ops import crop_resize_float, crop_resize_image, get_affine_transform
 from .renderer import Model3D, depth_refine, get_K_crop_resize
 
 
@@ -49,44 +49,51 @@ class GdrnPredictor:
         if models is not None:
             self.ren_models = [Model3D(*models[i], device=self.device) for i in self.obj_ids]
 
-    # ---- preprocessing (predictor_gdrn.py:301-476; bilinear affine crop) -----------------------
+    # ---- preprocessing (predictor_gdrn.py:301-476) ---------------------------------------------
     def preprocessing(self, outputs, image, depth_img=None):
-        """outputs: [n,7] detections (x1,y1,x2,y2,score,cls_score,cls) like the YOLOX stage; image: HxWx3 BGR uint8."""
+        """outputs: [n,7] detections (x1,y1,x2,y2,score,cls_score,cls) like the YOLOX stage; image: HxWx3 BGR uint8;
+        depth_img: HxW (scaled by depth_scale like the reference).  Per-ROI bookkeeping follows predictor_gdrn.py:396-415
+        (centre, bw/bh >= 1, scale = min(max(bw,bh)*DZI_PAD_SCALE, max(H,W)), resize_ratio = out_res/scale); the crops
+        -- the reference's per-ROI cv2.warpAffine loop (:417-438) -- are three batched GPU launches with OpenCV's exact
+        arithmetic (csrc/crop_resize.cu)."""
         dev = self.device
-        det = torch.as_tensor(outputs, dtype=torch.float32)
+        det = np.asarray(outputs.detach().cpu() if torch.is_tensor(outputs) else outputs, np.float32).reshape(-1, 7)
         n = det.shape[0]
-        im = torch.as_tensor(image).to(dev).permute(2, 0, 1).float()[None] / 255.0
-        H, W = im.shape[-2:]
-        x1, y1, x2, y2 = det[:, 0], det[:, 1], det[:, 2], det[:, 3]
-        cx, cy = (x1 + x2) / 2, (y1 + y2) / 2
-        bw, bh = (x2 - x1).clamp_min(1), (y2 - y1).clamp_min(1)
-        scale = torch.clamp(torch.maximum(bw, bh) * self.dzi_pad_scale, max=float(max(H, W)))
-
-        def crop(src, res):
-            u = torch.arange(res, dtype=torch.float32)
-            sx = cx[:, None] + (u[None] - res / 2) * (scale[:, None] / res)
-            sy = cy[:, None] + (u[None] - res / 2) * (scale[:, None] / res)
-            gx = (sx / (W - 1) * 2 - 1)[:, None, :].expand(n, res, res)
-            gy = (sy / (H - 1) * 2 - 1)[:, :, None].expand(n, res, res)
-            grid = torch.stack([gx, gy], -1).to(dev)
-            return F.grid_sample(src.expand(n, -1, -1, -1), grid, mode="bilinear", padding_mode="zeros", align_corners=True)
-
-        roi_img = crop(im, 256)
-        yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32) / H, torch.arange(W, dtype=torch.float32) / W, indexing="ij")
-        coord = torch.stack([xx, yy])[None].to(dev)
-        roi_coord_2d = crop(coord, 64)
-        cls = det[:, 6].long()
-        ext = torch.stack([torch.from_numpy(self.extents[self.obj_ids[int(c)]]) for c in cls])
+        image = np.ascontiguousarray(image.detach().cpu().numpy() if torch.is_tensor(image) else image, np.uint8)
+        H, W = image.shape[:2]
+        in_res, out_res = 256, 64
+        centers = np.zeros((n, 2), np.float32)
+        whs = np.zeros((n, 2), np.float32)
+        scales = np.zeros((n,), np.float32)
+        M_in, M_out = np.zeros((n, 2, 3)), np.zeros((n, 2, 3))
+        for i in range(n):
+            x1, y1, x2, y2 = det[i, :4]
+            c = np.array([0.5 * (x1 + x2), 0.5 * (y1 + y2)])
+            bw, bh = max(x2 - x1, 1), max(y2 - y1, 1)
+            scale = min(max(bh, bw) * self.dzi_pad_scale, max(H, W)) * 1.0
+            centers[i], whs[i], scales[i] = c.astype(np.float32), (bw, bh), scale
+            M_in[i] = get_affine_transform(c, scale, 0, in_res)
+            M_out[i] = get_affine_transform(c, scale, 0, out_res)
+        img_d = torch.from_numpy(image).to(dev)
+        roi_img = crop_resize_image(img_d, M_in, in_res)       # PIXEL_MEAN 0 / PIXEL_STD 255 (cfg :67-68)
+        # get_2d_coord_np(W, H, low=0, high=1) (data_utils.py:304-323): linspace(endpoint=False) grid, [H,W,2] (x, y)
+        xs = torch.from_numpy(np.linspace(0, 1, W, endpoint=False, dtype=np.float32))
+        ys = torch.from_numpy(np.linspace(0, 1, H, endpoint=False, dtype=np.float32))
+        coord = torch.stack([xs[None, :].expand(H, W), ys[:, None].expand(H, W)], dim=2).contiguous().to(dev)
+        roi_coord_2d = crop_resize_float(coord, M_out, out_res)
+        cls = torch.from_numpy(det[:, 6].astype(np.int64))
+        ext = torch.stack([torch.from_numpy(self.extents[self.obj_ids[int(c)]]) for c in cls]) if n else torch.zeros((0, 3))
         data = {
             "roi_img": roi_img, "roi_cls": cls.to(dev), "roi_coord_2d": roi_coord_2d,
             "roi_cam": torch.from_numpy(self.cam)[None].repeat(n, 1, 1).to(dev),
-            "roi_center": torch.stack([cx, cy], 1).to(dev), "roi_wh": torch.stack([bw, bh], 1).to(dev),
-            "scale": scale.to(dev), "resize_ratio": (64.0 / scale).to(dev), "roi_extent": ext.to(dev),
-            "score": det[:, 4] * det[:, 5] if det.shape[1] > 5 else det[:, 4], "bbox_est": det[:, :4],
+            "roi_center": torch.from_numpy(centers).to(dev), "roi_wh": torch.from_numpy(whs).to(dev),
+            "scale": torch.from_numpy(scales).to(dev), "resize_ratio": torch.from_numpy((out_res / scales).astype(np.float32)).to(dev),
+            "roi_extent": ext.to(dev),
+            "score": torch.from_numpy(det[:, 4] * det[:, 5]), "bbox_est": torch.from_numpy(det[:, :4].copy()),
         }
         if depth_img is not None:
-            d = torch.as_tensor(np.asarray(depth_img, np.float32) * self.depth_scale).to(dev)[None, None]
-            data["roi_depth"] = crop(d, 64)[:, 0]
+            d = torch.from_numpy(np.ascontiguousarray(np.asarray(depth_img, np.float32) * np.float32(self.depth_scale))).to(dev)
+            data["roi_depth"] = crop_resize_float(d, M_in, in_res, nearest=True)      # [n,1,256,256] like the reference
         return data
 
     # ---- inference (predictor_gdrn.py:122-147) --------------------------------------------------
@@ -126,7 +133,16 @@ class GdrnPredictor:
         crop_xy = inputs["roi_center"] - inputs["scale"].view(n, 1) / 2
         K_crop = get_K_crop_resize(inputs["roi_cam"], crop_xy, (64.0 / inputs["scale"]).view(n, 1))
         xyz = torch.cat([out_dict["coor_x"], out_dict["coor_y"], out_dict["coor_z"]], dim=1)
+        # depth_sensor_crop = cv2.resize(roi_depth[i].squeeze(), (64, 64)) (predictor_gdrn.py:238): for the exact 4:1
+        # ratio INTER_LINEAR samples at 4*d + 1.5, i.e. the mean of the centre 2x2 of every 4x4 cell (weights 1/2, 1/2 per
+        # axis).  Computed as ((a+b)+(c+d))/4 = the correctly rounded mean; cv2's two-pass float path differs from it by
+        # at most 1 ulp on ~8 % of the pixels (double rounding), far below the sensor noise the refinement thresholds on
+        d = inputs["roi_depth"]
+        if d.dim() == 4:
+            d = d[:, 0]
+        if d.shape[-1] == 256:
+            d = ((d[:, 1::4, 1::4] + d[:, 1::4, 2::4]) + (d[:, 2::4, 1::4] + d[:, 2::4, 2::4])) * 0.25
         return depth_refine([m.vertices for m in self.ren_models], [m.faces for m in self.ren_models], out_dict["rot"],
-                            out_dict["trans"], K_crop, xyz, out_dict["mask"], inputs["roi_depth"],
+                            out_dict["trans"], K_crop, xyz, out_dict["mask"], d.contiguous(),
                             iters=self.cfg.TEST.DEPTH_REFINE_ITER, thresh=self.cfg.TEST.DEPTH_REFINE_THRESHOLD,
                             mesh_ids=inputs["roi_cls"])

@@ -186,6 +186,24 @@ size_t rast_scratch_bytes(int n, int H, int W);
 int gdrn_depth_refine_step(const float* xyz, const float* mask, const float* depth_sensor, const float* ren_depth,
                            const float* K_crop, float* trans, int n, int hw, float thresh, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * ROI crop + resize -- replaces crop_resize_by_warp_affine = cv2.warpAffine
+ * (core/utils/data_utils.py:115-133) as called once per ROI by GdrnPredictor.preprocessing
+ * (core/gdrn_modeling/demo/predictor_gdrn.py:417-438) and the test data loader
+ * (core/gdrn_modeling/datasets/data_loader.py:758-797).  OpenCV's warpAffine arithmetic is reproduced exactly
+ * (bit-exact for uint8 and nearest, bit-exact with the scalar float path for float bilinear; zero border).
+ *   M [n,6] f64 (device): forward (source -> crop) 2x3 matrices, row-major, as get_affine_transform returns them.
+ *   gdrn_crop_resize_u8 : image [H,W,C] u8 (BGR as cv2.imread, device), INTER_LINEAR, followed by
+ *                         normalize_image ((v - pixel_mean[c]) / pixel_std[c] in f64 -> f32; host arrays [C])
+ *                         -> out [n,C,out_h,out_w] f32 (the roi_img the model consumes).
+ *   gdrn_crop_resize_f32: src [H,W,C] f32 (device), INTER_LINEAR (nearest = 0; roi_coord_2d) or INTER_NEAREST
+ *                         (nearest = 1; roi_depth) -> out [n,C,out_h,out_w] f32.
+ * ------------------------------------------------------------------------------------------- */
+int gdrn_crop_resize_u8(const uint8_t* image, int H, int W, int C, const double* M, int n, int out_h, int out_w,
+                        const double* pixel_mean, const double* pixel_std, float* out, void* stream);
+int gdrn_crop_resize_f32(const float* src, int H, int W, int C, const double* M, int n, int out_h, int out_w,
+                         int nearest, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -237,3 +237,107 @@ void oracle_flow(const float* depth_src, const float* depth_tgt, const float* KT
     valid[index] = ok;
   }
 }
+
+/* =================================================================================================
+ * ROI crop + resize = cv2.warpAffine(img, trans, (ow, oh), flags=INTER_LINEAR | INTER_NEAREST), borderMode constant 0,
+ * as called by crop_resize_by_warp_affine (core/utils/data_utils.py:115-133; predictor_gdrn.py:417-438).
+ * The arithmetic lives in OpenCV 4.x (un-vendored dependency, opencv-python; imgwarp.cpp warpAffine / WarpAffineInvoker /
+ * remapBilinear): the forward matrix is inverted in double, destination pixels are mapped to source coordinates in
+ * 10-bit fixed point (per-column terms cvRound(M0*x*1024), per-row terms cvRound((M1*y+M2)*1024) + round_delta),
+ * bilinear: 5 fractional bits, uint8 data blended with 15-bit integer weights ((1-fx)(1-fy) ... scaled by 32768,
+ * saturated to short with the deficit added to the fx*fy weight -> (32767, 0, 0, 1) at integer positions),
+ * result (sum + 16384) >> 15; float data blended with the float weights; taps outside the image read 0.
+ * Pinned bit-exactly (uint8, nearest) / to 1e-6 (float bilinear) against cv2 itself in tests/test_oracle_pinning.py.
+ * ================================================================================================= */
+static int ora_cvround(double v) {
+  double r = nearbyint(v); /* round half to even (default rounding mode), like cvRound / lrint */
+  if (r > 2147483647.0) return 2147483647;
+  if (r < -2147483648.0) return (-2147483647 - 1);
+  return (int)r;
+}
+
+/* forward 2x3 matrix (src -> dst) to the inverse used for sampling: cv::warpAffine, "if( !(flags & WARP_INVERSE_MAP) )" */
+void oracle_invert_affine(const double* M, double* iM) {
+  double D = M[0] * M[4] - M[1] * M[3];
+  D = D != 0 ? 1. / D : 0;
+  double A11 = M[4] * D, A22 = M[0] * D;
+  iM[0] = A11; iM[1] = M[1] * (-D); iM[3] = M[3] * (-D); iM[4] = A22;
+  double b1 = -iM[0] * M[2] - iM[1] * M[5];
+  double b2 = -iM[3] * M[2] - iM[4] * M[5];
+  iM[2] = b1; iM[5] = b2;
+}
+
+static void ora_src_coord(const double* iM, int x, int y, int nearest, int* X, int* Y) {
+  const int AB_BITS = 10, AB_SCALE = 1 << 10, INTER_BITS = 5;
+  const int round_delta = nearest ? AB_SCALE / 2 : AB_SCALE / 32 / 2;
+  const int adelta = ora_cvround(iM[0] * x * AB_SCALE), bdelta = ora_cvround(iM[3] * x * AB_SCALE);
+  const int X0 = ora_cvround((iM[1] * y + iM[2]) * AB_SCALE) + round_delta;
+  const int Y0 = ora_cvround((iM[4] * y + iM[5]) * AB_SCALE) + round_delta;
+  if (nearest) { *X = (X0 + adelta) >> AB_BITS; *Y = (Y0 + bdelta) >> AB_BITS; }
+  else { *X = (X0 + adelta) >> (AB_BITS - INTER_BITS); *Y = (Y0 + bdelta) >> (AB_BITS - INTER_BITS); }
+}
+
+static void ora_bilinear_itab(int fx, int fy, int* w) {
+  /* float table entries are exact multiples of 1/1024; x 32768 is exact; saturate_cast<short> clips 32768 -> 32767 */
+  const float ax = fx * (1.f / 32), ay = fy * (1.f / 32);
+  const float t[4] = {(1.f - ay) * (1.f - ax), (1.f - ay) * ax, ay * (1.f - ax), ay * ax};
+  int isum = 0;
+  for (int k = 0; k < 4; ++k) {
+    int r = ora_cvround((double)(t[k] * 32768.f));
+    if (r > 32767) r = 32767;
+    w[k] = r; isum += r;
+  }
+  if (isum != 32768) w[3] -= (isum - 32768);   /* only element (1,1) is inspected for ksize = 2 */
+}
+
+/* uint8 image [H][W][C] -> dst [oh][ow][C] */
+void oracle_warp_affine_u8(const unsigned char* src, int H, int W, int C, const double* M, unsigned char* dst, int oh, int ow) {
+  double iM[6];
+  oracle_invert_affine(M, iM);
+  for (int y = 0; y < oh; ++y)
+    for (int x = 0; x < ow; ++x) {
+      int X, Y, w[4];
+      ora_src_coord(iM, x, y, 0, &X, &Y);
+      int sx = X >> 5, sy = Y >> 5;
+      if (sx > 32767) sx = 32767; if (sx < -32768) sx = -32768;   /* saturate_cast<short> */
+      if (sy > 32767) sy = 32767; if (sy < -32768) sy = -32768;
+      ora_bilinear_itab(X & 31, Y & 31, w);
+      for (int c = 0; c < C; ++c) {
+        int v = 0;
+        for (int k = 0; k < 4; ++k) {
+          const int xx = sx + (k & 1), yy = sy + (k >> 1);
+          const int s = (xx >= 0 && xx < W && yy >= 0 && yy < H) ? src[((long long)yy * W + xx) * C + c] : 0;
+          v += s * w[k];
+        }
+        v = (v + (1 << 14)) >> 15;
+        dst[((long long)y * ow + x) * C + c] = (unsigned char)(v < 0 ? 0 : (v > 255 ? 255 : v));
+      }
+    }
+}
+
+/* float image [H][W][C]; nearest = 1: INTER_NEAREST */
+void oracle_warp_affine_f32(const float* src, int H, int W, int C, const double* M, float* dst, int oh, int ow, int nearest) {
+  double iM[6];
+  oracle_invert_affine(M, iM);
+  for (int y = 0; y < oh; ++y)
+    for (int x = 0; x < ow; ++x) {
+      int X, Y;
+      ora_src_coord(iM, x, y, nearest, &X, &Y);
+      if (nearest) {
+        for (int c = 0; c < C; ++c)
+          dst[((long long)y * ow + x) * C + c] = (X >= 0 && X < W && Y >= 0 && Y < H) ? src[((long long)Y * W + X) * C + c] : 0.f;
+        continue;
+      }
+      int sx = X >> 5, sy = Y >> 5;
+      const float ax = (X & 31) * (1.f / 32), ay = (Y & 31) * (1.f / 32);
+      const float w[4] = {(1.f - ay) * (1.f - ax), (1.f - ay) * ax, ay * (1.f - ax), ay * ax};
+      for (int c = 0; c < C; ++c) {
+        float s[4];
+        for (int k = 0; k < 4; ++k) {
+          const int xx = sx + (k & 1), yy = sy + (k >> 1);
+          s[k] = (xx >= 0 && xx < W && yy >= 0 && yy < H) ? src[((long long)yy * W + xx) * C + c] : 0.f;
+        }
+        dst[((long long)y * ow + x) * C + c] = s[0] * w[0] + s[1] * w[1] + s[2] * w[2] + s[3] * w[3];
+      }
+    }
+}

@@ -236,3 +236,35 @@ def uncertainty_pnp(p2, p3, w, K, init_rt, max_iter=50):
             if radius < 1e-32:
                 break
     return x
+
+
+# ---- ROI crop + resize: restatement of cv2.warpAffine (ops_oracle.c), pinned against cv2 in tests/test_oracle_pinning.py
+def warp_affine_u8(img, M, out_size):
+    """img [H,W,C] uint8, M [2,3] float64 forward transform, out_size (w, h) -> [h,w,C] uint8 (INTER_LINEAR, border 0)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    if img.ndim == 2:
+        img = img[:, :, None]
+    M = np.ascontiguousarray(M, np.float64).reshape(6)
+    ow, oh = out_size
+    dst = np.zeros((oh, ow, img.shape[2]), np.uint8)
+    lib().oracle_warp_affine_u8(_p(img), img.shape[0], img.shape[1], img.shape[2], _p(M), _p(dst), oh, ow)
+    return dst
+
+
+def warp_affine_f32(src, M, out_size, nearest=False):
+    src = np.ascontiguousarray(src, np.float32)
+    if src.ndim == 2:
+        src = src[:, :, None]
+    M = np.ascontiguousarray(M, np.float64).reshape(6)
+    ow, oh = out_size
+    dst = np.zeros((oh, ow, src.shape[2]), np.float32)
+    lib().oracle_warp_affine_f32(_p(src), src.shape[0], src.shape[1], src.shape[2], _p(M), _p(dst), oh, ow, int(bool(nearest)))
+    return dst
+
+
+def crop_resize_roi(image_u8, M, out_res, pixel_mean=(0.0, 0.0, 0.0), pixel_std=(255.0, 255.0, 255.0)):
+    """crop_resize_by_warp_affine + transpose + normalize_image + astype(float32) (predictor_gdrn.py:417-422)."""
+    crop = warp_affine_u8(image_u8, M, (out_res, out_res)).transpose(2, 0, 1)
+    mean = np.array(pixel_mean, np.float64).reshape(-1, 1, 1)
+    std = np.array(pixel_std, np.float64).reshape(-1, 1, 1)
+    return ((crop - mean) / std).astype(np.float32)

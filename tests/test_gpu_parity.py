@@ -543,3 +543,81 @@ def test_depth_refine_vs_oracle(dev):
     # and the refinement actually moves towards the truth
     err0 = np.abs(poses[:4, 2, 3] - true_poses[:4, 2, 3]); err1 = np.abs(new_t[:4, 2].cpu().numpy() - true_poses[:4, 2, 3])
     assert (err1 < err0).all()
+
+
+# ----------------------------------------------------------------------------------------------- ROI crop + resize
+def _crop_Ms(rng, n, out, W=640, H=480):
+    Ms = []
+    for i in range(n):
+        cx, cy, scale = rng.uniform(-40, W + 40), rng.uniform(-40, H + 40), float(rng.uniform(24, 720))
+        s = out / scale
+        M = np.array([[s, 0, out * 0.5 - cx * s], [0, s, out * 0.5 - cy * s]], np.float64)
+        if i % 4 == 3:
+            a = rng.uniform(-0.6, 0.6)
+            M[:, :2] = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]]) * s
+        Ms.append(M)
+    return np.stack(Ms)
+
+
+def test_crop_resize_bit_exact(dev):
+    """ROI crops on the GPU == the oracle restatement of cv2.warpAffine (pinned bit-exactly against cv2 on the CPU):
+    uint8 bilinear + normalize_image, float bilinear (coordinate grid), float nearest (depth)."""
+    from gdrnpp_bop2022_b200 import native_ops as NO
+
+    rng = np.random.RandomState(5)
+    img = rng.randint(0, 256, (480, 640, 3)).astype(np.uint8)
+    coord = rng.rand(480, 640, 2).astype(np.float32)
+    depth = (rng.rand(480, 640) * 2).astype(np.float32)
+    M256, M64 = _crop_Ms(rng, 9, 256), _crop_Ms(rng, 9, 64)
+    got = NO.crop_resize_image(torch.from_numpy(img).to(dev), M256, 256).cpu().numpy()
+    for i in range(9):
+        assert np.array_equal(got[i], OO.crop_resize_roi(img, M256[i], 256)), i
+    got = NO.crop_resize_float(torch.from_numpy(coord).to(dev), M64, 64).cpu().numpy()
+    for i in range(9):
+        assert np.array_equal(got[i], OO.warp_affine_f32(coord, M64[i], (64, 64)).transpose(2, 0, 1)), i
+    got = NO.crop_resize_float(torch.from_numpy(depth).to(dev), M256, 256, nearest=True).cpu().numpy()
+    for i in range(9):
+        assert np.array_equal(got[i, 0], OO.warp_affine_f32(depth, M256[i], (256, 256), nearest=True)[:, :, 0]), i
+    # empty batch and the committed cv2 golden crop
+    assert NO.crop_resize_image(torch.from_numpy(img).to(dev), np.zeros((0, 2, 3)), 256).shape == (0, 3, 256, 256)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "crop_golden.npz"))
+    gi = torch.from_numpy(g["img"]).to(dev)
+    for i in range(g["M"].shape[0]):
+        out = int(g["out"][i])
+        crop = NO.crop_resize_image(gi, g["M"][i][None], out, pixel_std=(1.0, 1.0, 1.0))[0].cpu().numpy()
+        assert np.array_equal(crop.transpose(1, 2, 0).astype(np.uint8), g["crop_%d" % i]), i
+
+
+def test_predictor_preprocessing_matches_reference_recipe(dev):
+    """GdrnPredictor.preprocessing (GPU crops) vs the per-ROI host recipe of predictor_gdrn.py:396-438 restated with the
+    oracle warp: roi_img, roi_coord_2d, roi_depth, scale / resize_ratio / roi_wh bookkeeping."""
+    from gdrnpp_bop2022_b200.native_ops import get_affine_transform
+    from gdrnpp_bop2022_b200.predictor import GdrnPredictor
+    from gdrnpp_bop2022_b200.synthetic import make_state_dict
+
+    rng = np.random.RandomState(11)
+    H, W = 480, 640
+    image = rng.randint(0, 256, (H, W, 3)).astype(np.uint8)
+    depth = (rng.rand(H, W) * 1.5).astype(np.float32)
+    K = np.array([[1066.778, 0, 312.9869], [0, 1067.487, 241.3109], [0, 0, 1]], np.float32)
+    objs = {i + 1: "obj_%d" % (i + 1) for i in range(21)}
+    extents = {i + 1: np.array([0.1, 0.12, 0.08], np.float32) for i in range(21)}
+    pred = GdrnPredictor(K, objs, extents, state_dict=make_state_dict(), device=dev)
+    dets = np.array([[100, 80, 220, 260, 0.9, 0.8, 3], [400, 200, 460, 250, 0.7, 0.9, 10], [-20, 300, 90, 470, 0.5, 0.5, 0]],
+                    np.float32)
+    data = pred.preprocessing(dets, image, depth)
+    xx, yy = np.meshgrid(np.linspace(0, 1, W, endpoint=False, dtype=np.float32), np.linspace(0, 1, H, endpoint=False, dtype=np.float32))
+    coord_2d = np.stack([xx, yy], axis=2)
+    for i, d in enumerate(dets):
+        x1, y1, x2, y2 = d[:4]
+        c = np.array([0.5 * (x1 + x2), 0.5 * (y1 + y2)])
+        bw, bh = max(x2 - x1, 1), max(y2 - y1, 1)
+        scale = min(max(bh, bw) * 1.5, max(H, W)) * 1.0
+        M256, M64 = get_affine_transform(c, scale, 0, 256), get_affine_transform(c, scale, 0, 64)
+        assert np.array_equal(data["roi_img"][i].cpu().numpy(), OO.crop_resize_roi(image, M256, 256))
+        assert np.array_equal(data["roi_coord_2d"][i].cpu().numpy(), OO.warp_affine_f32(coord_2d, M64, (64, 64)).transpose(2, 0, 1))
+        assert np.array_equal(data["roi_depth"][i, 0].cpu().numpy(), OO.warp_affine_f32(depth, M256, (256, 256), nearest=True)[:, :, 0])
+        assert abs(float(data["scale"][i]) - scale) < 1e-4 and abs(float(data["resize_ratio"][i]) - 64 / scale) < 1e-7
+        assert np.allclose(data["roi_wh"][i].cpu().numpy(), [bw, bh])
+    out = pred.inference(data)
+    assert out["rot"].shape == (3, 3, 3) and torch.isfinite(out["trans"]).all()

@@ -149,3 +149,73 @@ def test_upnp_oracle_known_answer():
     init = rt + rs.rand(6) * 0.1
     sol = OO.uncertainty_pnp(p2, p3, w, K, init)
     assert np.abs(sol - rt).max() < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ROI crop + resize: the arithmetic lives in OpenCV (un-vendored dependency of the reference).  opencv-python is in
+# this image, so the oracle is pinned against cv2.warpAffine itself, exactly as crop_resize_by_warp_affine calls it
+# (core/utils/data_utils.py:115-133), and against a committed golden crop for boxes without cv2.
+# ---------------------------------------------------------------------------------------------------------------
+def _crop_cases(rng, n, W=640, H=480):
+    for i in range(n):
+        cx, cy = rng.uniform(-40, W + 40), rng.uniform(-40, H + 40)
+        scale = float(rng.uniform(24, 720))
+        out = 256 if i % 2 == 0 else 64
+        s = out / scale
+        M = np.array([[s, 0, out * 0.5 - cx * s], [0, s, out * 0.5 - cy * s]], np.float64)
+        if i % 5 == 0:   # a rotated crop (the data loader's augmentation path uses rot != 0)
+            a = rng.uniform(-0.6, 0.6)
+            M[:, :2] = np.array([[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]]) * s
+        yield M, out
+
+
+def test_warp_affine_oracle_bit_exact_vs_cv2():
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.RandomState(0)
+    img = rng.randint(0, 256, (480, 640, 3)).astype(np.uint8)
+    coord = rng.rand(480, 640, 2).astype(np.float32)
+    depth = (rng.rand(480, 640) * 2).astype(np.float32)
+    for M, out in _crop_cases(rng, 24):
+        ref = cv2.warpAffine(img, M, (out, out), flags=cv2.INTER_LINEAR)
+        assert np.array_equal(ref, OO.warp_affine_u8(img, M, (out, out)))
+        ref = cv2.warpAffine(coord, M, (out, out), flags=cv2.INTER_LINEAR)
+        got = OO.warp_affine_f32(coord, M, (out, out))
+        assert np.abs(ref - got).max() <= 1e-6            # measured 0 with the scalar float path of cv2 4.13
+        ref = cv2.warpAffine(depth, M, (out, out), flags=cv2.INTER_NEAREST)
+        assert np.array_equal(ref, OO.warp_affine_f32(depth, M, (out, out), nearest=True)[:, :, 0])
+
+
+def test_warp_affine_oracle_matches_golden_fixture():
+    """tests/golden/crop_golden.npz was written by tools/make_golden_crop.py from cv2.warpAffine outputs."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "crop_golden.npz"))
+    for i in range(g["M"].shape[0]):
+        out = int(g["out"][i])
+        assert np.array_equal(OO.warp_affine_u8(g["img"], g["M"][i], (out, out)), g["crop_%d" % i])
+
+
+def test_get_affine_transform_matches_reference_formula():
+    """Host mirror of get_affine_transform (data_utils.py:136-189) vs the cv2.getAffineTransform-based original."""
+    cv2 = pytest.importorskip("cv2")
+    from gdrnpp_bop2022_b200.native_ops import get_affine_transform
+
+    def ref(center, scale, rot, out):
+        center = np.array(center, np.float32)
+        scale = np.array([scale, scale], np.float32)
+        rot_rad = np.pi * rot / 180
+        sn, cs = np.sin(rot_rad), np.cos(rot_rad)
+        sp = [0, scale[0] * -0.5]
+        src_dir = [sp[0] * cs - sp[1] * sn, sp[0] * sn + sp[1] * cs]
+        dst_dir = np.array([0, out * -0.5], np.float32)
+        src, dst = np.zeros((3, 2), np.float32), np.zeros((3, 2), np.float32)
+        src[0, :], src[1, :] = center, center + src_dir
+        dst[0, :] = [out * 0.5, out * 0.5]
+        dst[1, :] = np.array([out * 0.5, out * 0.5], np.float32) + dst_dir
+        t3 = lambda a, b: b + np.array([-(a - b)[1], (a - b)[0]], np.float32)
+        src[2, :], dst[2, :] = t3(src[0], src[1]), t3(dst[0], dst[1])
+        return cv2.getAffineTransform(np.float32(src), np.float32(dst))
+
+    rng = np.random.RandomState(3)
+    for _ in range(100):
+        c, s = rng.uniform(0, 640, 2), float(rng.uniform(20, 700))
+        rot, out = float(rng.choice([0, 0, 15, -30])), int(rng.choice([64, 256]))
+        assert np.abs(get_affine_transform(c, s, rot, out) - ref(c, s, rot, out)).max() < 1e-9
