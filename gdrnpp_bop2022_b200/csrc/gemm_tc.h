@@ -81,6 +81,10 @@ struct GemmPlan {
 // block_n in {16, 64, 80, 128, 256}
 int gemm_tc_launch(const GemmPlan& plan, int block_n, cudaStream_t stream);
 
+// CTA-pair (cta_group::2) kernel for rank-2, single-tap, BLOCK_N = 256 plans (gemm_pair.cu); called by gemm_tc_launch,
+// which also re-tiles plan.tmap_b to 128-row boxes.  epi_warps = 8 or 16 (16: EPI_GELU only).
+int gemm_pair_launch(const GemmPlan& plan, int epi_warps, cudaStream_t stream);
+
 // Fused ConvNeXt MLP block (C = 128): x += gamma * (W2 . gelu(W1 . A + b1) + b2), hidden activation kept on chip.
 // A bf16 [M, C]; W1 bf16 [4C, C]; W2 bf16 [C, 4C]; x fp32 [M, C] updated in place.
 int mlp_fused_supported(int C, long long M);
