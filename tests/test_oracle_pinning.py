@@ -219,3 +219,41 @@ def test_get_affine_transform_matches_reference_formula():
         c, s = rng.uniform(0, 640, 2), float(rng.uniform(20, 700))
         rot, out = float(rng.choice([0, 0, 15, -30])), int(rng.choice([64, 256]))
         assert np.abs(get_affine_transform(c, s, rot, out) - ref(c, s, rot, out)).max() < 1e-9
+
+
+def test_baseline_config0_cpu_plumbing():
+    """BASELINE.json configs[0] / SURVEY.md 8d config 1: one 256x256 synthetic ROI through a random-init ConvNeXt-tiny
+    model, one FPS (pn = 8192 in U[-0.1, 0.1]^3, sn = 64, init_center), one RANSAC voting round (tn = 2048, vn = 9,
+    hn = 128, unit-norm directions, threshold 0.999) and the Patch-PnP forward, CPU only.  Pass = runs, finite,
+    self-consistent (rotation orthonormal, FPS indices distinct and equal to the reference build when present,
+    vote counts bounded by tn)."""
+    from gdrnpp_bop2022_b200.synthetic import make_batch, make_state_dict
+
+    sd = make_state_dict("convnext_tiny", seed=0)
+    batch = make_batch(B=1, seed=0)
+    with torch.no_grad():
+        out = O.gdrn_forward(sd, batch, arch="convnext_tiny", return_maps=True)
+    R = out["rot"][0].double()
+    assert torch.isfinite(out["trans"]).all() and (R @ R.T - torch.eye(3, dtype=torch.float64)).abs().max() < 1e-5
+    assert abs(float(torch.det(R)) - 1.0) < 1e-5 and out["region"].shape == (1, 65, 64, 64)
+
+    rng = np.random.RandomState(0)
+    pts = rng.uniform(-0.1, 0.1, (8192, 3)).astype(np.float32)
+    idx = OO.fps(pts, 64)
+    assert len(set(idx.tolist())) == 64 and idx.min() >= 0 and idx.max() < 8192
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libfps_ref.so")
+    if os.path.exists(ref_so):
+        L = ctypes.CDLL(ref_so)
+        ref = np.zeros(64, np.int32)
+        L.farthest_point_sampling_init_center(pts.ctypes.data_as(ctypes.c_void_p), ref.ctypes.data_as(ctypes.c_void_p), 8192, 64)
+        assert np.array_equal(ref, idx)
+
+    tn, vn, hn = 2048, 9, 128
+    coords = rng.uniform(0, 64, (tn, 2)).astype(np.float32)
+    direct = rng.normal(size=(tn, vn, 2)).astype(np.float32)
+    direct /= np.linalg.norm(direct, axis=2, keepdims=True)
+    idxs = rng.randint(0, tn, (hn, vn, 2)).astype(np.int32)
+    hypo = OO.generate_hypothesis(direct, coords, idxs)
+    inl, cnt = OO.voting(direct, coords, hypo, 0.999)
+    assert hypo.shape == (hn, vn, 2) and cnt.shape == (hn, vn) and cnt.min() >= 0 and cnt.max() <= tn
+    assert np.array_equal(inl.sum(axis=2).astype(np.int64), cnt.astype(np.int64))
