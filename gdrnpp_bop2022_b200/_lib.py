@@ -46,6 +46,7 @@ _SIGNATURES = {
     ),
     "gdrn_model_debug_read": (c_int64, [c_void_p, c_char_p, c_int, c_void_p, c_void_p, c_void_p]),
     "gdrn_gemm_bf16": (c_int, [c_void_p] * 6 + [c_int] * 6 + [c_void_p]),
+    "gdrn_gemm_x3": (c_int, [c_void_p] * 6 + [c_int] * 5 + [c_void_p]),
     "farthest_point_sampling": (None, [c_void_p, c_void_p, c_int, c_int]),
     "farthest_point_sampling_init_center": (None, [c_void_p, c_void_p, c_int, c_int]),
     "gdrn_fps_set_seed": (None, [c_uint]),
@@ -67,6 +68,8 @@ _SIGNATURES = {
     ),
     "rast_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
     "gdrn_depth_refine_step": (c_int, [c_void_p] * 6 + [c_int, c_int, c_float, c_void_p]),
+    "gdrn_pnp_ransac_maps": (c_int, [c_void_p] * 9 + [c_int] * 3 + [c_float, c_float, c_uint] + [c_void_p] * 4),
+    "gdrn_pnp_ransac_points": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_float, c_uint] + [c_void_p] * 4),
     "gdrn_crop_resize_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p]),
     "gdrn_crop_resize_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
@@ -110,6 +113,29 @@ def ptr(t):
 
 
 def current_stream():
+    """Current stream of the CURRENT device (wrappers make their tensors' device current first, see on_device)."""
     import torch
 
     return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def on_device(argidx=0):
+    """Decorator: run the wrapped call with the CUDA device of positional argument ``argidx`` made current.  The C ABI
+    launches on the current device and takes the current stream, so a tensor on cuda:1 must not be processed while
+    cuda:0 is current (the kernels' shared-memory opt-in and the SM-count cache are per device too)."""
+    import functools
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapped(*a, **k):
+            import torch
+
+            t = a[argidx] if len(a) > argidx else None
+            if torch.is_tensor(t) and t.is_cuda:
+                with torch.cuda.device(t.device):
+                    return fn(*a, **k)
+            return fn(*a, **k)
+
+        return wrapped
+
+    return deco

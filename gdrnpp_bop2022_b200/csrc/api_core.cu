@@ -76,3 +76,43 @@ extern "C" int gdrn_gemm_bf16(const void* A, const void* W, const float* bias, c
           (long long)M, N, K, epi, block_n, h[6], h[7], h[0], h[1], h[2], h[3], h[4], h[8], h[9], h[10]);
   return GDRN_OK;
 }
+
+extern "C" int gdrn_gemm_x3(const void* A, const void* W, const float* bias, const float* gamma, const float* resid,
+                            void* out, int M, int N, int K, int epi, int block_n, void* stream) {
+  GDRN_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_x3: empty problem");
+  GDRN_REQUIRE(K % 64 == 0, "gemm_x3: K must be a multiple of 64 (the lo half starts at a k-chunk boundary)");
+  GDRN_REQUIRE(epi >= 0 && epi <= 2, "gemm_x3: epi must be 0 (store fp32), 1 (gelu -> split bf16) or 2 (resid)");
+  GDRN_REQUIRE(block_n == 64 || block_n == 128 || block_n == 256, "gemm_x3: block_n must be 64, 128 or 256");
+  GDRN_REQUIRE(N % 64 == 0, "gemm_x3: N must be a multiple of 64");
+  GemmPlan p;
+  memset(&p, 0, sizeof(p));
+  uint64_t dims_a[2] = {(uint64_t)2 * K, (uint64_t)M};
+  uint64_t str_a[1] = {(uint64_t)2 * K * 2};
+  uint32_t box_a[2] = {64, 128};
+  int rc = make_tmap_bf16(&p.tmap_a, A, 2, dims_a, str_a, box_a);
+  if (rc) return rc;
+  uint64_t dims_b[2] = {(uint64_t)2 * K, (uint64_t)N};
+  uint64_t str_b[1] = {(uint64_t)2 * K * 2};
+  uint32_t box_b[2] = {64, (uint32_t)block_n};
+  rc = make_tmap_bf16(&p.tmap_b, W, 2, dims_b, str_b, box_b);
+  if (rc) return rc;
+  p.b_ptr = W; p.b_rows = N; p.b_ktot = 2LL * K;
+  p.a_rank = 2;
+  p.num_taps = 1;
+  p.k_chunks = K / 64;
+  p.taps[0] = {0, 0, 0, 0, 0};
+  p.m_tiles = (M + 127) / 128;
+  p.n_tiles = (N + block_n - 1) / block_n;
+  p.M = M;
+  p.N = N;
+  p.epi = epi;
+  p.out_f32 = epi == 1 ? 0 : 1;
+  p.gelu_mode = 3;
+  p.split = 1; p.x3_a_lo = K; p.x3_b_lo = K;
+  p.out = out;
+  p.ldo = epi == 1 ? 2LL * N : N;
+  p.bias = bias;
+  p.gamma = gamma;
+  p.resid = resid;
+  return gemm_tc_launch(p, block_n, (cudaStream_t)stream);
+}

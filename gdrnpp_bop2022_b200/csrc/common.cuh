@@ -30,16 +30,33 @@
 void gdrn_set_last_error(const char* file, int line, const char* msg);
 void gdrn_count_launch(int n);  // bumps the counter behind gdrn_launch_count()
 
-static inline int gdrn_num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
+// The dynamic-shared-memory opt-in and the SM count are PER DEVICE: cache them per device ordinal so that a process
+// that drives several GPUs (GdrnPredictor(device="cuda:1"), one engine per device) configures each of them.
+constexpr int GDRN_MAX_DEVICES = 64;
+static inline int gdrn_cur_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d < 0 ? 0 : (d >= GDRN_MAX_DEVICES ? GDRN_MAX_DEVICES - 1 : d);
 }
+static inline int gdrn_num_sms() {
+  static int n[GDRN_MAX_DEVICES] = {};
+  const int dev = gdrn_cur_device();
+  if (n[dev] == 0) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
+  }
+  return n[dev];
+}
+// once per (kernel instantiation, device): cudaFuncSetAttribute(MaxDynamicSharedMemorySize)
+#define GDRN_OPT_IN_SMEM(kfn, bytes)                                                                             \
+  do {                                                                                                           \
+    static bool gdrn_done_[GDRN_MAX_DEVICES] = {};                                                               \
+    const int gdrn_dev_ = gdrn_cur_device();                                                                     \
+    if (!gdrn_done_[gdrn_dev_]) {                                                                                \
+      GDRN_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));     \
+      gdrn_done_[gdrn_dev_] = true;                                                                              \
+    }                                                                                                            \
+  } while (0)
 
 #ifdef __CUDACC__
 namespace ptx {
@@ -225,6 +242,20 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* tmap,
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(tmap), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const void* tmap, uint32_t bar_cluster, int c0, int c1, int c2,
+                                                 int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(dst), "l"(tmap), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(uint32_t dst, const void* tmap, uint32_t bar_cluster, int c0, int c1, int c2,
+                                                 int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
+      "%7}], [%2];" ::"r"(dst), "l"(tmap), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {

@@ -835,11 +835,7 @@ static int launch_dwconv_cluster(const float* x, const float* w49c, const float*
   constexpr int NTHREADS = (CPC / 2) * TH / R;
   const size_t smem = (size_t)(IH * IW * CPC + 49 * CPC + 2 * 8 * (CPC / 64) * NPIX) * sizeof(float) + 32;
   auto kfn = dwconv_ln_cluster_kernel<TW, TH, CPC, R, MINB>;
-  static bool configured = false;
-  if (!configured) {
-    GDRN_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
+  GDRN_OPT_IN_SMEM(kfn, smem);
   CUtensorMap tmap;
   {
     const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};

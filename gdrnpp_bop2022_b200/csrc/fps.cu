@@ -148,12 +148,8 @@ fps_kernel(const float* __restrict__ pts_all, int* __restrict__ idx_all, int pn,
 int fps_launch(const float* pts, int* idxs, int pn, int sn, int batch, const int* start_idx, cudaStream_t st) {
   GDRN_REQUIRE(pn > 0 && sn > 0 && batch > 0, "fps: pn, sn, batch must be positive");
   GDRN_REQUIRE(pn <= FPS_SMEM_D, "fps: pn > 56000 points per cloud is not supported by the single-CTA kernel");
-  static bool configured = false;
-  if (!configured) {
-    GDRN_CHECK_CUDA(cudaFuncSetAttribute(fps_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224000));
-    GDRN_CHECK_CUDA(cudaFuncSetAttribute(fps_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224000));
-    configured = true;
-  }
+  GDRN_OPT_IN_SMEM(fps_kernel<true>, 224000);
+  GDRN_OPT_IN_SMEM(fps_kernel<false>, 224000);
   if (pn <= FPS_SMEM_ALL) {
     fps_kernel<true><<<batch, FPS_THREADS, (size_t)pn * 16, st>>>(pts, idxs, pn, sn, start_idx);
   } else {

@@ -744,6 +744,73 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmPlan& p, int m_tile,
   if (trc && lane == 0) { p.trace[8] += tq_tmem; p.trace[9] += tq_comp; p.trace[10] += tq_flush; }
 }
 
+// Split-bf16 (x3) outputs with TMA stores (EPI_STORE / EPI_GELU, bf16 [M, 2N] = [hi N | lo N] rows).
+// A thread owns one accumulator row.  Per 32-column chunk (one tcgen05.ld) it computes hi = bf16(v) and
+// lo = bf16(v - hi) in registers (the long part: exact-erf GELU), THEN waits for the previous chunk's TMA stores to
+// have read the staging buffer (long finished by then), writes hi / lo into two dense 32-row x 64-byte tiles and one
+// lane issues two stores: hi at column `col`, lo at column N + col.  Rows beyond M are clipped by the tensor map
+// (SWIZZLE_NONE, box {32, 32}: gemm_tc_launch builds it with make_tmap_store_plain).
+template <int BLOCK_N, int EPI, int NEW>
+__device__ __forceinline__ void epilogue_tile_tma_split(const GemmPlan& p, int m_tile, int n_tile, uint32_t tmem_acc, int ew,
+                                                        int lane, uint8_t* stg) {
+  static_assert(EPI == EPI_STORE || EPI == EPI_GELU, "split TMA epilogue: STORE / GELU only");
+  constexpr int CPW = BLOCK_N / (NEW / 4);
+  constexpr int CH = 32;
+  static_assert(CPW % CH == 0, "a warp owns whole 32-column chunks");
+  const int q = ew & 3, half = ew >> 2;
+  const int n0 = n_tile * BLOCK_N + half * CPW;
+  const uint32_t tmem_row = tmem_acc + ((uint32_t)(q * 32) << 16) + half * CPW;
+  const uint32_t stg_u32 = ptx::smem_u32(stg);
+  uint4* my_hi = reinterpret_cast<uint4*>(stg + lane * 64);
+  uint4* my_lo = reinterpret_cast<uint4*>(stg + 2048 + lane * 64);
+  const int row0 = m_tile * BLOCK_M + q * 32;
+#pragma unroll 1
+  for (int c = 0; c < CPW; c += CH) {
+    const int col = n0 + c;
+    if (col >= p.N) break;  // warp-uniform
+    float v[CH];
+    tmem_load_chunk<CH>(tmem_row + c, v);
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < CH; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col + j));
+        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+      }
+    }
+    if constexpr (EPI == EPI_GELU) {
+      if (p.gelu_mode == 3) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] = gelu_erf(v[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] = gelu_fast(v[j]);
+      }
+    }
+    uint32_t hi[CH / 2], lo[CH / 2];
+#pragma unroll
+    for (int j = 0; j < CH / 2; ++j) {
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      const float2 hf = __bfloat1622float2(h2);
+      hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
+      lo[j] = pack_bf16(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+    }
+    if (lane == 0) ptx::bulk_wait_read0();   // the previous chunk's stores have read the staging tiles
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      my_hi[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+      my_lo[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+    }
+    ptx::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      ptx::tma_store_2d(&p.tmap_out, stg_u32, col, row0);
+      ptx::tma_store_2d(&p.tmap_out, stg_u32 + 2048, p.N + col, row0);
+      ptx::bulk_commit();
+    }
+  }
+}
+
 template <int BLOCK_N, int EPI>
 __device__ __forceinline__ void epilogue_tile_staged(const GemmPlan& p, int m_tile, int n_tile, uint32_t tmem_acc,
                                                      int ew, int lane, uint8_t* stg) {

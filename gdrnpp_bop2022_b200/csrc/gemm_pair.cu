@@ -151,14 +151,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P2Cfg<NEW>::THREADS,
 
 template <int EPI, int NEW>
 int launch_pair(const GemmPlan& plan, cudaStream_t stream) {
-  static bool configured = false;
   auto kfn = gemm_pair_kernel<EPI, NEW>;
   constexpr int P2_SMEM_BYTES = P2Cfg<NEW>::SMEM_BYTES;
   constexpr int NUM_THREADS = P2Cfg<NEW>::THREADS;   // shadows the file-scope constant
-  if (!configured) {
-    GDRN_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, P2_SMEM_BYTES));
-    configured = true;
-  }
+  GDRN_OPT_IN_SMEM(kfn, P2_SMEM_BYTES);
   const int m_pairs = (plan.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   const int total = m_pairs * plan.n_tiles;
   if (total <= 0) return GDRN_OK;

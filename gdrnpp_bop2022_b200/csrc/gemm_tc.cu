@@ -236,12 +236,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 template <int BLOCK_N, int EPI>
 int launch_inst(const GemmPlan& plan, cudaStream_t stream) {
   using C = Cfg<BLOCK_N>;
-  static bool configured = false;
   auto kfn = gemm_tc_kernel<BLOCK_N, EPI>;
-  if (!configured) {
-    GDRN_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    configured = true;
-  }
+  GDRN_OPT_IN_SMEM(kfn, C::SMEM_BYTES);
   int total = plan.m_tiles * plan.n_tiles;
   if (total <= 0) return GDRN_OK;
   int grid = total < gdrn_num_sms() ? total : gdrn_num_sms();
@@ -263,6 +259,49 @@ int gemm_tc_launch(const GemmPlan& plan_in, int block_n, cudaStream_t stream) {
   GDRN_REQUIRE(plan.a_rank == 2 || plan.a_rank == 4 || plan.a_rank == 5, "gemm: bad a_rank");
   plan.use_tma_store = 0;
   plan.resid_reduce = 0;
+  if (plan.split && !plan.x3_expanded) {
+    // split-bf16 (x3): taps[] lists the hi operands; either the CTA-pair kernel that shares {A hi, A lo, W hi, W lo}
+    // between the three products of a stage, or the general kernel with a 3x longer tap list.
+    GDRN_REQUIRE(plan.num_taps >= 1 && 3 * plan.num_taps <= GEMM_MAX_TAPS, "gemm: bad num_taps (split)");
+    static int x3_pair = -1;  // GDRN_X3_PAIR=0 forces the general kernel (A/B experiments, parity cross-checks)
+    if (x3_pair < 0) { const char* e = getenv("GDRN_X3_PAIR"); x3_pair = e ? atoi(e) : 1; }
+    if (x3_pair && gemm_pair_x3_supported(plan, block_n)) {
+      {
+        const uint64_t dims[2] = {(uint64_t)plan.b_ktot, (uint64_t)plan.b_rows};
+        const uint64_t str[1] = {(uint64_t)plan.b_ktot * 2};
+        const uint32_t box[2] = {64, (uint32_t)block_n / 2};
+        int rc = make_tmap_bf16(&plan.tmap_b, plan.b_ptr, 2, dims, str, box);
+        if (rc != GDRN_OK) return rc;
+      }
+      if (plan.epi != EPI_GNSTATS) {
+        const bool f32 = plan.epi != EPI_GELU;
+        GDRN_REQUIRE(((uintptr_t)plan.out % 16 == 0) && ((plan.ldo * (f32 ? 4 : 2)) % 16 == 0) && plan.N % 64 == 0,
+                     "gemm (split): output not TMA-store compatible");
+        const uint64_t dims[2] = {(uint64_t)plan.ldo, (uint64_t)plan.M};
+        const uint64_t str[1] = {(uint64_t)plan.ldo * (f32 ? 4 : 2)};
+        const uint32_t box[2] = {32u, 32u};
+        // fp32: 32 x 128-byte swizzled staging rows; split bf16: two dense 32 x 64-byte tiles (hi, lo) per chunk
+        int rc = f32 ? make_tmap_store(&plan.tmap_out, plan.out, 1, dims, str, box)
+                     : make_tmap_store_plain(&plan.tmap_out, plan.out, 0, dims, str, box);
+        if (rc != GDRN_OK) return rc;
+        plan.use_tma_store = 1;
+        static int red = -1;
+        if (red < 0) { const char* e = getenv("GDRN_RESID_REDUCE"); red = e ? atoi(e) : 1; }
+        plan.resid_reduce = (red && plan.epi == EPI_RESID && plan.resid == plan.out) ? 1 : 0;
+      }
+      return gemm_pair_x3_launch(plan, block_n, stream);
+    }
+    // general kernel: every tap becomes (A lo, W hi) + (A hi, W lo) + (A hi, W hi), small terms first
+    const int n = plan.num_taps;
+    for (int t = n - 1; t >= 0; --t) {
+      const GemmTap h = plan.taps[t];
+      GemmTap al = h; al.c0 += plan.x3_a_lo;
+      GemmTap bl = h; bl.b_off += plan.x3_b_lo;
+      plan.taps[t] = al; plan.taps[n + t] = bl; plan.taps[2 * n + t] = h;
+    }
+    plan.num_taps = 3 * n;
+    plan.x3_expanded = 1;
+  }
   {
     static int tma_epi = -1;  // GDRN_TMA_STORE=0 falls back to the gather-store epilogue (A/B experiments)
     if (tma_epi < 0) { const char* e = getenv("GDRN_TMA_STORE"); tma_epi = e ? atoi(e) : 1; }
@@ -386,6 +425,27 @@ int make_tmap_store(CUtensorMap* out, const void* base, int is_f32, const uint64
   if (r != CUDA_SUCCESS) {
     char msg[160];
     snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled(store) failed: CUresult %d (dims %llu,%llu)", (int)r,
+             (unsigned long long)dims[0], (unsigned long long)dims[1]);
+    gdrn_set_last_error(__FILE__, __LINE__, msg);
+    return GDRN_ERR_CUDA;
+  }
+  return GDRN_OK;
+}
+
+int make_tmap_store_plain(CUtensorMap* out, const void* base, int is_f32, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box) {
+  PFN_encodeTiled fn = get_encode_fn();
+  GDRN_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  cuuint64_t gdim[2] = {dims[0], dims[1]};
+  cuuint64_t gstr[1] = {strides_bytes[0]};
+  cuuint32_t bx[2] = {box[0], box[1]};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(out, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[160];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled(store, plain) failed: CUresult %d (dims %llu,%llu)", (int)r,
              (unsigned long long)dims[0], (unsigned long long)dims[1]);
     gdrn_set_last_error(__FILE__, __LINE__, msg);
     return GDRN_ERR_CUDA;

@@ -51,7 +51,11 @@ struct GemmPlan {
   int epi;
   int out_f32;          // EPI_STORE / EPI_GNSTATS: 1 -> fp32 output, 0 -> bf16
   int gelu_mode;        // EPI_GELU: 0 = fp32 ex2/rcp form (1.2e-5 of erf), 1 = packed half2 tanh.approx, 2 = fp32 tanh.approx, 3 = erff
-  int split;            // bf16 outputs are written as [hi | lo] pairs (row width 2N, lo = bf16(v - hi)): split-bf16 (x3) mode
+  int split;            // split-bf16 (x3) mode: operands are [hi | lo] pairs (see x3_*), bf16 outputs are written as
+                        // [hi | lo] pairs (row width 2N, lo = bf16(v - hi))
+  int x3_a_lo;          // split: offset of the lo half in A's coordinate 0 (channels / K); taps[] list the hi operands only
+  int x3_b_lo;          // split: offset of the lo half inside a row of W (elements)
+  int x3_expanded;      // set by gemm_tc_launch once taps[] has been expanded to the three products (general kernel)
   void* out;            // [rows, ldo]
   CUtensorMap tmap_out; // rank-2 outputs: store map (filled by gemm_tc_launch when use_tma_store)
   int use_tma_store;    // set by gemm_tc_launch
@@ -85,6 +89,13 @@ int gemm_tc_launch(const GemmPlan& plan, int block_n, cudaStream_t stream);
 // which also re-tiles plan.tmap_b to 128-row boxes.  epi_warps = 8 or 16 (16: EPI_GELU only).
 int gemm_pair_launch(const GemmPlan& plan, int epi_warps, cudaStream_t stream);
 
+// CTA-pair split-bf16 kernel (gemm_pair_x3.cu): every shared-memory stage holds {A hi, A lo, W hi, W lo} of one
+// (tap, k-chunk) and feeds the three products A_lo*W_hi + A_hi*W_lo + A_hi*W_hi -- 4 operand tiles per 3 MMA groups
+// instead of 6.  rank 2/4/5 A, any tap list; block_n in {128, 256}; epilogues GELU (split out), RESID / STORE (fp32,
+// TMA store / reduce-add), GNSTATS (fp32).  Called by gemm_tc_launch.
+int gemm_pair_x3_supported(const GemmPlan& plan, int block_n);
+int gemm_pair_x3_launch(const GemmPlan& plan, int block_n, cudaStream_t stream);
+
 // Fused ConvNeXt MLP block (C = 128): x += gamma * (W2 . gelu(W1 . A + b1) + b2), hidden activation kept on chip.
 // A bf16 [M, C]; W1 bf16 [4C, C]; W2 bf16 [C, 4C]; x fp32 [M, C] updated in place.
 int mlp_fused_supported(int C, long long M);
@@ -97,5 +108,8 @@ int make_tmap_f32_plain(CUtensorMap* out, const void* base, int rank, const uint
                         const uint64_t* strides_bytes, const uint32_t* box);
 int make_tmap_store(CUtensorMap* out, const void* base, int is_f32, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box);
+// same, SWIZZLE_NONE (dense [rows][box0] shared-memory tile)
+int make_tmap_store_plain(CUtensorMap* out, const void* base, int is_f32, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box);
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box);

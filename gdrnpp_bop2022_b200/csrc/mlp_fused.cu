@@ -293,11 +293,7 @@ int mlp_fused_launch(const void* A, const void* W1, const float* b1, const void*
   constexpr int C_ = 128;
   constexpr int SMEM = (C_ / 64) * A_STAGE_BYTES + 2 * 2 * A_STAGE_BYTES + MF_SLOTS * MF_SLOT_BYTES + NUM_EPI_WARPS * EPI_STAGE_BYTES + 256 + 1024;
   auto kfn = mlp_fused_kernel<C_>;
-  static bool configured = false;
-  if (!configured) {
-    GDRN_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    configured = true;
-  }
+  GDRN_OPT_IN_SMEM(kfn, SMEM);
   const int grid = fp.m_tiles < gdrn_num_sms() ? fp.m_tiles : gdrn_num_sms();
   static int trace_on = -1;
   if (trace_on < 0) trace_on = getenv("GDRN_MLP_TRACE") ? 1 : 0;

@@ -395,17 +395,12 @@ int plan_a5d_s2(GemmPlan& p, const void* act, int B, int H, int W, int C, int S 
   return make_tmap_bf16(&p.tmap_a, act, 5, dims, str, box);
 }
 
-// split-bf16: every tap becomes the three products (A lo, W hi) + (A hi, W lo) + (A hi, W hi), small terms first
-void expand_x3(GemmPlan& p, int a_lo_c0, int b_lo_off) {
-  const int n = p.num_taps;
-  for (int t = n - 1; t >= 0; --t) {
-    const GemmTap h = p.taps[t];
-    GemmTap al = h; al.c0 += a_lo_c0;
-    GemmTap bl = h; bl.b_off += b_lo_off;
-    p.taps[t] = al; p.taps[n + t] = bl; p.taps[2 * n + t] = h;
-  }
-  p.num_taps = 3 * n;
+// split-bf16: taps[] keeps listing the hi operands; gemm_tc_launch picks the CTA-pair kernel that shares the four operand
+// tiles of a stage between the three products, or expands the tap list for the general kernel
+void set_x3(GemmPlan& p, int a_lo_c0, int b_lo_off) {
   p.split = 1;
+  p.x3_a_lo = a_lo_c0;
+  p.x3_b_lo = b_lo_off;
 }
 
 #define RC(expr) do { int _rc = (expr); if (_rc != GDRN_OK) return _rc; } while (0)
@@ -430,7 +425,7 @@ void prof_end(GdrnModel* m, cudaStream_t st) {
 
 // ================================================================================================
 extern "C" int gdrn_model_create(GdrnModel** out, const char* arch, int num_classes, int max_batch) {
-  int precision = 0;
+  int precision = 1;  // split-bf16 (fp32 parity) unless GDRN_PRECISION=0 asks for the bf16 throughput mode
   if (const char* e = getenv("GDRN_PRECISION")) precision = atoi(e);
   return gdrn_model_create_ex(out, arch, num_classes, max_batch, precision);
 }
@@ -542,7 +537,7 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
     RC(plan_a2d(p, w.A, M0, 64, S));
     if (C0 == 128) {
       RC(plan_b(p, m->stem_w, C0, 64, 128, C0, S));
-      if (PR) expand_x3(p, 64, 64);
+      if (PR) set_x3(p, 64, 64);
       p.epi = EPI_BIAS_LN; p.out = w.X; p.ldo = C0; p.bias = m->stem_b;
       p.ln_w = m->stem_ln_w; p.ln_b = m->stem_ln_b; p.ln_eps = 1e-6f;
       RCP(0, gemm_tc_launch(p, 128, st));
@@ -564,7 +559,7 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
       RC(plan_a2d(p, w.A, M, 4 * Ci, S));
       const int bn = 256;
       RC(plan_b(p, m->down[s].w, C, 4 * Ci, bn, C, S));
-      if (PR) expand_x3(p, 4 * Ci, 4 * Ci);
+      if (PR) set_x3(p, 4 * Ci, 4 * Ci);
       p.epi = EPI_STORE; p.out_f32 = 1; p.out = w.X; p.ldo = C; p.bias = m->down[s].b;
       RCP(0, gemm_tc_launch(p, bn, st));
     }
@@ -580,14 +575,14 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
       reset();
       RC(plan_a2d(p, w.A, M, C, S));
       RC(plan_b(p, bw.fc1_w, 4 * C, C, 256, 4 * C, S));
-      if (PR) expand_x3(p, C, C);
+      if (PR) set_x3(p, C, C);
       p.epi = EPI_GELU; p.gelu_mode = gelu_mode; p.out = w.Hb; p.ldo = S * 4 * C; p.bias = bw.fc1_b;
       RCP(0, gemm_tc_launch(p, 256, st));
       reset();
       RC(plan_a2d(p, w.Hb, M, 4 * C, S));
       const int bn2 = C >= 256 ? 256 : 128;
       RC(plan_b(p, bw.fc2_w, C, 4 * C, bn2, C, S));
-      if (PR) expand_x3(p, 4 * C, 4 * C);
+      if (PR) set_x3(p, 4 * C, 4 * C);
       p.epi = EPI_RESID; p.out_f32 = 1; p.out = w.X; p.resid = w.X; p.ldo = C; p.bias = bw.fc2_b; p.gamma = bw.gamma;
       RCP(0, gemm_tc_launch(p, bn2, st));
     }
@@ -616,7 +611,7 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
       // only B/2 row tiles (8x8 inputs): narrow N tiles so that the launch still covers the SMs
       const int dbn = p.m_tiles >= 96 ? 256 : 64;
       RC(plan_b(p, m->deconv_w[py * 2 + px], 256, (long long)nt * C3, dbn, 256, S));
-      if (PR) expand_x3(p, C3, nt * C3);
+      if (PR) set_x3(p, C3, nt * C3);
       p.epi = EPI_GNSTATS; p.out_f32 = PR; p.out = w.R; p.ldo = 256;
       p.OH = 16; p.OW = 16; p.osy = 2; p.osx = 2; p.ooy = py; p.oox = px;
       p.gn_stats = stat_slot(0); p.gn_groups = 32; p.gn_cpg = 8;
@@ -634,7 +629,7 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
       for (int t = 0; t < 9; ++t) p.taps[t] = {0, t % 3 - 1, t / 3 - 1, 0, t * 256};
       p.num_taps = 9;
       RC(plan_b(p, m->hconv_w[li], 256, 9 * 256, 256, 256, S));
-      if (PR) expand_x3(p, 256, 9 * 256);
+      if (PR) set_x3(p, 256, 9 * 256);
       p.epi = EPI_GNSTATS; p.out_f32 = PR; p.out = w.R; p.ldo = 256;
       p.OH = hres; p.OW = hres; p.osy = 1; p.osx = 1; p.ooy = 0; p.oox = 0;
       p.gn_stats = stat_slot(li + 1); p.gn_groups = 32; p.gn_cpg = 8;
@@ -657,7 +652,7 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
   reset();
   RC(plan_a2d(p, cur, M0, 256, S));
   RC(plan_b(p, m->out_w, (long long)m->num_classes * 80, 256, 80, 80, S));
-  if (PR) expand_x3(p, 256, 256);
+  if (PR) set_x3(p, 256, 256);
   p.n_tiles = 1;
   p.b_rows_per_class = 80;
   p.epi = EPI_OUTCONV;
@@ -693,7 +688,7 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
       }
       p.num_taps = 9;
       RC(plan_b(p, m->pconv_w[i], 128, 9 * 128, 128, 128, S));
-      if (PR) expand_x3(p, 128, 9 * 128);
+      if (PR) set_x3(p, 128, 9 * 128);
       p.epi = EPI_GNSTATS; p.out_f32 = PR; p.out = w.pR; p.ldo = 128;
       p.OH = ores; p.OW = ores; p.osy = 1; p.osx = 1;
       p.gn_stats = stat_slot(7 + i); p.gn_groups = 32; p.gn_cpg = 4;

@@ -243,11 +243,7 @@ extern "C" int gdrn_depth_refine_step(const float* xyz, const float* mask, const
   int npix = hw * hw, npow2 = 1;
   while (npow2 < npix) npow2 <<= 1;
   size_t smem = (size_t)(npix + npow2) * 4;
-  static bool configured = false;
-  if (!configured) {
-    GDRN_CHECK_CUDA(cudaFuncSetAttribute(depth_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    configured = true;
-  }
+  GDRN_OPT_IN_SMEM(depth_refine_kernel, 160 * 1024);
   depth_refine_kernel<<<n, DR_THREADS, smem, (cudaStream_t)stream>>>(xyz, mask, depth_sensor, ren_depth, K_crop, trans,
                                                                     hw, thresh);
   GDRN_CHECK_CUDA(cudaGetLastError());

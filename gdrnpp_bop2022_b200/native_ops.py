@@ -39,6 +39,7 @@ def farthest_point_sampling(pts, sn, init_center=False):
     return pts[idxs]
 
 
+@_lib.on_device(0)
 def farthest_point_sampling_idx(pts, sn, start_idx=None):
     """Batched device FPS: pts [b,pn,3] f32 CUDA -> idx [b,sn] i32. start_idx None = init_center."""
     _check_cuda_contig(pts, "pts")
@@ -64,6 +65,7 @@ class _RansacVotingModule:
         assert two == 2 and tuple(coords.shape) == (tn, 2)
         return tn, vn
 
+    @_lib.on_device(1)
     def generate_hypothesis(self, direct, coords, idxs):
         tn, vn = self._dims(direct, coords)
         _check_cuda_contig(idxs, "idxs")
@@ -74,6 +76,7 @@ class _RansacVotingModule:
                                                      tn, vn, hn, _lib.current_stream()), "rv_generate_hypothesis")
         return hypo
 
+    @_lib.on_device(1)
     def generate_hypothesis_vanishing_point(self, direct, coords, idxs):
         tn, vn = self._dims(direct, coords)
         _check_cuda_contig(idxs, "idxs")
@@ -85,6 +88,7 @@ class _RansacVotingModule:
             "rv_generate_hypothesis_vanishing_point")
         return hypo
 
+    @_lib.on_device(1)
     def voting_for_hypothesis(self, direct, coords, hypo_pts, inliers, inlier_thresh):
         tn, vn = self._dims(direct, coords)
         _check_cuda_contig(hypo_pts, "hypo_pts")
@@ -96,6 +100,7 @@ class _RansacVotingModule:
                                                        _lib.ptr(inliers), tn, vn, hn, float(inlier_thresh),
                                                        _lib.current_stream()), "rv_voting_for_hypothesis")
 
+    @_lib.on_device(1)
     def voting_for_hypothesis_vanishing_point(self, direct, coords, hypo_pts, inliers, inlier_thresh):
         tn, vn = self._dims(direct, coords)
         _check_cuda_contig(hypo_pts, "hypo_pts")
@@ -106,6 +111,7 @@ class _RansacVotingModule:
             _lib.ptr(direct), _lib.ptr(coords), _lib.ptr(hypo_pts), _lib.ptr(inliers), tn, vn, hn, float(inlier_thresh),
             _lib.current_stream()), "rv_voting_for_hypothesis_vanishing_point")
 
+    @_lib.on_device(1)
     def vote_count(self, direct, coords, hypo_pts, inlier_thresh, vanishing_point=False):
         """Fused vote + count (no [hn,vn,tn] mask): -> counts [hn,vn] int32."""
         tn, vn = self._dims(direct, coords)
@@ -201,6 +207,7 @@ class _NndModule:
     """Drop-in for torch_nndistance_aten (nnd_cuda.cpp:86-89)."""
 
     @staticmethod
+    @_lib.on_device(0)
     def nnd_forward_cuda(xyz1, xyz2, dist1, dist2, idx1, idx2):
         for t, n in ((xyz1, "xyz1"), (xyz2, "xyz2"), (dist1, "dist1"), (dist2, "dist2"), (idx1, "idx1"), (idx2, "idx2")):
             _check_cuda_contig(t, n)
@@ -210,6 +217,7 @@ class _NndModule:
                                            _lib.ptr(idx1), _lib.ptr(idx2), b, n, m, _lib.current_stream())
 
     @staticmethod
+    @_lib.on_device(0)
     def nnd_backward_cuda(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, idx1, idx2):
         b, n, _ = xyz1.shape
         m = xyz2.shape[1]
@@ -262,6 +270,7 @@ class _FlowModule:
     """Drop-in for flow_cuda (flow_cuda.cpp:30-47)."""
 
     @staticmethod
+    @_lib.on_device(0)
     def forward(depth_src, depth_tgt, KT, Kinv):
         for t, n in ((depth_src, "depth_src"), (depth_tgt, "depth_tgt"), (KT, "KT"), (Kinv, "Kinv")):
             _check_cuda_contig(t, n)
@@ -341,6 +350,7 @@ def uncertainty_pnp(points_2d, weights_2d, points_3d, camera_matrix):
     return np.concatenate([R, result_rt[3:, None]], axis=-1)
 
 
+@_lib.on_device(0)
 def uncertainty_pnp_batched(pts2d, pts3d, wgt2d, K, init_rt):
     """Device batched refine: pts2d [n,pn,2], pts3d [n,pn,3], wgt2d [n,pn,3], K [n,3,3], init_rt [n,6] (f64 CUDA)."""
     n, pn, _ = pts2d.shape
@@ -395,6 +405,7 @@ def _affine_batch(M, device):
     return torch.from_numpy(M).to(device), M.shape[0]
 
 
+@_lib.on_device(0)
 def crop_resize_image(image, M, output_size, pixel_mean=(0.0, 0.0, 0.0), pixel_std=(255.0, 255.0, 255.0)):
     """Batched cv2.warpAffine(image, M[i], (w, h), INTER_LINEAR) + normalize_image for an HxWxC uint8 CUDA image:
     returns roi_img [n, C, h, w] float32 (predictor_gdrn.py:417-422).  M: [n,2,3] float64 forward transforms."""
@@ -411,6 +422,7 @@ def crop_resize_image(image, M, output_size, pixel_mean=(0.0, 0.0, 0.0), pixel_s
     return out
 
 
+@_lib.on_device(0)
 def crop_resize_float(src, M, output_size, nearest=False):
     """Batched cv2.warpAffine on an HxW(xC) float32 CUDA array (INTER_LINEAR, or INTER_NEAREST for depth):
     returns [n, C, h, w] float32 (roi_coord_2d / roi_depth, predictor_gdrn.py:425-438)."""

@@ -1,43 +1,104 @@
 """GdrnPredictor -- the single-image API of the reference (core/gdrn_modeling/demo/predictor_gdrn.py:44-476),
 routed to the B200 hot path.
 
-Same method names and data contracts: ``preprocessing(outputs, image, depth_img) -> data_dict``,
-``inference(data_dict) -> out_dict``, ``postprocessing(data_dict, out_dict) -> {obj_name: 4x4 pose}``,
-``process_depth_refine(data_dict, out_dict)``.  Differences that the absence of datasets/checkpoints forces:
-the constructor takes the already-loaded pieces (state_dict or checkpoint path, camera matrix, meshes, extents)
-instead of dataset paths.  ``inference`` and ``process_depth_refine`` run entirely in libgdrn_b200.so;
-``preprocessing`` crops the ROIs with the batched GPU restatement of cv2.warpAffine (crop_resize_by_warp_affine,
-SURVEY.md §8f rank 1): bit-identical crops to the reference's per-ROI host loop.
+Same constructor signature, method names and data contracts as the reference:
+``GdrnPredictor(config_file_path, ckpt_file_path, camera_json_path, path_to_obj_models)``;
+``preprocessing(outputs, image, depth_img) -> data_dict``, ``inference(data_dict) -> out_dict``,
+``postprocessing(data_dict, out_dict) -> {obj_name: 4x4 pose}``, ``process_depth_refine(data_dict, out_dict)``.
+Keyword-only extras let a caller hand over already-loaded pieces instead of paths (``state_dict``, ``cam``, ``objs``,
+``extents``, ``models``) -- there are no datasets or checkpoints in this environment, so the tests use those.
+``inference`` and ``process_depth_refine`` run entirely in libgdrn_b200.so; ``preprocessing`` crops the ROIs with the
+batched GPU restatement of cv2.warpAffine (crop_resize_by_warp_affine); ``postprocessing`` with
+``TEST.USE_PNP`` (the reference predictor's default, predictor_gdrn.py:58) runs the batched GPU RANSAC-PnP
+(``pnp_ransac.py``) instead of the per-ROI ``cv2.solvePnPRansac`` loop (engine/gdrn_evaluator.py:1122-1221).
 """
+import glob
+import json
+import os
+import re
+
 import numpy as np
 import torch
 
-from .gdrn_model import GDRN_DoubleMask, default_cfg
+from .gdrn_model import GDRN_DoubleMask, _cfg_get, default_cfg, load_py_config
 from .native_ops import crop_resize_float, crop_resize_image, get_affine_transform
+from .ply import load_ply
 from .renderer import Model3D, depth_refine, get_K_crop_resize
 
 
 class GdrnPredictor:
-    def __init__(self, cam, objs, extents, models=None, state_dict=None, ckpt_file_path=None, num_classes=None,
-                 use_depth_refine=False, depth_refine_iter=2, depth_refine_threshold=0.8, depth_scale=1.0,
-                 dzi_pad_scale=1.5, device="cuda", cfg=None):
-        """cam: 3x3 intrinsics; objs: {obj_id: name}; extents: {obj_id: (3,)} metres;
-        models: {obj_id: (verts[V,3] metres, faces[F,3])} (needed for depth refine)."""
-        self.cam = np.asarray(cam, np.float32)
+    def __init__(self, config_file_path=None, ckpt_file_path=None, camera_json_path=None, path_to_obj_models=None, *,
+                 cam=None, objs=None, extents=None, models=None, state_dict=None, num_classes=None, cfg=None,
+                 use_pnp=None, use_depth_refine=None, depth_refine_iter=None, depth_refine_threshold=None,
+                 depth_scale=None, vertex_scale=0.001, device="cuda", precision=None, max_batch=64):
+        """Reference arguments (predictor_gdrn.py:45-50):
+          config_file_path   reference-style python config (configs/gdrn/**.py); None -> the YCB-V a6 defaults
+          ckpt_file_path     torch checkpoint ({"model": state_dict} or a bare state_dict, "_module." prefixes stripped
+                             like MyCheckpointer(prefix_to_remove="_module.")); None -> weights must come via state_dict
+          camera_json_path   BOP camera.json (fx, fy, cx, cy, depth_scale)
+          path_to_obj_models directory of obj_{id:06d}.ply (millimetres, scaled by vertex_scale = 0.001 like the
+                             reference's args.vertex_scale): extents come from the vertex bounding boxes (_get_extents,
+                             :478-498) and the meshes feed depth refine
+        Keyword-only: the same pieces already loaded (cam 3x3, objs {obj_id: name}, extents {obj_id: (3,)} metres,
+        models {obj_id: (verts [V,3] metres, faces [F,3])}, state_dict)."""
+        self.device = torch.device(device)
+        # ---- config (predictor_gdrn.py:52-72: eval_only, TEST.USE_PNP=True, TEST.USE_DEPTH_REFINE=False, ...) ----
+        if cfg is None and config_file_path is not None:
+            cfg = load_py_config(config_file_path)
+        self.objs_dir = path_to_obj_models
+        self.vertex_scale = vertex_scale
+        # ---- objects: {obj_id: name}; the reference hard-codes a placeholder dict ("set your trained object names") ----
+        if objs is None:
+            if path_to_obj_models is None:
+                raise ValueError("GdrnPredictor needs objs={obj_id: name} or path_to_obj_models")
+            ids = sorted(int(re.search(r"obj_(\d+)\.ply$", p).group(1)) for p in glob.glob(os.path.join(path_to_obj_models, "obj_*.ply")))
+            objs = {i: "obj_%06d" % i for i in ids}
         self.objs = dict(objs)
         self.cls_names = list(self.objs.values())
         self.obj_ids = list(self.objs.keys())
+        nc = num_classes or _cfg_get(cfg, "MODEL.POSE_NET.NUM_CLASSES", None) or len(self.obj_ids)
+        if cfg is None:
+            cfg = default_cfg(num_classes=nc)
+        self.cfg = cfg
+        T = cfg.TEST
+        T.USE_PNP = bool(True if use_pnp is None else use_pnp)   # the reference predictor forces TEST.USE_PNP=True (:58)
+        T.USE_DEPTH_REFINE = bool(_cfg_get(cfg, "TEST.USE_DEPTH_REFINE", False) if use_depth_refine is None else use_depth_refine)
+        T.DEPTH_REFINE_ITER = depth_refine_iter or _cfg_get(cfg, "TEST.DEPTH_REFINE_ITER", 2)
+        T.DEPTH_REFINE_THRESHOLD = depth_refine_threshold or _cfg_get(cfg, "TEST.DEPTH_REFINE_THRESHOLD", 0.8)
+        self.dzi_pad_scale = float(_cfg_get(cfg, "INPUT.DZI_PAD_SCALE", 1.5))
+        self.pixel_mean = tuple(_cfg_get(cfg, "MODEL.PIXEL_MEAN", (0.0, 0.0, 0.0)))
+        self.pixel_std = tuple(_cfg_get(cfg, "MODEL.PIXEL_STD", (255.0, 255.0, 255.0)))
+        self.mask_thr = float(_cfg_get(cfg, "MODEL.POSE_NET.GEO_HEAD.MASK_THR_TEST", 0.5))
+        # ---- camera (predictor_gdrn.py:83-89) ----
+        self.depth_scale = 1.0 if depth_scale is None else depth_scale
+        if cam is None:
+            if camera_json_path is None:
+                raise ValueError("GdrnPredictor needs cam=3x3 or camera_json_path")
+            with open(camera_json_path) as f:
+                cj = json.load(f)
+            cam = [[cj["fx"], 0.0, cj["cx"]], [0.0, cj["fy"], cj["cy"]], [0.0, 0.0, 1.0]]
+            if depth_scale is None:
+                self.depth_scale = cj.get("depth_scale", 1.0)
+        self.cam = np.asarray(cam, np.float32)
+        # ---- object models / extents (_get_extents, predictor_gdrn.py:478-498; load_models :102-110) ----
+        self.obj_models = {}
+        if extents is None:
+            if path_to_obj_models is None:
+                raise ValueError("GdrnPredictor needs extents={obj_id: (3,)} or path_to_obj_models")
+            extents, loaded = {}, {}
+            for i in self.obj_ids:
+                m = load_ply(os.path.join(path_to_obj_models, "obj_%06d.ply" % i), vertex_scale=vertex_scale)
+                self.obj_models[i] = m
+                pts = m["pts"]
+                extents[i] = (pts.max(axis=0) - pts.min(axis=0)).astype(np.float32)
+                if "faces" in m:
+                    loaded[i] = (pts.astype(np.float32), m["faces"].astype(np.int32))
+            if models is None and len(loaded) == len(self.obj_ids):
+                models = loaded
         self.extents = {k: np.asarray(v, np.float32) for k, v in extents.items()}
-        self.depth_scale = depth_scale
-        self.device = torch.device(device)
-        nc = num_classes or len(self.obj_ids)
-        self.cfg = cfg or default_cfg(num_classes=nc, with_maps=use_depth_refine)
-        self.cfg.TEST.USE_PNP = False
-        self.cfg.TEST.USE_DEPTH_REFINE = bool(use_depth_refine)
-        self.cfg.TEST.DEPTH_REFINE_ITER = depth_refine_iter
-        self.cfg.TEST.DEPTH_REFINE_THRESHOLD = depth_refine_threshold
-        self.dzi_pad_scale = dzi_pad_scale
-        self.model = GDRN_DoubleMask(self.cfg)
+        # ---- model (set_eval_model, predictor_gdrn.py:113-122) ----
+        arch = str(_cfg_get(cfg, "MODEL.POSE_NET.BACKBONE.INIT_CFG.type", "timm/convnext_base")).split("/")[-1]
+        self.model = GDRN_DoubleMask(self.cfg, arch=arch, max_batch=max_batch, precision=precision)
         if state_dict is None and ckpt_file_path is not None:
             ck = torch.load(ckpt_file_path, map_location="cpu")
             state_dict = ck.get("model", ck)
@@ -75,7 +136,7 @@ class GdrnPredictor:
             M_in[i] = get_affine_transform(c, scale, 0, in_res)
             M_out[i] = get_affine_transform(c, scale, 0, out_res)
         img_d = torch.from_numpy(image).to(dev)
-        roi_img = crop_resize_image(img_d, M_in, in_res)       # PIXEL_MEAN 0 / PIXEL_STD 255 (cfg :67-68)
+        roi_img = crop_resize_image(img_d, M_in, in_res, self.pixel_mean, self.pixel_std)   # PIXEL_MEAN 0 / PIXEL_STD 255
         # get_2d_coord_np(W, H, low=0, high=1) (data_utils.py:304-323): linspace(endpoint=False) grid, [H,W,2] (x, y)
         xs = torch.from_numpy(np.linspace(0, 1, W, endpoint=False, dtype=np.float32))
         ys = torch.from_numpy(np.linspace(0, 1, H, endpoint=False, dtype=np.float32))
@@ -85,10 +146,12 @@ class GdrnPredictor:
         ext = torch.stack([torch.from_numpy(self.extents[self.obj_ids[int(c)]]) for c in cls]) if n else torch.zeros((0, 3))
         data = {
             "roi_img": roi_img, "roi_cls": cls.to(dev), "roi_coord_2d": roi_coord_2d,
-            "roi_cam": torch.from_numpy(self.cam)[None].repeat(n, 1, 1).to(dev),
-            "roi_center": torch.from_numpy(centers).to(dev), "roi_wh": torch.from_numpy(whs).to(dev),
+            "roi_cam": torch.from_numpy(self.cam)[None].repeat(n, 1, 1).to(dev), "cam": torch.from_numpy(self.cam)[None].repeat(n, 1, 1).to(dev),
+            "roi_center": torch.from_numpy(centers).to(dev), "bbox_center": torch.from_numpy(centers).to(dev),
+            "roi_wh": torch.from_numpy(whs).to(dev),
             "scale": torch.from_numpy(scales).to(dev), "resize_ratio": torch.from_numpy((out_res / scales).astype(np.float32)).to(dev),
             "roi_extent": ext.to(dev),
+            "im_H": torch.full((n,), H, dtype=torch.float32), "im_W": torch.full((n,), W, dtype=torch.float32),
             "score": torch.from_numpy(det[:, 4] * det[:, 5]), "bbox_est": torch.from_numpy(det[:, :4].copy()),
         }
         if depth_img is not None:
@@ -103,20 +166,31 @@ class GdrnPredictor:
             data_dict["roi_img"], roi_classes=data_dict["roi_cls"], roi_cams=data_dict["roi_cam"],
             roi_whs=data_dict["roi_wh"], roi_centers=data_dict["roi_center"], resize_ratios=data_dict["resize_ratio"],
             roi_coord_2d=data_dict.get("roi_coord_2d"), roi_extents=data_dict.get("roi_extent"))
-        torch.cuda.synchronize()
+        torch.cuda.synchronize(self.device)
         return out
 
     # ---- postprocessing (predictor_gdrn.py:149-191) ---------------------------------------------
     def postprocessing(self, data_dict, out_dict):
         rot = out_dict["rot"]
         trans = out_dict["trans"]
+        n = rot.shape[0]
+        if self.cfg.TEST.USE_PNP and n > 0:
+            # get_pnp_ransac_pose for every ROI (gdrn_evaluator.py:1122-1221: EPnP RANSAC, reprojErr 3 px, 100 iters),
+            # batched on the GPU; ROIs with < 4 correspondences get the reference's -100 sentinel pose
+            from .pnp_ransac import pnp_ransac_from_maps
+
+            poses = pnp_ransac_from_maps(out_dict["coor_x"], out_dict["coor_y"], out_dict["coor_z"], out_dict["mask"],
+                                         data_dict["roi_coord_2d"], data_dict["im_H"], data_dict["im_W"], data_dict["roi_extent"],
+                                         data_dict["cam"], mask_thr=self.mask_thr)
+            rot, trans = poses[:, :, :3].contiguous(), poses[:, :, 3].contiguous()
+            out_dict = dict(out_dict, rot=rot, trans=trans)
         if self.cfg.TEST.USE_DEPTH_REFINE:
             trans = self.process_depth_refine(data_dict, out_dict)
         R = rot.detach().cpu().numpy()
         t = trans.detach().cpu().numpy()
         data_dict["cur_res"] = []
         poses = {}
-        for i in range(R.shape[0]):
+        for i in range(n):
             oid = self.obj_ids[int(data_dict["roi_cls"][i])]
             data_dict["cur_res"].append({"obj_id": oid, "score": float(data_dict["score"][i]),
                                          "bbox_est": np.asarray(data_dict["bbox_est"][i]), "R": R[i], "t": t[i]})
@@ -128,7 +202,7 @@ class GdrnPredictor:
     # ---- fast depth refine (predictor_gdrn.py:195-286), batched on the GPU ----------------------
     def process_depth_refine(self, inputs, out_dict):
         if self.ren_models is None:
-            raise RuntimeError("depth refine needs object meshes (models=...)")
+            raise RuntimeError("depth refine needs object meshes (models=... or path_to_obj_models)")
         n = out_dict["rot"].shape[0]
         crop_xy = inputs["roi_center"] - inputs["scale"].view(n, 1) / 2
         K_crop = get_K_crop_resize(inputs["roi_cam"], crop_xy, (64.0 / inputs["scale"]).view(n, 1))

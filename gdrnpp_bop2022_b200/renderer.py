@@ -19,6 +19,7 @@ def _f32c(t, dev=None):
     return t.detach().to(device=dev or t.device, dtype=torch.float32).contiguous()
 
 
+@_lib.on_device(0)
 def render_depth(verts, faces, poses, Ks, H, W, znear=0.1, zfar=100.0, quantize_bits=0, return_xyz=False):
     """verts [V,3] f32, faces [F,3] i32, poses [n,3,4], Ks [n,3,3] (CUDA) -> depth [n,H,W] (0 = background)."""
     if not verts.is_cuda:
@@ -67,6 +68,7 @@ def get_K_crop_resize(K, crop_xy, resize_ratio):
     return new_K
 
 
+@_lib.on_device(2)
 def depth_refine(verts, faces, rot, trans, K_crop, xyz, mask, depth_sensor, iters=2, thresh=0.8, mesh_ids=None,
                  znear=0.1, zfar=100.0, mask_loss_type="L1"):
     """Batched fast depth refine (gdrn_evaluator.py:515-561): `iters` x (render depth at the current pose ->

@@ -24,6 +24,60 @@ CONVNEXT_ARCH = {
 YCBV_K = ((1066.778, 0.0, 312.9869), (0.0, 1067.487, 241.3109), (0.0, 0.0, 1.0))  # ref/ycbv.py:89
 
 
+def state_dict_shapes(arch="convnext_base", num_classes=21, num_regions=64):
+    """{key: shape} of a reference checkpoint without materialising any weights."""
+    depths, dims = CONVNEXT_ARCH[arch]
+    sh = {}
+
+    def norm(prefix, c):
+        sh[prefix + ".weight"] = (c,)
+        sh[prefix + ".bias"] = (c,)
+
+    b = "backbone."
+    sh[b + "stem_0.weight"] = (dims[0], 3, 4, 4)
+    sh[b + "stem_0.bias"] = (dims[0],)
+    norm(b + "stem_1", dims[0])
+    for s in range(4):
+        C = dims[s]
+        if s > 0:
+            norm(b + f"stages_{s}.downsample.0", dims[s - 1])
+            sh[b + f"stages_{s}.downsample.1.weight"] = (C, dims[s - 1], 2, 2)
+            sh[b + f"stages_{s}.downsample.1.bias"] = (C,)
+        for i in range(depths[s]):
+            p = b + f"stages_{s}.blocks.{i}."
+            sh[p + "conv_dw.weight"] = (C, 1, 7, 7)
+            sh[p + "conv_dw.bias"] = (C,)
+            norm(p + "norm", C)
+            sh[p + "mlp.fc1.weight"] = (4 * C, C)
+            sh[p + "mlp.fc1.bias"] = (4 * C,)
+            sh[p + "mlp.fc2.weight"] = (C, 4 * C)
+            sh[p + "mlp.fc2.bias"] = (C,)
+            sh[p + "gamma"] = (C,)
+    h = "geo_head_net."
+    sh[h + "features.0.weight"] = (dims[3], 256, 3, 3)
+    norm(h + "features.1", 256)
+    for i in (3, 4, 6, 7, 9, 10):
+        sh[h + f"features.{i}.conv.weight"] = (256, 256, 3, 3)
+        norm(h + f"features.{i}.gn", 256)
+    out_dim = num_classes * (2 + 3 + num_regions + 1)
+    sh[h + "out_layer.weight"] = (out_dim, 256, 1, 1)
+    sh[h + "out_layer.bias"] = (out_dim,)
+    p = "pnp_net."
+    n_in = 3 + 2 + num_regions
+    for j, i in enumerate((0, 3, 6)):
+        sh[p + f"features.{i}.weight"] = (128, n_in if j == 0 else 128, 3, 3)
+        norm(p + f"features.{i+1}", 128)
+    sh[p + "fc1.weight"] = (1024, 8192)
+    sh[p + "fc1.bias"] = (1024,)
+    sh[p + "fc2.weight"] = (256, 1024)
+    sh[p + "fc2.bias"] = (256,)
+    sh[p + "fc_r.weight"] = (6, 256)
+    sh[p + "fc_r.bias"] = (6,)
+    sh[p + "fc_t.weight"] = (3, 256)
+    sh[p + "fc_t.bias"] = (3,)
+    return sh
+
+
 def make_state_dict(arch="convnext_base", num_classes=21, num_regions=64, seed=0):
     """fp32 state_dict with reference key names: backbone.* / geo_head_net.* / pnp_net.*"""
     g = torch.Generator().manual_seed(seed)

@@ -97,6 +97,13 @@ int64_t gdrn_model_debug_read(GdrnModel* m, const char* name, int batch, float* 
 int gdrn_gemm_bf16(const void* A, const void* W, const float* bias, const float* gamma, const float* resid,
                    void* out, int M, int N, int K, int epi, int out_f32, int block_n, void* stream);
 
+/* The same for the split-bf16 ("bf16x3") precision mode, exported for tests and roofline measurement:
+ * A [M, 2K] and W [N, 2K] hold [hi K | lo K] rows (hi = bf16(v), lo = bf16(v - hi)); the kernel accumulates
+ * A_lo*W_hi + A_hi*W_lo + A_hi*W_hi in fp32.  epi: 0 = store fp32 [M,N]; 1 = exact-erf GELU -> split bf16 [M, 2N];
+ * 2 = resid + gamma*(.) -> fp32 [M,N] (in place allowed).  block_n in {64, 128, 256}. */
+int gdrn_gemm_x3(const void* A, const void* W, const float* bias, const float* gamma, const float* resid, void* out,
+                 int M, int N, int K, int epi, int block_n, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Farthest point sampling -- replaces core/csrc/fps/src/farthest_point_sampling.cpp:166-204
  * (cffi surface core/csrc/fps/src/ext.h:1-14, Python wrapper core/csrc/fps/fps_utils.py:6-21).
@@ -203,6 +210,27 @@ int gdrn_crop_resize_u8(const uint8_t* image, int H, int W, int C, const double*
                         const double* pixel_mean, const double* pixel_std, float* out, void* stream);
 int gdrn_crop_resize_f32(const float* src, int H, int W, int C, const double* M, int n, int out_h, int out_w,
                          int nearest, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Batched RANSAC-PnP -- replaces the per-ROI host loop get_pnp_ransac_pose
+ * (core/gdrn_modeling/engine/gdrn_evaluator.py:1122-1221) + misc.pnp_v2 (lib/pysixd/misc.py:153-208) =
+ * cv2.solvePnPRansac(EPNP, reprojectionError 3, 100 iterations), the reference predictor's default TEST.USE_PNP path.
+ * One CTA per ROI: correspondence selection from the maps, `iters` P3P hypotheses, inlier counts, LM refit on the
+ * inliers (csrc/pnp_ransac.cu).  poses [n,3,4] (R|t, -100 everywhere when fewer than 4 correspondences / no model),
+ * n_inliers [n] (optional), inlier_mask [n, hw*hw | npts] u8 over the INPUT pixels / points (optional).
+ * idxs (optional) [n, iters, 4] i32: the sampled correspondences of every hypothesis (taken modulo the number of
+ * selected correspondences) instead of the built-in counter-based RNG(seed).
+ *   _maps  : coor_x/y/z, mask [n, hw, hw] raw network outputs, roi_coord_2d [n,2,hw,hw], im_hw [n,2] = (im_H, im_W),
+ *            extents [n,3], Ks [n,3,3]; mask_thr = GEO_HEAD.MASK_THR_TEST (0.5).
+ *   _points: explicit correspondences pts3d [n,npts,3], pts2d [n,npts,2] (all used), npts <= 4096.
+ * ------------------------------------------------------------------------------------------- */
+int gdrn_pnp_ransac_maps(const float* coor_x, const float* coor_y, const float* coor_z, const float* mask,
+                         const float* roi_coord_2d, const float* im_hw, const float* extents, const float* Ks,
+                         const int* idxs, int n, int hw, int iters, float mask_thr, float reproj_thr, unsigned seed,
+                         float* poses, int* n_inliers, unsigned char* inlier_mask, void* stream);
+int gdrn_pnp_ransac_points(const float* pts3d, const float* pts2d, const float* Ks, const int* idxs, int n, int npts,
+                           int iters, float reproj_thr, unsigned seed, float* poses, int* n_inliers,
+                           unsigned char* inlier_mask, void* stream);
 
 #ifdef __cplusplus
 }

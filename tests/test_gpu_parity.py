@@ -93,18 +93,60 @@ def test_gemm_gelu_modes(dev, lib, mode, monkeypatch):
     assert (err <= tol).all(), float((err - tol).max())
 
 
+def _split_bf16(t):
+    hi = t.bfloat16()
+    lo = (t - hi.float()).bfloat16()
+    return torch.cat([hi, lo], dim=1).contiguous()
+
+
+@pytest.mark.parametrize("M,N,K,bn,epi", [
+    # CTA-pair split kernel (>= 48 pair tiles): GELU -> split bf16, fp32 store, in-place residual (TMA reduce-add),
+    # BLOCK_N 128, ragged M (odd tile count + partial tile: the peer CTA of the last pair has no rows)
+    (8192, 512, 256, 256, 1), (8192, 1024, 128, 256, 0), (12417, 256, 512, 256, 2), (16384, 128, 512, 128, 2),
+    (12300, 128, 128, 128, 1), (16384, 512, 2048, 256, 2),
+    # general kernel with the 3x tap list (too few tiles for the pairs, or BLOCK_N 64)
+    (300, 128, 64, 128, 0), (1000, 512, 128, 256, 1), (64, 1024, 8192, 64, 1), (4096, 256, 1024, 256, 2),
+])
+def test_gemm_x3_vs_fp64(dev, lib, M, N, K, bn, epi):
+    """Split-bf16 ("bf16x3") GEMM -- the tensor-core path of the fp32-parity mode -- vs an fp64 torch reference of the
+    same op on the ORIGINAL fp32 operands: the dropped lo*lo term and the hi+lo representation are ~2^-17 relative."""
+    L = _lib()
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K + epi)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(dev)
+    W = (torch.randn(N, K, generator=g) / np.sqrt(K)).to(dev)
+    bias, gamma = torch.randn(N, generator=g).to(dev), torch.rand(N, generator=g).to(dev)
+    x = torch.randn(M, N, generator=g).to(dev)
+    ref = A.double() @ W.double().t() + bias.double()
+    if epi == 1:
+        ref = torch.nn.functional.gelu(ref)
+    if epi == 2:
+        ref = x.double() + gamma.double() * ref
+    A2, W2 = _split_bf16(A), _split_bf16(W)
+    if epi == 1:
+        out = torch.full((M + 64, 2 * N), float("nan"), dtype=torch.bfloat16, device=dev)
+    else:
+        out = torch.full((M + 64, N), 7.0, dtype=torch.float32, device=dev)   # canary rows behind the matrix
+        if epi == 2:
+            out[:M] = x
+    L.check(lib.gdrn_gemm_x3(L.ptr(A2), L.ptr(W2), L.ptr(bias), L.ptr(gamma), L.ptr(out), L.ptr(out), M, N, K, epi, bn,
+                             L.current_stream()), "gemm_x3")
+    torch.cuda.synchronize()
+    if epi == 1:
+        got = out[:M, :N].double() + out[:M, N:].double()
+        assert torch.isnan(out[M:].float()).all()
+    else:
+        got = out[:M].double()
+        assert torch.equal(out[M:], torch.full((64, N), 7.0, device=dev))
+    err = (got - ref).abs().max().item()
+    assert err < 4e-5 * max(1.0, ref.abs().max().item()), err
+
+
 # ----------------------------------------------------------------------------------------------- model
-def _run_model(dev, B, seed, with_maps=True, precision="bf16", trained_like_rot=False):
+def _run_model(dev, B, seed, with_maps=True, precision="bf16"):
     from gdrnpp_bop2022_b200.gdrn_model import GDRN_DoubleMask, default_cfg
     from gdrnpp_bop2022_b200.synthetic import make_batch, make_state_dict
 
-    sd = make_state_dict()
-    if trained_like_rot:
-        # The reference initialises fc_r with std 0.01 (conv_pnp_net.py:109-110), so a random-init head emits 6-D
-        # rotation vectors of norm ~0.05 and the Gram-Schmidt normalisation (rot_reps.py:34-55) amplifies any
-        # difference ~20x.  A trained head emits O(1) vectors: give fc_r an O(1) bias so the rotation error is
-        # measured at the conditioning the 1e-4 rad bar is meant for.  Oracle and device get the same weights.
-        sd["pnp_net.fc_r.bias"] = torch.tensor([0.9, 0.2, -0.35, -0.15, 0.8, 0.45])
+    sd = make_state_dict()   # the SAME weights bench.py and smoke() use (no per-test overrides)
     batch = make_batch(B=B, seed=seed)
     model = GDRN_DoubleMask(default_cfg(with_maps=with_maps), max_batch=max(B, 2), precision=precision)
     model.load_state_dict(sd)
@@ -144,12 +186,27 @@ def test_forward_vs_oracle_bf16(dev, B):
     assert (out["trans"].cpu() - ref["trans"]).abs().max().item() < 1e-2
 
 
+def _rot6d_conditioning(rot6d):
+    """Gram-Schmidt amplification of rot6d -> R (core/utils/rot_reps.py:34-55): a perturbation e of the 6-D vector moves
+    R by ~ e / min(|a1|, |a2 - (a2.x)x|).  A trained head emits near-orthonormal pairs (kappa ~ 1); random-init weights
+    occasionally emit a short a1 and then ANY fp32 implementation (cuBLAS vs MKL included) moves R by kappa x its own
+    round-off."""
+    a1, a2 = rot6d[:, :3].double(), rot6d[:, 3:].double()
+    n1 = a1.norm(dim=1)
+    x = a1 / n1[:, None]
+    a2p = a2 - (a2 * x).sum(1, keepdim=True) * x
+    return 1.0 / torch.minimum(n1, a2p.norm(dim=1))
+
+
 @pytest.mark.parametrize("B", [1, 5, 16])
 def test_forward_vs_oracle_north_star_tolerance(dev, B):
-    """BASELINE.json north_star parity bar, met by the split-bf16 ("bf16x3") precision mode: R within 1e-4 rad and
-    t within 1e-3 of the fp32 oracle (= the reference's fp32 forward, pinned by tests/golden/ref_heads.npz), with the
-    maps and the raw Patch-PnP output at fp32-class tolerances."""
-    sd, batch, model, out = _run_model(dev, B, seed=60 + B, precision="bf16x3", trained_like_rot=True)
+    """BASELINE.json north_star parity bar, met by the split-bf16 ("bf16x3") precision mode with the unmodified
+    make_state_dict() weights: t within 1e-3, the raw Patch-PnP output (rot6d, t_) within 1e-4 and the maps within 2e-3
+    of the fp32 oracle (= the reference's fp32 forward, pinned by tests/golden/ref_heads.npz and torchvision), and R within
+    1e-4 rad x max(1, kappa) where kappa is the oracle rot6d's own Gram-Schmidt conditioning (1 for the O(1)-norm vectors
+    a trained head emits; the seed-76 batch holds one random-init ROI with |a1| = 0.13, kappa = 7.4).  The un-scaled
+    1e-4 rad bar is asserted on the bench's own batch in test_forward_vs_oracle_b64."""
+    sd, batch, model, out = _run_model(dev, B, seed=60 + B, precision="bf16x3")
     with torch.no_grad():
         ref = O.gdrn_forward(sd, batch, return_maps=True, return_intermediate=True)
     x3 = model.debug_read("stage3_x", B, B * 64 * 1024).reshape(B, 8, 8, 1024).permute(0, 3, 1, 2).cpu()
@@ -160,10 +217,90 @@ def test_forward_vs_oracle_north_star_tolerance(dev, B):
     raw = out["raw"].cpu()
     assert (raw[:, :6] - ref["rot6d"]).abs().max().item() < 1e-4
     assert (raw[:, 6:] - ref["t_"]).abs().max().item() < 1e-4
+    rerr = _rot_err(out["rot"].cpu(), ref["rot"])
+    kappa = _rot6d_conditioning(ref["rot6d"]).clamp_min(1.0)
+    terr = (out["trans"].cpu() - ref["trans"]).abs().max().item()
+    assert (rerr < 1e-4 * kappa).all(), (rerr, kappa)   # north_star: R within 1e-4 rad (at unit conditioning)
+    assert terr < 1e-3, terr                           # north_star: t within 1e-3
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_forward_vs_oracle_b64(dev, precision):
+    """BASELINE.json configs[1] at its full size: the bench's own first batch (B = 64, seed 0, unmodified
+    make_state_dict() weights) against the fp32 oracle.  At B = 64 every GEMM takes the kernel the bench times (CTA-pair
+    kernels from M >= 4096 rows, the fused stage-0 MLP in bf16 mode) -- paths the small-batch tests do not reach.
+    bf16x3 (the mode of record): north-star bar R < 1e-4 rad, t < 1e-3.  bf16 (secondary throughput mode): its own
+    documented tolerances."""
+    sd, batch, model, out = _run_model(dev, 64, seed=0, precision=precision)
+    with torch.no_grad():
+        ref = O.gdrn_forward(sd, batch, return_maps=True, return_intermediate=True)
     rerr = _rot_err(out["rot"].cpu(), ref["rot"]).max().item()
     terr = (out["trans"].cpu() - ref["trans"]).abs().max().item()
-    assert rerr < 1e-4, rerr   # north_star: R within 1e-4 rad
-    assert terr < 1e-3, terr   # north_star: t within 1e-3
+    raw = out["raw"].cpu()
+    if precision == "bf16x3":
+        x3 = model.debug_read("stage3_x", 64, 64 * 64 * 1024).reshape(64, 8, 8, 1024).permute(0, 3, 1, 2).cpu()
+        assert ((x3 - ref["conv_feat"]).norm() / ref["conv_feat"].norm()).item() < 1e-4
+        for k in ("mask", "full_mask", "coor_x", "coor_y", "coor_z", "region"):
+            assert (out[k].cpu() - ref[k]).abs().max().item() < 2e-3, k
+        assert (raw[:, :6] - ref["rot6d"]).abs().max().item() < 1e-4
+        assert rerr < 1e-4, rerr
+        assert terr < 1e-3, terr
+    else:
+        for k in ("mask", "full_mask", "coor_x", "coor_y", "coor_z", "region"):
+            assert (out[k].cpu() - ref[k]).abs().max().item() < 0.15, k
+        assert rerr < 0.1 and terr < 1e-2, (rerr, terr)
+
+
+def test_sharded_4096_rois_vs_oracle_sample(dev):
+    """BASELINE.json configs[3]: 4096 ROIs in contiguous shards of 512 (dist.shard_range, 8 ranks), 64 ROIs per step
+    through one captured CUDA graph, poses packed / gathered in rank order like dist.all_gather_poses.  Here the 8
+    shards run back to back on one GPU (the NCCL gather itself is covered by the gloo world-2 test and by
+    bench.py --gpus N); three ROIs of every shard are checked against the fp32 oracle at the north-star bar."""
+    from gdrnpp_bop2022_b200.dist import pack_poses, shard_range, unpack_poses
+    from gdrnpp_bop2022_b200.gdrn_model import GDRN_DoubleMask, default_cfg
+    from gdrnpp_bop2022_b200.synthetic import make_batch, make_state_dict
+
+    total, world, step = 4096, 8, 64
+    sd = make_state_dict()
+    model = GDRN_DoubleMask(default_cfg(), max_batch=step, precision="bf16x3")
+    model.load_state_dict(sd)
+    model.to(dev)
+    keys = ("roi_img", "roi_classes", "roi_coord_2d", "roi_cams", "roi_centers", "roi_whs", "resize_ratios", "roi_extents")
+    static = {k: v.to(dev) for k, v in make_batch(B=step, seed=1).items() if k in keys}
+    replay, out = model.capture_graph(static)
+    gathered, sample_in, sample_idx = [], {k: [] for k in keys}, []
+    rs = np.random.RandomState(4)
+    for rank in range(world):
+        b, e = shard_range(total, rank, world)
+        assert (e - b) == 512 and b % step == 0
+        local = []
+        picks = set((b + rs.choice(e - b, 3, replace=False)).tolist())
+        for s0 in range(b, e, step):
+            hb = make_batch(B=step, seed=1 + s0 // step)     # ROI i lives in step i // 64 (seed 1 + step), slot i % 64
+            for k in keys:
+                static[k].copy_(hb[k])
+            replay()
+            local.append(pack_poses(out["rot"], out["trans"]).clone())
+            for i in range(s0, s0 + step):
+                if i in picks:
+                    sample_idx.append(i)
+                    for k in keys:
+                        sample_in[k].append(hb[k][i - s0])
+        gathered.append(torch.cat(local))
+    rot, trans = unpack_poses(torch.cat(gathered))
+    torch.cuda.synchronize()
+    assert rot.shape == (total, 3, 3) and trans.shape == (total, 3)
+    assert torch.isfinite(rot).all() and torch.isfinite(trans).all()
+    # rotations are orthonormal over the whole job (size-independent property)
+    eye = torch.eye(3, device=dev)
+    assert ((rot @ rot.transpose(1, 2)) - eye).abs().max().item() < 1e-5
+    sb = {k: torch.stack(v) for k, v in sample_in.items()}
+    with torch.no_grad():
+        ref = O.gdrn_forward(sd, sb, return_intermediate=True)
+    idx = torch.tensor(sample_idx)
+    kappa = _rot6d_conditioning(ref["rot6d"]).clamp_min(1.0)   # see test_forward_vs_oracle_north_star_tolerance
+    assert (_rot_err(rot[idx].cpu(), ref["rot"]) < 1e-4 * kappa).all()
+    assert (trans[idx].cpu() - ref["trans"]).abs().max().item() < 1e-3
 
 
 def test_precisions_agree_and_report(dev):
@@ -178,7 +315,7 @@ def test_precisions_agree_and_report(dev):
 def test_pose_lift_exact_given_head_output(dev):
     """rot6d -> R, centroid/z -> t, allo -> ego on the device vs the oracle's numpy/float64 path fed with the SAME
     Patch-PnP output: R within 1e-4 rad (measured ~1e-7), t within 1e-6 relative."""
-    sd, batch, model, out = _run_model(dev, 8, seed=77)
+    sd, batch, model, out = _run_model(dev, 8, seed=77, precision="bf16")
     raw = out["raw"].cpu()
     Rm = O.rot6d_to_mat_batch(raw[:, :6])
     ego, trans = O.pose_from_predictions_test(Rm, raw[:, 6:8], raw[:, 8:9], batch["roi_cams"], batch["roi_centers"],
@@ -199,7 +336,8 @@ def test_forward_is_deterministic_and_batch_invariant(dev):
     from gdrnpp_bop2022_b200.synthetic import make_batch, make_state_dict
 
     sd = make_state_dict()
-    model = GDRN_DoubleMask(default_cfg(), max_batch=8)
+    model = GDRN_DoubleMask(default_cfg(), max_batch=8)   # default precision = bf16x3, the mode of record
+    assert model.precision == "bf16x3"
     model.load_state_dict(sd)
     model.to(dev)
     b8 = {k: v.to(dev) for k, v in make_batch(B=8, seed=5).items()}
@@ -223,7 +361,7 @@ def test_fused_mlp_matches_unfused(dev, monkeypatch):
     outs = []
     for fused in ("0", "1"):
         monkeypatch.setenv("GDRN_MLP_FUSED", fused)
-        _, _, _, out = _run_model(dev, 8, seed=21)
+        _, _, _, out = _run_model(dev, 8, seed=21, precision="bf16")   # the fused kernel is a bf16-mode kernel
         outs.append(out)
     assert _rot_err(outs[0]["rot"].cpu(), outs[1]["rot"].cpu()).max().item() < 1e-3
     assert (outs[0]["trans"] - outs[1]["trans"]).abs().max().item() < 1e-4
@@ -321,7 +459,7 @@ def test_voting_vs_reference_cuda_build(dev):
     """The REFERENCE's own kernels (ransac_voting_kernel.cu compiled unmodified for sm_100a into oracle/_ref)."""
     ref = load_ref_ext("ransac_voting")
     if ref is None:
-        pytest.skip("oracle/_ref/ransac_voting not built")
+        pytest.xfail("oracle/_ref/ransac_voting not built (python oracle/build_ref.py --cuda-refs in the build container)")
     from gdrnpp_bop2022_b200.native_ops import ransac_voting as rv
 
     for tn, vn, hn, seed in ((2048, 9, 128, 1), (30000, 9, 128, 2), (777, 3, 64, 3)):
@@ -398,7 +536,7 @@ def test_nnd_bit_exact(dev, b, n, m):
 def test_nnd_vs_reference_cuda_build(dev):
     ref = load_ref_ext("torch_nndistance_aten")
     if ref is None:
-        pytest.skip("oracle/_ref/torch_nndistance_aten not built")
+        pytest.xfail("oracle/_ref/torch_nndistance_aten not built (python oracle/build_ref.py --cuda-refs in the build container)")
     from gdrnpp_bop2022_b200.native_ops import torch_nndistance_aten as mine
 
     torch.manual_seed(0)
@@ -602,7 +740,7 @@ def test_predictor_preprocessing_matches_reference_recipe(dev):
     K = np.array([[1066.778, 0, 312.9869], [0, 1067.487, 241.3109], [0, 0, 1]], np.float32)
     objs = {i + 1: "obj_%d" % (i + 1) for i in range(21)}
     extents = {i + 1: np.array([0.1, 0.12, 0.08], np.float32) for i in range(21)}
-    pred = GdrnPredictor(K, objs, extents, state_dict=make_state_dict(), device=dev)
+    pred = GdrnPredictor(cam=K, objs=objs, extents=extents, state_dict=make_state_dict(), device=dev, use_pnp=False)
     dets = np.array([[100, 80, 220, 260, 0.9, 0.8, 3], [400, 200, 460, 250, 0.7, 0.9, 10], [-20, 300, 90, 470, 0.5, 0.5, 0]],
                     np.float32)
     data = pred.preprocessing(dets, image, depth)
@@ -621,3 +759,176 @@ def test_predictor_preprocessing_matches_reference_recipe(dev):
         assert np.allclose(data["roi_wh"][i].cpu().numpy(), [bw, bh])
     out = pred.inference(data)
     assert out["rot"].shape == (3, 3, 3) and torch.isfinite(out["trans"]).all()
+
+
+# ------------------------------------------------------------------------- RANSAC-PnP post-process
+def _rand_pose(rs):
+    ax = rs.randn(3)
+    ax /= np.linalg.norm(ax)
+    R = O.axangle2mat(ax, rs.rand() * 3)
+    t = np.array([rs.randn() * 0.05, rs.randn() * 0.05, 0.7 + rs.rand() * 0.5])
+    return R, t
+
+
+def _rot_angle(Ra, Rb):
+    return float(np.arccos(np.clip((np.trace(Ra.T @ Rb) - 1) / 2, -1, 1)))
+
+
+def test_pnp_ransac_points_vs_cv2(dev):
+    """Batched GPU RANSAC-PnP on explicit correspondences vs cv2.solvePnPRansac (the call misc.pnp_v2 makes,
+    lib/pysixd/misc.py:187-196: EPnP, reprojectionError 3, 100 iterations) on synthetic 2D-3D pairs with pixel noise and
+    30 % gross outliers: both recover the ground truth, agree with each other to the noise level, and flag the same
+    correspondences as inliers; noise-free data is recovered exactly; < 4 points -> the reference's -100 sentinel."""
+    import cv2
+
+    from gdrnpp_bop2022_b200.pnp_ransac import solve_pnp_ransac
+
+    rs = np.random.RandomState(7)
+    K = np.array([[1066.778, 0, 312.9869], [0, 1067.487, 241.3109], [0, 0, 1]])
+    n, npts = 6, 600
+    P3, P2, GT, OUT = [], [], [], []
+    for i in range(n):
+        R, t = _rand_pose(rs)
+        X = (rs.rand(npts, 3) - 0.5) * np.array([0.12, 0.2, 0.09])
+        xc = X @ R.T + t
+        uv = np.stack([K[0, 0] * xc[:, 0] / xc[:, 2] + K[0, 2], K[1, 1] * xc[:, 1] / xc[:, 2] + K[1, 2]], 1)
+        outl = np.zeros(npts, bool)
+        if i > 0:                      # problem 0 is noise-free
+            uv += rs.randn(npts, 2) * 0.5
+            outl = rs.rand(npts) < 0.3
+            uv[outl] += rs.randn(int(outl.sum()), 2) * 40 + 25
+        P3.append(X); P2.append(uv); GT.append((R, t)); OUT.append(outl)
+    t_ = lambda a: torch.from_numpy(np.stack(a).astype(np.float32)).to(dev)
+    poses, ninl, imask = solve_pnp_ransac(t_(P3), t_(P2), torch.from_numpy(K.astype(np.float32))[None].to(dev), reproj_err=3.0,
+                                          iters=100, seed=3, return_inliers=True)
+    poses, ninl, imask = poses.cpu().numpy().astype(np.float64), ninl.cpu().numpy(), imask.cpu().numpy().astype(bool)
+    for i in range(n):
+        R, t = GT[i]
+        ok, rvec, tvec, inl = cv2.solvePnPRansac(P3[i][None].astype(np.float64), P2[i][None].astype(np.float64), K, np.zeros((8, 1)),
+                                                 flags=cv2.SOLVEPNP_EPNP, reprojectionError=3.0, iterationsCount=100)
+        assert ok
+        Rc = cv2.Rodrigues(rvec)[0]
+        Rm, tm = poses[i, :, :3], poses[i, :, 3]
+        assert abs(np.linalg.det(Rm) - 1) < 1e-5 and np.abs(Rm @ Rm.T - np.eye(3)).max() < 1e-5
+        tol_r, tol_t = (1e-4, 1e-5) if i == 0 else (4e-3, 2e-3)
+        assert _rot_angle(Rm, R) < tol_r and np.abs(tm - t).max() < tol_t, (i, _rot_angle(Rm, R), np.abs(tm - t).max())
+        assert _rot_angle(Rm, Rc) < 2 * tol_r + 1e-3 and np.abs(tm - tvec[:, 0]).max() < 2 * tol_t + 1e-3
+        cv_in = np.zeros(npts, bool)
+        cv_in[inl[:, 0]] = True
+        assert (imask[i] != cv_in).mean() < 0.03            # same inlier set up to points at the 3 px boundary
+        assert (imask[i] & OUT[i]).sum() <= 2 and ninl[i] == imask[i].sum()
+    few = solve_pnp_ransac(t_([P3[0][:3]]), t_([P2[0][:3]]), torch.from_numpy(K.astype(np.float32))[None].to(dev)).cpu().numpy()
+    assert (few == -100).all()
+    # caller-supplied samples: deterministic and independent of the seed
+    idxs = torch.from_numpy(rs.randint(0, npts, (n, 64, 4)).astype(np.int32))
+    a = solve_pnp_ransac(t_(P3), t_(P2), torch.from_numpy(K.astype(np.float32))[None].to(dev), idxs=idxs, seed=1)
+    b = solve_pnp_ransac(t_(P3), t_(P2), torch.from_numpy(K.astype(np.float32))[None].to(dev), idxs=idxs, seed=2)
+    assert torch.equal(a, b)
+
+
+def test_pnp_ransac_from_maps_vs_reference_recipe(dev):
+    """The map entry (get_pnp_ransac_pose, gdrn_evaluator.py:1122-1221) vs the reference recipe restated on the host with
+    numpy + cv2.solvePnPRansac: L1 mask min-max normalisation, xyz denormalisation by the extent, selection mask > 0.5 &
+    |xyz| > 1e-4 extent, image points = roi_coord_2d * (im_W, im_H).  Maps are synthesised from a known pose (object
+    points on a sphere seen through the ROI grid) with noise; one ROI has an empty mask."""
+    import cv2
+
+    from gdrnpp_bop2022_b200.pnp_ransac import pnp_ransac_from_maps
+
+    rs = np.random.RandomState(11)
+    K = np.array([[1066.778, 0, 312.9869], [0, 1067.487, 241.3109], [0, 0, 1]])
+    n, hw, imH, imW = 5, 64, 480, 640
+    cx_, cy_, cz_, mk, c2d, ext, GT = [], [], [], [], [], [], []
+    for i in range(n):
+        R, t = _rand_pose(rs)
+        r_obj = 0.05
+        e = np.array([0.12, 0.13, 0.11])
+        # ROI grid around the projected centre
+        pc = K @ t
+        pc = pc[:2] / pc[2]
+        scale = 2.6 * r_obj * K[0, 0] / t[2]
+        u = pc[0] + (np.arange(hw) - hw / 2) * scale / hw
+        v = pc[1] + (np.arange(hw) - hw / 2) * scale / hw
+        U, V = np.meshgrid(u, v)
+        rays = np.stack([(U - K[0, 2]) / K[0, 0], (V - K[1, 2]) / K[1, 1], np.ones_like(U)], -1)
+        rays /= np.linalg.norm(rays, axis=-1, keepdims=True)
+        b_ = (rays * t).sum(-1)
+        disc = b_ ** 2 - (t @ t - r_obj ** 2)
+        hit = disc > 0
+        depth = b_ - np.sqrt(np.where(hit, disc, 0))
+        Xc = rays * depth[..., None]
+        Xo = (Xc - t) @ R                     # R^T (Xc - t)
+        coor = Xo / e + 0.5 + rs.randn(hw, hw, 3) * 0.002
+        coor[~hit] = 0.5                      # background: exactly the centre -> rejected by the |xyz| > 1e-4 extent rule
+        m = np.where(hit, 0.9, 0.05) + rs.randn(hw, hw) * 0.02
+        if i == 3:
+            m[:] = 0.1; m[0, 0] = 0.2; coor[:] = 0.5      # nothing selectable
+        cx_.append(coor[..., 0]); cy_.append(coor[..., 1]); cz_.append(coor[..., 2]); mk.append(m)
+        c2d.append(np.stack([U / imW, V / imH])); ext.append(e); GT.append((R, t))
+    f = lambda a: torch.from_numpy(np.stack(a).astype(np.float32)).to(dev)
+    CX, CY, CZ, M = f(cx_)[:, None], f(cy_)[:, None], f(cz_)[:, None], f(mk)[:, None]
+    poses, ninl, imask = pnp_ransac_from_maps(CX, CY, CZ, M, f(c2d), torch.full((n,), imH), torch.full((n,), imW), f(ext),
+                                              torch.from_numpy(K.astype(np.float32))[None].repeat(n, 1, 1).to(dev), return_inliers=True)
+    poses = poses.cpu().numpy().astype(np.float64)
+    for i in range(n):
+        # host restatement of the reference recipe on the same float32 maps
+        m32 = np.stack(mk).astype(np.float32)[i]
+        mn = (m32 - m32.min()) / (m32.max() - m32.min())
+        e32 = ext[i].astype(np.float32)
+        xyz = np.stack([(np.float32(cx_[i]) - np.float32(0.5)) * e32[0], (np.float32(cy_[i]) - np.float32(0.5)) * e32[1],
+                        (np.float32(cz_[i]) - np.float32(0.5)) * e32[2]], -1).astype(np.float32)
+        sel = (mn > 0.5) & (np.abs(xyz[..., 0]) > 1e-4 * e32[0]) & (np.abs(xyz[..., 1]) > 1e-4 * e32[1]) & (np.abs(xyz[..., 2]) > 1e-4 * e32[2])
+        img = np.stack([np.float32(c2d[i][0]) * imW, np.float32(c2d[i][1]) * imH], -1)
+        if sel.sum() < 4:
+            assert (poses[i] == -100).all() and int(ninl[i]) == 0
+            continue
+        assert int(imask[i].sum()) <= int(sel.sum()) and not bool((imask[i].cpu().numpy().astype(bool) & ~sel).any())
+        ok, rvec, tvec, _ = cv2.solvePnPRansac(xyz[sel][None].astype(np.float64), img[sel][None].astype(np.float64), K, np.zeros((8, 1)),
+                                               flags=cv2.SOLVEPNP_EPNP, reprojectionError=3.0, iterationsCount=100)
+        Rc = cv2.Rodrigues(rvec)[0]
+        R, t = GT[i]
+        assert _rot_angle(poses[i, :, :3], R) < 0.02 and np.abs(poses[i, :, 3] - t).max() < 5e-3
+        assert _rot_angle(poses[i, :, :3], Rc) < 0.02 and np.abs(poses[i, :, 3] - tvec[:, 0]).max() < 5e-3
+
+
+def test_predictor_reference_constructor_and_use_pnp(dev, tmp_path):
+    """GdrnPredictor(config_file_path, ckpt_file_path, camera_json_path, path_to_obj_models) -- the reference's
+    constructor (predictor_gdrn.py:45-120): python config with _base_, checkpoint {"model": ...} with "_module."
+    prefixes, BOP camera.json, a directory of obj_{id:06d}.ply in millimetres; TEST.USE_PNP defaults to True like the
+    reference predictor and postprocessing returns {name: 4x4}."""
+    import json
+
+    from gdrnpp_bop2022_b200.ply import save_ply
+    from gdrnpp_bop2022_b200.predictor import GdrnPredictor
+    from gdrnpp_bop2022_b200.synthetic import make_icosphere_mesh, make_state_dict
+
+    nc = 3
+    (tmp_path / "cfg.py").write_text(
+        "MODEL = dict(PIXEL_MEAN=[0.0, 0.0, 0.0], PIXEL_STD=[255.0, 255.0, 255.0], POSE_NET=dict(NAME='GDRN_double_mask', NUM_CLASSES=%d,\n"
+        "    OUTPUT_RES=64, BACKBONE=dict(INIT_CFG=dict(type='timm/convnext_base')),\n"
+        "    GEO_HEAD=dict(NUM_REGIONS=64, XYZ_CLASS_AWARE=True, MASK_CLASS_AWARE=True, REGION_CLASS_AWARE=True, MASK_THR_TEST=0.5),\n"
+        "    PNP_NET=dict(ROT_TYPE='allo_rot6d', TRANS_TYPE='centroid_z', Z_TYPE='REL')))\n"
+        "TEST = dict(USE_PNP=False, USE_DEPTH_REFINE=False, DEPTH_REFINE_ITER=2, DEPTH_REFINE_THRESHOLD=0.8)\n"
+        "INPUT = dict(DZI_PAD_SCALE=1.5, WITH_DEPTH=False)\n" % nc)
+    sd = make_state_dict(num_classes=nc)
+    torch.save({"model": {"_module." + k: v for k, v in sd.items()}}, str(tmp_path / "model_final.pth"))
+    (tmp_path / "camera.json").write_text(json.dumps({"fx": 1066.778, "fy": 1067.487, "cx": 312.9869, "cy": 241.3109, "depth_scale": 0.1}))
+    mdir = tmp_path / "models"
+    mdir.mkdir()
+    for i, e in zip((1, 2, 5), ((120.0, 80.0, 100.0), (60.0, 60.0, 150.0), (90.0, 140.0, 70.0))):
+        v, f_ = make_icosphere_mesh(2, e)
+        save_ply(str(mdir / ("obj_%06d.ply" % i)), v, f_, binary=(i != 2))
+    pred = GdrnPredictor(str(tmp_path / "cfg.py"), str(tmp_path / "model_final.pth"), str(tmp_path / "camera.json"), str(mdir), device=dev)
+    assert pred.obj_ids == [1, 2, 5] and pred.cfg.TEST.USE_PNP is True and abs(pred.depth_scale - 0.1) < 1e-12
+    assert np.allclose(pred.extents[2], [0.06, 0.06, 0.15], atol=2e-3) and pred.ren_models is not None
+    assert abs(float(pred.cam[0, 0]) - 1066.778) < 1e-3
+    rng = np.random.RandomState(2)
+    image = rng.randint(0, 256, (480, 640, 3)).astype(np.uint8)
+    dets = np.array([[100, 80, 220, 260, 0.9, 0.8, 0], [400, 200, 460, 250, 0.7, 0.9, 2]], np.float32)
+    data = pred.preprocessing(dets, image)
+    out = pred.inference(data)
+    poses = pred.postprocessing(data, out)
+    assert set(poses.keys()) == {"obj_000001", "obj_000005"} and all(p.shape == (4, 4) for p in poses.values())
+    for r in data["cur_res"]:     # random-init maps carry no geometry: either a RANSAC pose or the -100 sentinel, never NaN
+        assert np.isfinite(r["R"]).all() and np.isfinite(r["t"]).all()
+    assert pred.postprocessing(pred.preprocessing(np.zeros((0, 7), np.float32), image), pred.inference(pred.preprocessing(np.zeros((0, 7), np.float32), image))) == {}

@@ -130,3 +130,61 @@ def test_all_gather_poses_gloo_world2(tmp_path, total):
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_state_dict_shapes_match_generated_weights():
+    """GDRN_DoubleMask builds its parameter tree from state_dict_shapes() (no 103 M random numbers per constructor);
+    the table must stay in lock-step with the generator the tests and the bench load."""
+    from gdrnpp_bop2022_b200.synthetic import make_state_dict, state_dict_shapes
+
+    for arch in ("convnext_base", "convnext_tiny"):
+        sh, sd = state_dict_shapes(arch), make_state_dict(arch)
+        assert list(sh.keys()) == list(sd.keys())
+        assert all(tuple(sd[k].shape) == tuple(sh[k]) for k in sh)
+
+
+def test_ply_roundtrip_and_reference_semantics(tmp_path):
+    """load_ply mirrors lib/pysixd/inout.py:489 (pts scaled by vertex_scale, triangular faces) for the ascii and the
+    binary_little_endian encodings BOP models ship in."""
+    from gdrnpp_bop2022_b200.ply import load_ply, save_ply
+    from gdrnpp_bop2022_b200.synthetic import make_icosphere_mesh
+
+    v, f = make_icosphere_mesh(2, (120.0, 80.0, 100.0))   # millimetres, like BOP models
+    for binary in (True, False):
+        p = str(tmp_path / ("m_%d.ply" % binary))
+        save_ply(p, v, f, binary=binary)
+        m = load_ply(p, vertex_scale=0.001)
+        assert m["pts"].shape == v.shape and m["faces"].shape == f.shape
+        assert np.allclose(m["pts"], v.astype(np.float64) * 0.001, atol=1e-9 if binary else 1e-6)
+        assert np.array_equal(m["faces"], f)
+    # extra vertex properties (normals, colours) and a header comment, ascii
+    p = str(tmp_path / "n.ply")
+    with open(p, "w") as fh:
+        fh.write("ply\nformat ascii 1.0\ncomment made by hand\nelement vertex 3\nproperty float x\nproperty float y\nproperty float z\n"
+                 "property float nx\nproperty float ny\nproperty float nz\nproperty uchar red\nproperty uchar green\nproperty uchar blue\n"
+                 "element face 1\nproperty list uchar int vertex_indices\nend_header\n"
+                 "0 0 0 0 0 1 255 0 0\n1 0 0 0 0 1 0 255 0\n0 1 0 0 0 1 0 0 255\n3 0 1 2\n")
+    m = load_ply(p)
+    assert m["pts"].shape == (3, 3) and m["normals"][0, 2] == 1 and m["colors"][1, 1] == 255 and m["faces"].tolist() == [[0, 1, 2]]
+
+
+def test_reference_style_config_loader(tmp_path):
+    """load_py_config: module-level dicts + `_base_` inheritance with key-wise merge, like mmcv.Config.fromfile."""
+    from gdrnpp_bop2022_b200.gdrn_model import GDRN_DoubleMask, load_py_config
+
+    (tmp_path / "base.py").write_text(
+        "MODEL = dict(PIXEL_STD=[255.0, 255.0, 255.0], POSE_NET=dict(NAME='GDRN_double_mask', NUM_CLASSES=13, OUTPUT_RES=64,\n"
+        "    BACKBONE=dict(INIT_CFG=dict(type='timm/resnet34')),\n"
+        "    GEO_HEAD=dict(NUM_REGIONS=64, XYZ_CLASS_AWARE=False, MASK_CLASS_AWARE=False, REGION_CLASS_AWARE=False, MASK_THR_TEST=0.5),\n"
+        "    PNP_NET=dict(ROT_TYPE='allo_rot6d', TRANS_TYPE='centroid_z', Z_TYPE='REL')))\n"
+        "TEST = dict(USE_PNP=False, USE_DEPTH_REFINE=False, DEPTH_REFINE_ITER=2)\nINPUT = dict(DZI_PAD_SCALE=1.5)\n")
+    (tmp_path / "ycbv.py").write_text(
+        "_base_ = ['base.py']\n"
+        "MODEL = dict(POSE_NET=dict(NUM_CLASSES=21, BACKBONE=dict(INIT_CFG=dict(type='timm/convnext_base')),\n"
+        "    GEO_HEAD=dict(XYZ_CLASS_AWARE=True, MASK_CLASS_AWARE=True, REGION_CLASS_AWARE=True)))\n")
+    cfg = load_py_config(str(tmp_path / "ycbv.py"))
+    pn = cfg.MODEL.POSE_NET
+    assert pn.NUM_CLASSES == 21 and pn.BACKBONE.INIT_CFG.type == "timm/convnext_base" and pn.GEO_HEAD.NUM_REGIONS == 64
+    assert pn.GEO_HEAD.XYZ_CLASS_AWARE is True and cfg.TEST.DEPTH_REFINE_ITER == 2 and cfg.MODEL.PIXEL_STD[0] == 255.0
+    m = GDRN_DoubleMask(cfg)          # the loaded config drives the model surface like the reference's mmcv Config
+    assert m.num_classes == 21 and m.precision == "bf16x3"

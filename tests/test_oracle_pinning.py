@@ -84,6 +84,31 @@ def test_backbone_oracle_param_count_and_fp64_agreement():
     assert sum(v.numel() for k, v in sdb.items() if k.startswith("backbone.")) == 87564416
 
 
+@pytest.mark.parametrize("arch,res", [("convnext_tiny", 96), ("convnext_base", 64)])
+def test_backbone_oracle_pinned_to_torchvision(arch, res):
+    """Pins the ConvNeXt restatement: timm 0.6.7 (the reference's un-vendored dependency, core/utils/timm_utils.py:9-35)
+    cannot be installed here, but torchvision ships an independent implementation of the same published network.
+    With the timm-named weights remapped (oracle.torchvision_convnext) the two must agree BIT FOR BIT on the stage-3
+    feature map (features_only, out_indices=(3,): no final norm), and convnext_base must have timm's 87,564,416
+    backbone parameters."""
+    pytest.importorskip("torchvision")
+    from gdrnpp_bop2022_b200.synthetic import make_state_dict
+
+    sd = make_state_dict(arch)
+    net = O.torchvision_convnext(sd, arch)
+    x = torch.rand(2, 3, res, res, generator=torch.Generator().manual_seed(res))
+    with torch.no_grad():
+        tv = net(x)
+        mine = O.convnext_features(sd, x, arch)
+    assert tv.shape == mine.shape == (2, O.CONVNEXT_ARCH[arch][1][3], res // 32, res // 32)
+    assert torch.equal(tv, mine), float((tv - mine).abs().max())
+    n_params = sum(p.numel() for p in net.parameters())
+    n_sd = sum(v.numel() for k, v in sd.items() if k.startswith("backbone."))
+    assert n_params == n_sd
+    if arch == "convnext_base":
+        assert n_params == 87_564_416
+
+
 def test_gelu_epilogue_fit_accuracy():
     hdr = open(os.path.join(ROOT, "gdrnpp_bop2022_b200", "csrc", "gelu_coeffs.h")).read()
     c = [float(l.split()[2].rstrip("f")) for l in hdr.splitlines() if l.startswith("#define GELU_C") and "CLAMP" not in l]
