@@ -328,7 +328,7 @@ def bench_config4(dev, T, peaks, precision="bf16x3"):
     return [{"op": "configs[4]: per-image pose path, 5 ROIs per image (preprocessing + inference + postprocessing)",
              "shape": {"rois_per_image": 5, "image": "480x640"}, "precision": precision, "ms": dt * 1e3,
              "images_per_s": 1.0 / dt, "rois_per_s": 5.0 / dt,
-             "note": "host-loop bound (eager launches of a B=5 forward, ~160 kernels); no CUDA graph on this path"}]
+             "note": "static per-batch-size input buffers + one CUDA graph per batch size (GdrnPredictor.use_cuda_graph); timed like gdrn_evaluator.py:707-751"}]
 
 
 WORKLOADS = {"fps": bench_fps, "voting": bench_voting, "nnd": bench_nnd, "flow": bench_flow, "raster": bench_raster,

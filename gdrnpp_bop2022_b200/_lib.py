@@ -46,6 +46,7 @@ _SIGNATURES = {
     ),
     "gdrn_model_debug_read": (c_int64, [c_void_p, c_char_p, c_int, c_void_p, c_void_p, c_void_p]),
     "gdrn_gemm_bf16": (c_int, [c_void_p] * 6 + [c_int] * 6 + [c_void_p]),
+    "gdrn_dwconv_ln": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_float, c_int, c_int, c_void_p]),
     "gdrn_gemm_x3": (c_int, [c_void_p] * 6 + [c_int] * 5 + [c_void_p]),
     "farthest_point_sampling": (None, [c_void_p, c_void_p, c_int, c_int]),
     "farthest_point_sampling_init_center": (None, [c_void_p, c_void_p, c_int, c_int]),
@@ -56,6 +57,9 @@ _SIGNATURES = {
     "rv_generate_hypothesis_vanishing_point": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_void_p]),
     "rv_voting_for_hypothesis_vanishing_point": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_float, c_void_p]),
     "rv_vote_count": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_float, c_int, c_void_p]),
+    "rv_layer_workspace_bytes": (c_size_t, [c_int] * 5),
+    "rv_ransac_voting_layer": (c_int, [c_void_p, c_void_p] + [c_int] * 5 + [c_float, c_int, c_int, c_uint] + [c_void_p] * 7
+                               + [c_size_t, c_void_p]),
     "nnd_forward_cuda": (c_int, [c_void_p] * 6 + [c_int] * 3 + [c_void_p]),
     "nnd_backward_cuda": (c_int, [c_void_p] * 8 + [c_int] * 3 + [c_void_p]),
     "flow_forward_cuda": (c_int, [c_void_p] * 6 + [c_int] * 3 + [c_void_p]),
@@ -68,6 +72,11 @@ _SIGNATURES = {
     ),
     "rast_scratch_bytes": (c_size_t, [c_int, c_int, c_int]),
     "gdrn_depth_refine_step": (c_int, [c_void_p] * 6 + [c_int, c_int, c_float, c_void_p]),
+    "gdrn_depth_refine_step_ex": (c_int, [c_void_p, c_void_p, c_int] + [c_void_p] * 4 + [c_int, c_int, c_float, c_void_p]),
+    "rast_upload_mesh": (c_int, [c_void_p, c_int, c_void_p, c_int]),
+    "rast_mesh_count": (c_int, []),
+    "rast_free_meshes": (None, []),
+    "rast_render_meshes": (c_int, [c_void_p] * 3 + [c_int] * 3 + [c_float, c_float, c_int] + [c_void_p] * 4),
     "gdrn_pnp_ransac_maps": (c_int, [c_void_p] * 9 + [c_int] * 3 + [c_float, c_float, c_uint] + [c_void_p] * 4),
     "gdrn_pnp_ransac_points": (c_int, [c_void_p] * 4 + [c_int] * 3 + [c_float, c_uint] + [c_void_p] * 4),
     "gdrn_crop_resize_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include "common.cuh"
+#include "dense_ops.h"
 #include "gemm_tc.h"
 
 static thread_local char g_last_error[512] = "";
@@ -108,11 +109,37 @@ extern "C" int gdrn_gemm_x3(const void* A, const void* W, const float* bias, con
   p.epi = epi;
   p.out_f32 = epi == 1 ? 0 : 1;
   p.gelu_mode = 3;
+  if (const char* e = getenv("GDRN_X3_GELU_MODE")) p.gelu_mode = atoi(e);   // 4 = libm erff (A/B experiments)
   p.split = 1; p.x3_a_lo = K; p.x3_b_lo = K;
   p.out = out;
   p.ldo = epi == 1 ? 2LL * N : N;
   p.bias = bias;
   p.gamma = gamma;
   p.resid = resid;
+  static int trace_on = -1;
+  if (trace_on < 0) trace_on = getenv("GDRN_GEMM_TRACE") ? 1 : 0;
+  if (trace_on) {
+    static long long* d_trace = nullptr;
+    if (!d_trace) GDRN_CHECK_CUDA(cudaMalloc(&d_trace, 16 * sizeof(long long)));
+    GDRN_CHECK_CUDA(cudaMemsetAsync(d_trace, 0, 16 * sizeof(long long), (cudaStream_t)stream));
+    p.trace = d_trace;
+    rc = gemm_tc_launch(p, block_n, (cudaStream_t)stream);
+    if (rc != GDRN_OK) return rc;
+    long long h[16];
+    GDRN_CHECK_CUDA(cudaMemcpyAsync(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    GDRN_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    fprintf(stderr, "[gemm x3 trace] M=%d N=%d K=%d epi=%d bn=%d: pair0 cycles=%lld tiles=%lld | producer empty-wait=%lld | "
+                    "mma full-wait=%lld acc-wait=%lld | epi0 acc-wait=%lld busy=%lld (tmem-ld=%lld compute=%lld wait+sts+store=%lld)\n",
+            M, N, K, epi, block_n, h[6], h[7], h[0], h[1], h[2], h[3], h[4], h[8], h[9], h[10]);
+    return GDRN_OK;
+  }
   return gemm_tc_launch(p, block_n, (cudaStream_t)stream);
+}
+
+extern "C" int gdrn_dwconv_ln(const float* x, const float* w49c, const float* bias, const float* ln_w, const float* ln_b,
+                              void* out, int B, int H, int W, int C, float eps, int split, int variant, void* stream) {
+  GDRN_REQUIRE(x && w49c && bias && ln_w && ln_b && out, "dwconv_ln: null argument");
+  GDRN_REQUIRE(variant >= -1 && variant <= 1, "dwconv_ln: variant must be -1 (default), 0 (per-tile cluster kernel) or 1 (ping-pong)");
+  return launch_dwconv_ln_variant(x, w49c, bias, ln_w, ln_b, reinterpret_cast<__nv_bfloat16*>(out), B, H, W, C, eps, split, variant,
+                                  (cudaStream_t)stream);
 }

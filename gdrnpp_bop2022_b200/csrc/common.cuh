@@ -326,8 +326,28 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
 
 }  // namespace ptx
 
-// exact-erf GELU (torch nn.GELU() default), used by the light elementwise kernels
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// exact-erf GELU (torch nn.GELU() default), x * Phi(x), BRANCH-FREE and short:
+//   Phi(x) = 1 - h (x >= 0) | h (x < 0),   h = 0.5 * erfc(|x| / sqrt 2)
+//   erfc(z) = (a1 t + a2 t^2 + a3 t^3 + a4 t^4 + a5 t^5) * exp(-z^2),  t = 1 / (1 + p z)     (Abramowitz & Stegun 7.1.26,
+//   |error| <= 1.5e-7), evaluated with one rcp.approx and one ex2.approx (MUFU pipe, otherwise idle in the epilogues) and
+//   12 FMA-pipe instructions.  Max abs error of the GELU against the fp64 erf form over [-12, 12]: 4.2e-7
+//   (tools/check_erf.py; torch's own fp32 GELU: 1.2e-6), and no cancellation for x < 0 (h is used directly).
+// CUDA's erff() costs ~25 FMA-pipe instructions and takes a data-dependent branch; the fc1 epilogue of the split-bf16
+// mode is FMA-pipe / issue bound (GDRN_GEMM_TRACE: ~30 instructions per element), so the instruction count is what matters.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  p *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * (z * -1.4426950408889634f)));
+  const float h = p * e;
+  return x * (x >= 0.0f ? 1.0f - h : h);
+}
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);

@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "dense_ops.h"
+#include "dw_helpers.cuh"
 #include "gemm_tc.h"
 
 namespace cg = cooperative_groups;
@@ -218,45 +219,6 @@ dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ w49c, co
 //   cluster = the C/CPC CTAs (2/4/8) that together hold all channels of the tile: the LayerNorm statistics are
 //          combined across them through distributed shared memory with ONE cluster barrier (see below).
 // In-warp per-pixel channel sums use a transposing shuffle reduction.
-typedef unsigned long long f32x2_t;
-__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) {
-  f32x2_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ float2 f2_unpack(f32x2_t v) {
-  float2 r;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
-  return r;
-}
-__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
-  f32x2_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-
-// sum over the 32 lanes of N per-lane values, N in {32,16,8}: lane L ends up with element (L * N) >> 5
-template <int N>
-__device__ __forceinline__ float lane_transpose_reduce(float (&a)[N], int lane) {
-  static_assert(N == 32 || N == 16 || N == 8, "N");
-  constexpr int STEPS = (N == 32) ? 5 : (N == 16 ? 4 : 3);
-#pragma unroll
-  for (int st = 0; st < STEPS; ++st) {
-    const int o = 16 >> st;        // lane bit
-    const int n = (N / 2) >> st;   // values kept after this step
-    const bool up = (lane & o) != 0;
-#pragma unroll
-    for (int j = 0; j < n; ++j) {
-      const float send = up ? a[j] : a[j + n];
-      const float keep = up ? a[j + n] : a[j];
-      a[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-    }
-  }
-#pragma unroll
-  for (int o = (16 >> STEPS); o > 0; o >>= 1) a[0] += __shfl_xor_sync(0xffffffffu, a[0], o);
-  return a[0];
-}
-
 // Depthwise 7x7 + bias + LayerNorm(C) -> bf16 GEMM operand.  One CTA = (TW x TH pixel tile) x CPC channels of one
 // image; the CTAs of a cluster hold the C / CPC channel slices of the same tile.  A thread owns one channel PAIR
 // (packed fma.rn.f32x2) and R consecutive output rows x TW pixels.  It walks the R + 6 input rows once: each row is
@@ -883,6 +845,13 @@ static int launch_dwconv_cluster(const float* x, const float* w49c, const float*
 
 int launch_dwconv_ln(const float* x, const float* w49c, const float* bias, const float* ln_w, const float* ln_b,
                      __nv_bfloat16* out, int B, int H, int W, int C, float eps, int split, cudaStream_t st) {
+  return launch_dwconv_ln_variant(x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps, split, -1, st);
+}
+
+// variant: -1 = default choice (env GDRN_DW_PP), 0 = one-tile-per-CTA cluster kernel, 1 = persistent ping-pong kernel
+int launch_dwconv_ln_variant(const float* x, const float* w49c, const float* bias, const float* ln_w, const float* ln_b,
+                             __nv_bfloat16* out, int B, int H, int W, int C, float eps, int split, int variant,
+                             cudaStream_t st) {
   GDRN_REQUIRE(C % 128 == 0 && C <= 1024, "dwconv: C must be a multiple of 128 and <= 1024");
   // cluster kernel: 16x8 tiles x 64 channels (cluster C/64 <= 8) or 8x8 tiles x 128 channels (cluster C/128 <= 8)
   static int rows = -1;  // GDRN_DW_ROWS=2: two output rows per thread (half the LDS traffic, half the warps: measured 4 % slower)
@@ -890,6 +859,14 @@ int launch_dwconv_ln(const float* x, const float* w49c, const float* bias, const
   static int var = -1;   // GDRN_DW_VARIANT: tile-shape experiments
   if (var < 0) { const char* e = getenv("GDRN_DW_VARIANT"); var = e ? atoi(e) : 0; }
 #define DW_ARGS x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps, split, st
+  static int pp = -1;    // GDRN_DW_PP=0: one-tile-per-CTA kernel instead of the persistent ping-pong kernel (A/B experiments)
+  if (pp < 0) { const char* e = getenv("GDRN_DW_PP"); pp = e ? atoi(e) : 1; }
+  const bool want_pp = variant == 1 || (variant < 0 && pp && var == 0 && rows == 1 && (long long)B * (H / 8) * (W / 16) >= 32);
+  if (want_pp) {
+    const int rc = launch_dwconv_ln_pp(DW_ARGS);
+    if (rc != 1) return rc;
+    GDRN_REQUIRE(variant != 1, "dwconv: shape not handled by the ping-pong kernel");
+  }
   if (H % 8 == 0 && W % 16 == 0 && C / 64 <= 8) {
     if (var == 1) return launch_dwconv_cluster<16, 4, 64, 1, 3>(DW_ARGS);   // 73 KB: 3 CTAs / SM, 128 threads
     if (var == 2) return launch_dwconv_cluster<8, 8, 64, 1, 3>(DW_ARGS);    // 67 KB: 3 CTAs / SM, 256 threads

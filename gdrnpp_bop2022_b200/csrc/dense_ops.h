@@ -21,6 +21,12 @@ int launch_stem_patchify(const float* img, __nv_bfloat16* out, int B, int H, int
 // x: fp32 NHWC; w: [49][C] (tap-major, repacked); all fp32.
 int launch_dwconv_ln(const float* x, const float* w49c, const float* bias, const float* ln_w, const float* ln_b,
                      __nv_bfloat16* out, int B, int H, int W, int C, float eps, int split, cudaStream_t st);
+int launch_dwconv_ln_variant(const float* x, const float* w49c, const float* bias, const float* ln_w, const float* ln_b,
+                             __nv_bfloat16* out, int B, int H, int W, int C, float eps, int split, int variant,
+                             cudaStream_t st);
+// persistent two-warpgroup ping-pong version (dwconv_pp.cu) for 16x8x64 tiles; returns 1 if the shape is not handled
+int launch_dwconv_ln_pp(const float* x, const float* w49c, const float* bias, const float* ln_w, const float* ln_b,
+                        __nv_bfloat16* out, int B, int H, int W, int C, float eps, int split, cudaStream_t st);
 
 // downsample front half: per-pixel LayerNorm over C then 2x2/s2 patchify -> bf16 [B*(H/2)*(W/2), 4*C]
 // (k = (ky*2+kx)*C + c)

@@ -1,0 +1,293 @@
+// Depthwise 7x7 + bias + LayerNorm(C) -> GEMM A operand: PERSISTENT, two-warpgroup ping-pong version for the
+// 16x8-pixel x 64-channel tiles of ConvNeXt stages 0-2 (33 of the 36 blocks).  Reference op: timm ConvNeXtBlock
+// conv_dw (7x7, groups = C) -> LayerNorm(C, eps 1e-6) (third-party timm 0.6.7; restated in oracle/gdrn_model_oracle.py).
+//
+// Why: the one-tile-per-CTA kernel (dense_ops.cu, dwconv_ln_cluster_kernel) spends only ~40 % of a CTA's life in the
+// convolution (FMA pipe); TMA load wait, the LayerNorm exchange across the channel-slice cluster and the output stores do
+// not overlap it, and the two CTAs resident on an SM run those phases in lock-step (profiles/r01_dwconv_experiments.md:
+// 41 % FMA-pipe active, 0.99 TB/s).  Here one CTA per SM stays resident and loops over pixel tiles with TWO warpgroups
+// (2 x 8 warps) in ping-pong, each with its own shared-memory halo slot:
+//     WG0:  conv(t0) | LN/exchange/store(t0) + TMA(t2) | conv(t2) | ...
+//     WG1:           | conv(t1)                        | LN/exchange/store(t1) + TMA(t3) | conv(t3) ...
+// A pair of named barriers hands the FMA pipe from one warpgroup to the other, so the convolutions never overlap each
+// other but everything else (load wait, LN shuffles, DSMEM pushes, stores) runs underneath the other warpgroup's
+// convolution.  The 49 x 64 filter taps of the CTA's channel slice are loaded once per launch.
+//
+// Cluster = the C/64 CTAs holding the channel slices of the same pixel-tile sequence (as before): per tile every warp
+// pushes its 64-channel (sum, M2) partials into all peers with st.async + mbarrier complete_tx (data and signal travel
+// together), double-buffered per warpgroup so that a fast peer can never overwrite partials that are still being read.
+#include <cooperative_groups.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "dense_ops.h"
+#include "dw_helpers.cuh"
+#include "gemm_tc.h"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+constexpr int PP_TW = 16, PP_TH = 8, PP_CPC = 64;
+constexpr int PP_IW = PP_TW + 6, PP_IH = PP_TH + 6;
+constexpr int PP_NPIX = PP_TW * PP_TH;                      // 128
+constexpr int PP_WG_THREADS = (PP_CPC / 2) * PP_TH;         // 256: lane = channel pair, warp = output row
+constexpr int PP_SLOT_FLOATS = PP_IH * PP_IW * PP_CPC;      // 19 712 floats = 78 848 B
+constexpr int PP_MAX_RANKS = 8;
+constexpr size_t PP_SMEM = (size_t)(2 * PP_SLOT_FLOATS + 49 * PP_CPC) * 4 + (size_t)2 * 2 * PP_MAX_RANKS * PP_NPIX * 8 + 128;
+
+__global__ void __launch_bounds__(2 * PP_WG_THREADS, 1)
+dwconv_ln_pp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                    const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                    __nv_bfloat16* __restrict__ out, int B, int H, int W, int C, float eps, int split, int use_token,
+                    long long* trace) {
+  constexpr int TW = PP_TW, TH = PP_TH, CPC = PP_CPC, IW = PP_IW, NPIX = PP_NPIX;
+  constexpr int NV = TW;              // pixels per thread (one output row)
+  constexpr int LPP = 32 / NV;        // lanes per pixel after the transposing reduction (2)
+  extern __shared__ __align__(1024) float smem_pp[];
+  float* slot0 = smem_pp;                                        // [2][IH][IW][CPC] halo tiles (TMA destinations)
+  float* wsm = smem_pp + 2 * PP_SLOT_FLOATS;                     // [49][CPC]
+  float2* parts = reinterpret_cast<float2*>(wsm + 49 * CPC);     // [2 wg][2 buf][MAX_RANKS][NPIX]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(parts + 2 * 2 * PP_MAX_RANKS * NPIX);
+  // bars: [0] weights, [1..2] tile loaded (per wg), [3..6] partials (wg * 2 + buf)
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int nrank = (int)cluster.num_blocks();
+  const int rank = (int)cluster.block_rank();
+  const int cluster_id = blockIdx.x / nrank, nclusters = gridDim.x / nrank;
+  const int c0 = rank * CPC;
+  const int tiles_x = W / TW, tiles_y = H / TH;
+  const int n_tiles = B * tiles_x * tiles_y;
+  const int n_my = cluster_id < n_tiles ? (n_tiles - cluster_id + nclusters - 1) / nclusters : 0;
+  const int wg = threadIdx.x >> 8;
+  const int tidw = threadIdx.x & 255, lane = tidw & 31;
+  const int row0 = tidw >> 5;          // output row of this warp
+  const int cl = 2 * lane;             // first channel of the pair (CTA-local)
+  const int n_w = (n_my - wg + 1) >> 1;                    // tiles of this warpgroup: k = wg, wg + 2, ...
+  const int n_other = (n_my - (wg ^ 1) + 1) >> 1;
+  float* tile = slot0 + wg * PP_SLOT_FLOATS;
+
+  const uint32_t bar_w = ptx::smem_u32(bars);
+  const uint32_t bar_tile = ptx::smem_u32(bars + 1 + wg);
+  auto bar_parts = [&](int buf) { return ptx::smem_u32(bars + 3 + wg * 2 + buf); };
+  const uint32_t parts_bytes = (uint32_t)(nrank * NPIX * sizeof(float2));
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 7; ++i) ptx::mbar_init(ptx::smem_u32(bars + i), 1);
+    ptx::fence_barrier_init();
+    // every (rank, pixel) partial of the cluster lands as one 8-byte st.async on the barrier of its (wg, buffer)
+    for (int i = 3; i < 7; ++i) ptx::mbar_arrive_expect_tx(ptx::smem_u32(bars + i), parts_bytes);
+  }
+  __syncthreads();
+  auto tile_coords = [&](int k, int& b, int& y0, int& x0) {
+    const int t = cluster_id + k * nclusters;
+    x0 = (t % tiles_x) * TW;
+    y0 = ((t / tiles_x) % tiles_y) * TH;
+    b = t / (tiles_x * tiles_y);
+  };
+  if (threadIdx.x == 0) {
+    ptx::mbar_arrive_expect_tx(bar_w, (uint32_t)(49 * CPC * sizeof(float)));
+    ptx::tma_load_2d(ptx::smem_u32(wsm), &tmap_w, bar_w, c0, 0);          // this CTA's 49 x 64 filter taps, once
+  }
+  if (tidw == 0 && n_w > 0) {
+    int b, y0, x0;
+    tile_coords(wg, b, y0, x0);
+    ptx::mbar_arrive_expect_tx(bar_tile, (uint32_t)(PP_SLOT_FLOATS * sizeof(float)));
+    ptx::tma_load_4d(ptx::smem_u32(tile), &tmap_x, bar_tile, c0, x0 - 3, y0 - 3, b);
+  }
+  cluster.sync();     // every peer's barriers exist and are armed before the first push (once per launch)
+  const f32x2_t bv = f2_pack(__ldg(bias + c0 + cl), __ldg(bias + c0 + cl + 1));
+  const float gw0 = __ldg(ln_w + c0 + cl), gw1 = __ldg(ln_w + c0 + cl + 1);
+  const float gb0 = __ldg(ln_b + c0 + cl), gb1 = __ldg(ln_b + c0 + cl + 1);
+  const int ldc = split ? 2 * C : C;
+  ptx::mbar_wait(bar_w, 0);
+
+  // GDRN_DW_TRACE: phase cycle counts of warpgroup 0 / thread 0 of one mid-grid CTA, summed over its tiles
+  const bool trc = trace != nullptr && blockIdx.x == (gridDim.x / 2) && threadIdx.x == 0;
+  long long tt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tq = trc ? clock64() : 0;
+#define PP_MARK(slot) do { if (trc) { const long long t_ = clock64(); tt[slot] += t_ - tq; tq = t_; } } while (0)
+  for (int i = 0; i < n_w; ++i) {
+    const int k = wg + 2 * i;
+    int b, y0, x0;
+    tile_coords(k, b, y0, x0);
+    ptx::mbar_wait(bar_tile, (uint32_t)(i & 1));          // halo tile landed
+    PP_MARK(0);
+    // ---- FMA-pipe hand-over: the convolutions of the two warpgroups alternate ----
+    if (use_token) {
+      if (wg == 0) { if (i > 0) named_bar_sync(2, 2 * PP_WG_THREADS); }
+      else named_bar_sync(1, 2 * PP_WG_THREADS);
+    }
+    PP_MARK(1);
+    f32x2_t acc[TW];
+#pragma unroll
+    for (int ox = 0; ox < TW; ++ox) acc[ox] = bv;
+#pragma unroll
+    for (int ky = 0; ky < 7; ++ky) {
+      f32x2_t v[IW], wk[7];
+      const float* rowp = tile + ((row0 + ky) * IW) * CPC + cl;
+#pragma unroll
+      for (int j = 0; j < IW; ++j) v[j] = *reinterpret_cast<const f32x2_t*>(rowp + j * CPC);
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) wk[kx] = *reinterpret_cast<const f32x2_t*>(wsm + (ky * 7 + kx) * CPC + cl);
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx)
+#pragma unroll
+        for (int ox = 0; ox < TW; ++ox) acc[ox] = f2_fma(v[ox + kx], wk[kx], acc[ox]);
+    }
+    PP_MARK(2);
+    if (use_token) {
+      if (wg == 0) { if (i < n_other) named_bar_arrive(1, 2 * PP_WG_THREADS); }
+      else { if (i + 1 < n_other) named_bar_arrive(2, 2 * PP_WG_THREADS); }
+    }
+    // the whole warpgroup has finished reading its halo slot: prefetch the next tile into it
+    named_bar_sync(3 + wg, PP_WG_THREADS);
+    if (tidw == 0 && i + 1 < n_w) {
+      int nb, ny0, nx0;
+      tile_coords(k + 2, nb, ny0, nx0);
+      ptx::mbar_arrive_expect_tx(bar_tile, (uint32_t)(PP_SLOT_FLOATS * sizeof(float)));
+      ptx::tma_load_4d(ptx::smem_u32(tile), &tmap_x, bar_tile, c0, nx0 - 3, ny0 - 3, nb);
+    }
+    PP_MARK(3);
+    // ---- LayerNorm statistics of this warp's 64 channels (shuffles only) ----
+    float ax[NV], ay[NV];
+#pragma unroll
+    for (int ox = 0; ox < TW; ++ox) { const float2 t = f2_unpack(acc[ox]); ax[ox] = t.x; ay[ox] = t.y; }
+    constexpr float INV_W = 1.0f / 64.0f;
+    const int pix = row0 * TW + lane / LPP;
+    float s_loc, m2_loc;
+    {
+      float a[NV];
+#pragma unroll
+      for (int q = 0; q < NV; ++q) a[q] = ax[q] + ay[q];
+      s_loc = lane_transpose_reduce<NV>(a, lane);
+#pragma unroll
+      for (int q = 0; q < NV; ++q) {
+        const float m = __shfl_sync(0xffffffffu, s_loc, q * LPP) * INV_W;
+        const float dx = ax[q] - m, dy = ay[q] - m;
+        a[q] = fmaf(dx, dx, dy * dy);
+      }
+      m2_loc = lane_transpose_reduce<NV>(a, lane);
+    }
+    PP_MARK(4);
+    const int buf = i & 1;
+    float2* my_parts = parts + (size_t)(wg * 2 + buf) * PP_MAX_RANKS * NPIX;
+    if ((lane % LPP) == 0) {
+      const uint32_t la = ptx::smem_u32(my_parts + rank * NPIX + pix);
+      const uint32_t lb = bar_parts(buf);
+      for (int rk = 0; rk < nrank; ++rk) ptx::st_async_f32x2(ptx::mapa_shared(la, rk), s_loc, m2_loc, ptx::mapa_shared(lb, rk));
+    }
+    ptx::mbar_wait_cluster(bar_parts(buf), (uint32_t)((i >> 1) & 1));
+    PP_MARK(5);
+    float mean_p, rstd_p;
+    {
+      float tot = 0.f;
+      for (int r = 0; r < nrank; ++r) tot += my_parts[r * NPIX + pix].x;
+      mean_p = tot / (float)C;
+      float m2 = 0.f;
+      for (int r = 0; r < nrank; ++r) {
+        const float2 v = my_parts[r * NPIX + pix];
+        const float d = v.x * INV_W - mean_p;
+        m2 += fmaf(64.0f * d, d, v.y);
+      }
+      rstd_p = rsqrtf(m2 / (float)C + eps);
+    }
+    // re-arm this (wg, buffer) barrier for its next use (tile i + 2): strictly before this CTA's own push of tile i + 1,
+    // which is what a peer needs before it can push tile i + 2 (see the banner)
+    named_bar_sync(3 + wg, PP_WG_THREADS);     // all reads of my_parts done
+    if (tidw == 0 && i + 2 < n_w) ptx::mbar_arrive_expect_tx(bar_parts(buf), parts_bytes);
+    // ---- normalise + affine, bf16x2 out (a warp writes 128 contiguous bytes per pixel) ----
+    __nv_bfloat16* orow = out + (((long long)b * H + (y0 + row0)) * W + x0) * ldc + c0 + cl;
+#pragma unroll
+    for (int ox = 0; ox < TW; ++ox) {
+      const float m = __shfl_sync(0xffffffffu, mean_p, ox * LPP);
+      const float rs = __shfl_sync(0xffffffffu, rstd_p, ox * LPP);
+      const float o0 = fmaf((ax[ox] - m) * rs, gw0, gb0), o1 = fmaf((ay[ox] - m) * rs, gw1, gb1);
+      const __nv_bfloat162 o = __floats2bfloat162_rn(o0, o1);
+      *reinterpret_cast<__nv_bfloat162*>(orow + (long long)ox * ldc) = o;
+      if (split) {
+        const float2 of = __bfloat1622float2(o);
+        *reinterpret_cast<__nv_bfloat162*>(orow + (long long)ox * ldc + C) = __floats2bfloat162_rn(o0 - of.x, o1 - of.y);
+      }
+    }
+    PP_MARK(6);
+  }
+#undef PP_MARK
+  if (trc) { for (int q = 0; q < 7; ++q) trace[q] = tt[q]; trace[7] = n_w; }
+}
+
+}  // namespace
+
+// returns GDRN_OK when launched, 1 when the shape is not handled by this kernel (caller falls back)
+int launch_dwconv_ln_pp(const float* x, const float* w49c, const float* bias, const float* ln_w, const float* ln_b,
+                        __nv_bfloat16* out, int B, int H, int W, int C, float eps, int split, cudaStream_t st) {
+  if (!(H % PP_TH == 0 && W % PP_TW == 0 && C % PP_CPC == 0 && C / PP_CPC <= PP_MAX_RANKS && C / PP_CPC >= 1)) return 1;
+  const int csize = C / PP_CPC;
+  auto kfn = dwconv_ln_pp_kernel;
+  GDRN_OPT_IN_SMEM(kfn, PP_SMEM);
+  CUtensorMap tmap, tmap_w;
+  {
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)C * 4, (uint64_t)W * C * 4, (uint64_t)H * W * C * 4};
+    const uint32_t box[4] = {(uint32_t)PP_CPC, (uint32_t)PP_IW, (uint32_t)PP_IH, 1};
+    int rc = make_tmap_f32_plain(&tmap, x, 4, dims, str, box);
+    if (rc != GDRN_OK) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)C, 49};
+    const uint64_t str[1] = {(uint64_t)C * 4};
+    const uint32_t box[2] = {(uint32_t)PP_CPC, 49};
+    int rc = make_tmap_f32_plain(&tmap_w, w49c, 2, dims, str, box);
+    if (rc != GDRN_OK) return rc;
+  }
+  const int n_tiles = B * (H / PP_TH) * (W / PP_TW);
+  // how many clusters of `csize` one-CTA-per-SM blocks the device can hold at once (GPC-granular), per (device, csize)
+  static int max_clusters[GDRN_MAX_DEVICES][PP_MAX_RANKS + 1] = {};
+  const int dev = gdrn_cur_device();
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(2 * PP_WG_THREADS);
+  cfg.dynamicSmemBytes = PP_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (max_clusters[dev][csize] == 0) {
+    int n = 0;
+    cfg.gridDim = dim3(gdrn_num_sms() / csize * csize);
+    if (cudaOccupancyMaxActiveClusters(&n, kfn, &cfg) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = gdrn_num_sms() / csize / 2; }
+    if (n < 1) n = 1;
+    max_clusters[dev][csize] = n;
+  }
+  int nclusters = max_clusters[dev][csize];
+  if (nclusters > n_tiles) nclusters = n_tiles;
+  cfg.gridDim = dim3(nclusters * csize);
+  static int trace_on = -1;  // GDRN_DW_TRACE=1: phase cycle counts of one mid-grid CTA on stderr (synchronises)
+  if (trace_on < 0) trace_on = getenv("GDRN_DW_TRACE") ? 1 : 0;
+  static long long* d_trace = nullptr;
+  if (trace_on && !d_trace) GDRN_CHECK_CUDA(cudaMalloc(&d_trace, 8 * sizeof(long long)));
+  long long* trp = trace_on ? d_trace : nullptr;
+  static int token = -1;     // GDRN_DW_TOKEN=0: no hand-over of the FMA pipe between the warpgroups (measured 3-4 % slower)
+  if (token < 0) { const char* e = getenv("GDRN_DW_TOKEN"); token = e ? atoi(e) : 1; }
+  GDRN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kfn, tmap, tmap_w, bias, ln_w, ln_b, out, B, H, W, C, eps, split, token, trp));
+  gdrn_count_launch(1);
+  if (trace_on) {
+    long long h[8];
+    GDRN_CHECK_CUDA(cudaMemcpyAsync(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost, st));
+    GDRN_CHECK_CUDA(cudaStreamSynchronize(st));
+    fprintf(stderr, "[dwconv pp trace] %dx%d C=%d split=%d clusters=%d x %d, wg0 tiles=%lld: tile-wait=%lld token-wait=%lld conv=%lld "
+                    "sync+tma=%lld ln-local=%lld push+parts-wait=%lld combine+store=%lld\n",
+            H, W, C, split, nclusters, csize, h[7], h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
+  }
+  return GDRN_OK;
+}

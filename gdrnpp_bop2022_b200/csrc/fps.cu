@@ -4,13 +4,17 @@
 //
 // One CTA per cloud.  The cloud (x,y,z SoA) and the running min-distance live in shared memory (up to
 // 14 000 points) or, for larger clouds, min-distance in shared memory and the points streamed from
-// L2 (up to 56 000 points).  Every iteration: each thread relaxes its points against the last pick
+// L2 (up to 56 000 points); beyond that a cluster of 2 / 4 / 8 CTAs shares one cloud (fps_cluster_kernel, up to
+// 448 000 points).  Every iteration: each thread relaxes its points against the last pick
 // and keeps a local (value, index) arg-max; one shuffle tree + one __syncthreads per pick.
 // Algorithmic traffic: 12*pn + 4*sn bytes per cloud; the op is latency-bound on sn block reductions.
+#include <cooperative_groups.h>
 #include <float.h>
 #include <stdlib.h>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -145,9 +149,151 @@ fps_kernel(const float* __restrict__ pts_all, int* __restrict__ idx_all, int pn,
   }
 }
 
+// Clouds beyond one CTA's shared memory (pn > 56 000; BOP meshes reach 10^5 vertices): a thread-block
+// CLUSTER of CS CTAs per cloud.  CTA `rank` owns points [rank*chunk, (rank+1)*chunk) with its slice of the running
+// min-distance in its own shared memory (points streamed from L2); per pick every CTA pushes its local arg-max
+// candidate into all peers' shared memory (distributed shared memory stores), one cluster barrier, and every CTA
+// reduces the CS candidates identically (strict '>' then lowest index: the reference's scan order).  Same arithmetic,
+// same tie-breaking => the same indices as the single-CTA kernel and the reference.
+template <int CS>
+__global__ void __launch_bounds__(FPS_THREADS, 1)
+fps_cluster_kernel(const float* __restrict__ pts_all, int* __restrict__ idx_all, int pn, int sn,
+                   const int* __restrict__ start_idx) {
+  extern __shared__ float sm[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int cloud = blockIdx.x / CS;
+  const float* pts = pts_all + (size_t)cloud * pn * 3;
+  int* out = idx_all + (size_t)cloud * sn;
+  const int chunk = (pn + CS - 1) / CS;
+  const int i0 = rank * chunk, i1 = min(pn, i0 + chunk);
+  float* sd = sm;                         // [chunk] running min distance of this CTA's points
+  __shared__ Cand red[32];
+  __shared__ Cand xch[2][CS];             // candidates of every rank, double-buffered by pick parity
+  __shared__ float redf[6][32];
+  __shared__ float xbb[CS][6];            // bbox partials of every rank
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto PX = [&](int i) { return __ldg(pts + 3 * i); };
+  auto PY = [&](int i) { return __ldg(pts + 3 * i + 1); };
+  auto PZ = [&](int i) { return __ldg(pts + 3 * i + 2); };
+  // block arg-max of `best` -> pushed to every rank's xch[buf][rank]; cluster barrier; identical final reduction
+  auto cluster_argmax = [&](Cand best, int buf) {
+    best = warp_argmax(best);
+    if (lane == 0) red[warp] = best;
+    __syncthreads();
+    if (warp == 0) {
+      Cand t = warp_argmax(red[lane]);
+      if (lane < CS) *cluster.map_shared_rank(&xch[buf][rank], lane) = t;
+    }
+    cluster.sync();
+    Cand t = xch[buf][0];
+#pragma unroll
+    for (int r = 1; r < CS; ++r) t = better(t, xch[buf][r]);
+    return t.i;
+  };
+
+  int cur;
+  if (start_idx == nullptr) {
+    float mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX}, mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
+    for (int i = i0 + tid; i < i1; i += FPS_THREADS) {
+      float x = PX(i), y = PY(i), z = PZ(i);
+      mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
+      mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+        mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+      }
+      if (lane == 0) { redf[k][warp] = mx[k]; redf[3 + k][warp] = mn[k]; }
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        float a = redf[k][lane], b = redf[3 + k][lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
+          b = fminf(b, __shfl_xor_sync(0xffffffffu, b, o));
+        }
+        if (lane < CS) { *cluster.map_shared_rank(&xbb[rank][k], lane) = a; *cluster.map_shared_rank(&xbb[rank][3 + k], lane) = b; }
+      }
+    }
+    cluster.sync();
+    float c[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float a = xbb[0][k], b = xbb[0][3 + k];
+#pragma unroll
+      for (int r = 1; r < CS; ++r) { a = fmaxf(a, xbb[r][k]); b = fminf(b, xbb[r][3 + k]); }   // max / min are order independent
+      c[k] = __fmul_rn(__fadd_rn(a, b), 0.5f);
+    }
+    Cand best = {0.f, 0};
+    for (int i = i0 + tid; i < i1; i += FPS_THREADS) {
+      float d = sqdist_nofma(PX(i), PY(i), PZ(i), c[0], c[1], c[2]);
+      d = fminf(d, FLT_MAX);
+      sd[i - i0] = d;
+      best = better(best, Cand{d, i});
+    }
+    cur = cluster_argmax(best, 1);
+  } else {
+    for (int i = i0 + tid; i < i1; i += FPS_THREADS) sd[i - i0] = FLT_MAX;
+    cur = start_idx[cloud];
+    __syncthreads();
+  }
+
+  for (int s = 0; s < sn; ++s) {
+    if (tid == 0 && rank == 0) out[s] = cur;
+    if (s == sn - 1) break;
+    const float cx = PX(cur), cy = PY(cur), cz = PZ(cur);
+    Cand best = {0.f, 0};
+    for (int i = i0 + tid; i < i1; i += FPS_THREADS) {
+      float d = sd[i - i0];
+      if (i == cur) { d = -1.f; sd[i - i0] = d; }
+      if (d >= 0.f) {
+        float nd = sqdist_nofma(PX(i), PY(i), PZ(i), cx, cy, cz);
+        if (nd < d) { d = nd; sd[i - i0] = d; }
+        best = better(best, Cand{d, i});
+      }
+    }
+    cur = cluster_argmax(best, s & 1);
+  }
+  cluster.sync();   // no CTA exits while a peer may still write its shared memory
+}
+
+template <int CS>
+int fps_launch_cluster(const float* pts, int* idxs, int pn, int sn, int batch, const int* start_idx, cudaStream_t st) {
+  auto kfn = fps_cluster_kernel<CS>;
+  const size_t smem = (size_t)((pn + CS - 1) / CS) * 4;
+  GDRN_OPT_IN_SMEM(kfn, 224000);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(batch * CS);
+  cfg.blockDim = dim3(FPS_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  GDRN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kfn, pts, idxs, pn, sn, start_idx));
+  gdrn_count_launch(1);
+  return GDRN_OK;
+}
+
 int fps_launch(const float* pts, int* idxs, int pn, int sn, int batch, const int* start_idx, cudaStream_t st) {
   GDRN_REQUIRE(pn > 0 && sn > 0 && batch > 0, "fps: pn, sn, batch must be positive");
-  GDRN_REQUIRE(pn <= FPS_SMEM_D, "fps: pn > 56000 points per cloud is not supported by the single-CTA kernel");
+  GDRN_REQUIRE(pn <= 8 * FPS_SMEM_D, "fps: more than 448000 points per cloud are not supported (8-CTA cluster x 56000)");
+  if (pn > FPS_SMEM_D) {   // cluster of 2 / 4 / 8 CTAs per cloud
+    if (pn <= 2 * FPS_SMEM_D) return fps_launch_cluster<2>(pts, idxs, pn, sn, batch, start_idx, st);
+    if (pn <= 4 * FPS_SMEM_D) return fps_launch_cluster<4>(pts, idxs, pn, sn, batch, start_idx, st);
+    return fps_launch_cluster<8>(pts, idxs, pn, sn, batch, start_idx, st);
+  }
   GDRN_OPT_IN_SMEM(fps_kernel<true>, 224000);
   GDRN_OPT_IN_SMEM(fps_kernel<false>, 224000);
   if (pn <= FPS_SMEM_ALL) {

@@ -747,9 +747,9 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmPlan& p, int m_tile,
 // Split-bf16 (x3) outputs with TMA stores (EPI_STORE / EPI_GELU, bf16 [M, 2N] = [hi N | lo N] rows).
 // A thread owns one accumulator row.  Per 32-column chunk (one tcgen05.ld) it computes hi = bf16(v) and
 // lo = bf16(v - hi) in registers (the long part: exact-erf GELU), THEN waits for the previous chunk's TMA stores to
-// have read the staging buffer (long finished by then), writes hi / lo into two dense 32-row x 64-byte tiles and one
+// have read the staging buffer (long finished by then), writes hi / lo into two 32-row x 64-byte tiles and one
 // lane issues two stores: hi at column `col`, lo at column N + col.  Rows beyond M are clipped by the tensor map
-// (SWIZZLE_NONE, box {32, 32}: gemm_tc_launch builds it with make_tmap_store_plain).
+// (SWIZZLE_64B, box {32, 32}: gemm_tc_launch builds it with make_tmap_store_plain).
 template <int BLOCK_N, int EPI, int NEW>
 __device__ __forceinline__ void epilogue_tile_tma_split(const GemmPlan& p, int m_tile, int n_tile, uint32_t tmem_acc, int ew,
                                                         int lane, uint8_t* stg) {
@@ -764,12 +764,16 @@ __device__ __forceinline__ void epilogue_tile_tma_split(const GemmPlan& p, int m
   uint4* my_hi = reinterpret_cast<uint4*>(stg + lane * 64);
   uint4* my_lo = reinterpret_cast<uint4*>(stg + 2048 + lane * 64);
   const int row0 = m_tile * BLOCK_M + q * 32;
+  const bool trc = (p.trace != nullptr) && blockIdx.x == 0 && ew == 0;   // GDRN_GEMM_TRACE: phase cycles of one warp
+  long long tq_tmem = 0, tq_comp = 0, tq_flush = 0;
 #pragma unroll 1
   for (int c = 0; c < CPW; c += CH) {
     const int col = n0 + c;
     if (col >= p.N) break;  // warp-uniform
     float v[CH];
+    long long tq0 = trc ? clock64() : 0;
     tmem_load_chunk<CH>(tmem_row + c, v);
+    if (trc) { const long long t = clock64(); tq_tmem += t - tq0; tq0 = t; }
     if (p.bias) {
 #pragma unroll
       for (int j = 0; j < CH; j += 4) {
@@ -781,6 +785,9 @@ __device__ __forceinline__ void epilogue_tile_tma_split(const GemmPlan& p, int m
       if (p.gelu_mode == 3) {
 #pragma unroll
         for (int j = 0; j < CH; ++j) v[j] = gelu_erf(v[j]);
+      } else if (p.gelu_mode == 4) {   // A/B knob: libm erff (data-dependent branch inside)
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752440f));
       } else {
 #pragma unroll
         for (int j = 0; j < CH; ++j) v[j] = gelu_fast(v[j]);
@@ -794,12 +801,15 @@ __device__ __forceinline__ void epilogue_tile_tma_split(const GemmPlan& p, int m
       hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
       lo[j] = pack_bf16(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
     }
+    if (trc) { const long long t = clock64(); tq_comp += t - tq0; tq0 = t; }
     if (lane == 0) ptx::bulk_wait_read0();   // the previous chunk's stores have read the staging tiles
     __syncwarp();
+    // 64-byte rows, SWIZZLE_64B: chunk c of row r lives at c ^ ((r >> 1) & 3) -- eight consecutive lanes cover all 32 banks
+    const int sw = (lane >> 1) & 3;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      my_hi[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-      my_lo[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+      my_hi[j ^ sw] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+      my_lo[j ^ sw] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
     }
     ptx::fence_proxy_async();
     __syncwarp();
@@ -808,7 +818,9 @@ __device__ __forceinline__ void epilogue_tile_tma_split(const GemmPlan& p, int m
       ptx::tma_store_2d(&p.tmap_out, stg_u32 + 2048, p.N + col, row0);
       ptx::bulk_commit();
     }
+    if (trc) tq_flush += clock64() - tq0;
   }
+  if (trc && lane == 0) { p.trace[8] += tq_tmem; p.trace[9] += tq_comp; p.trace[10] += tq_flush; }
 }
 
 template <int BLOCK_N, int EPI>

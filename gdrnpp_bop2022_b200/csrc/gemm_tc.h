@@ -108,7 +108,8 @@ int make_tmap_f32_plain(CUtensorMap* out, const void* base, int rank, const uint
                         const uint64_t* strides_bytes, const uint32_t* box);
 int make_tmap_store(CUtensorMap* out, const void* base, int is_f32, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box);
-// same, SWIZZLE_NONE (dense [rows][box0] shared-memory tile)
+// same for narrow tiles: 64-byte rows use SWIZZLE_64B (16-byte chunk c of row r at c ^ ((r >> 1) & 3): conflict-free
+// row-wise STS.128), anything else SWIZZLE_NONE (dense [rows][box0] shared-memory tile)
 int make_tmap_store_plain(CUtensorMap* out, const void* base, int is_f32, const uint64_t* dims,
                           const uint64_t* strides_bytes, const uint32_t* box);
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,

@@ -13,6 +13,7 @@
 // hypotheses over it: HBM traffic = 8*tn*vn + 8*tn + 8|12*hn*vn read, and either hn*vn*tn mask bytes
 // written (reference-compatible entry) or 4*hn*vn count bytes (fused entry).
 #include "common.cuh"
+#include "rv_math.cuh"
 
 namespace {
 
@@ -68,31 +69,6 @@ __global__ void gen_hyp_vp_kernel(const float* __restrict__ direct, const float*
   hypo[hvi * 3] = x;
   hypo[hvi * 3 + 1] = y;
   hypo[hvi * 3 + 2] = z;
-}
-
-template <bool VP>
-__device__ __forceinline__ bool vote(float nx, float ny, float norm1, float cx, float cy, float hx, float hy,
-                                     float hz, float thresh) {
-  float dx, dy;
-  if (VP) {
-    dx = __fmaf_rn(-cx, hz, hx);
-    dy = __fmaf_rn(-cy, hz, hy);
-  } else {
-    dx = __fsub_rn(hx, cx);
-    dy = __fsub_rn(hy, cy);
-  }
-  float norm2 = __fsqrt_rn(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-  if ((double)norm1 < 1e-6 || (double)norm2 < 1e-6) return false;
-  float den = __fmul_rn(norm1, norm2);
-  if (VP) {
-    float vx = __fmul_rn(nx, dx), vy = __fmul_rn(ny, dy);
-    float ang = __fdiv_rn(__fadd_rn(vx, vy), den);
-    if (vx < 0 || vy < 0) return false;
-    return fabsf(ang) > thresh;
-  } else {
-    float ang = __fdiv_rn(__fmaf_rn(nx, dx, __fmul_rn(ny, dy)), den);
-    return ang > thresh;
-  }
 }
 
 // grid: (ceil(tn / RV_TILE_T), ceil(hn / RV_H_CHUNK)); block RV_TILE_T threads, one pixel per thread.

@@ -4,7 +4,8 @@ Mirrors (same names, argument meaning and error behaviour):
   * core/csrc/fps/fps_utils.py:6-21                  -> farthest_point_sampling(pts, sn, init_center)
   * core/csrc/ransac_voting (pybind module)          -> ransac_voting.{generate_hypothesis, voting_for_hypothesis,
         generate_hypothesis_vanishing_point, voting_for_hypothesis_vanishing_point}
-    and the driver core/csrc/ransac_voting/ransac_voting_gpu.py:7-104 -> ransac_voting_layer / _v3
+    and the driver core/csrc/ransac_voting/ransac_voting_gpu.py:7-330 -> ransac_voting_layer / _v3 /
+    estimate_voting_distribution_with_mean, as ONE device-side call (csrc/ransac_layer.cu)
   * core/csrc/torch_nndistance/torch_nndistance.py   -> NNDFunction, nnd
   * core/csrc/flow/flow_torch.py:15-40               -> FlowFunction, flow; flow_cuda.forward
   * core/csrc/uncertainty_pnp/un_pnp_utils.py:11-78  -> uncertainty_pnp (EPnP init stays cv2 on the host)
@@ -127,79 +128,83 @@ class _RansacVotingModule:
 ransac_voting = _RansacVotingModule()
 
 
-def _b_inv(b_mat):
-    eye = b_mat.new_ones(b_mat.size(-1)).diag().expand_as(b_mat)
-    try:
-        return torch.linalg.solve(b_mat, eye)
-    except Exception:  # singular: the reference falls back to identity (ransac_voting_gpu.py:107-119)
-        return eye
-
-
-def ransac_voting_layer(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20, min_num=5,
-                        max_num=30000, fused=True, idxs_fn=None):
-    """ransac_voting_gpu.py:7-104 (v3 = same loop with bool masks and b_inv).  mask [b,h,w], vertex [b,h,w,vn,2].
-
-    ``fused=True`` counts inliers with rv_vote_count instead of materialising the [hn,vn,tn] mask + torch.sum
-    (identical counts).  ``idxs_fn(round_hyp_num, vn, tn)`` may supply the hypothesis pixel pairs (tests)."""
+def _ransac_layer_call(mask, vertex, hn, inlier_thresh, min_num, max_num, idxs, seed, want_hyp=False, want_inliers=False):
+    """One call of rv_ransac_voting_layer for the whole batch: compaction of the foreground, hypotheses, fused
+    vote + count, per-keypoint winner, inlier set of the winner and its least-squares refit -- all on the device."""
+    if not vertex.is_cuda:
+        raise RuntimeError("ransac_voting_layer: CUDA tensors required (no CPU fallback)")
+    dev = vertex.device
     b, h, w, vn, _ = vertex.shape
-    batch_win_pts = []
-    for bi in range(b):
-        hyp_num = 0
-        cur_mask = mask[bi].to(torch.bool)
-        foreground_num = torch.sum(cur_mask)
-        if foreground_num < min_num:
-            batch_win_pts.append(torch.zeros([1, vn, 2], dtype=torch.float32, device=mask.device))
-            continue
-        if foreground_num > max_num:
-            selection = torch.zeros(cur_mask.shape, dtype=torch.float32, device=mask.device).uniform_(0, 1)
-            cur_mask = cur_mask & (selection < (max_num / foreground_num.float()))
-        coords = torch.nonzero(cur_mask).float()[:, [1, 0]].contiguous()
-        direct = vertex[bi].masked_select(cur_mask[:, :, None, None]).view([coords.shape[0], vn, 2]).contiguous()
-        tn = coords.shape[0]
-        if idxs_fn is not None:
-            idxs = idxs_fn(round_hyp_num, vn, tn).to(device=mask.device, dtype=torch.int32).contiguous()
-        else:
-            idxs = torch.zeros([round_hyp_num, vn, 2], dtype=torch.int32, device=mask.device).random_(0, tn)
-        all_win_ratio = torch.zeros([vn], dtype=torch.float32, device=mask.device)
-        all_win_pts = torch.zeros([vn, 2], dtype=torch.float32, device=mask.device)
-        cur_iter = 0
-        while True:
-            cur_hyp_pts = ransac_voting.generate_hypothesis(direct, coords, idxs)
-            if fused:
-                cur_inlier_counts = ransac_voting.vote_count(direct, coords, cur_hyp_pts, inlier_thresh).long()
-            else:
-                cur_inlier = torch.zeros([round_hyp_num, vn, tn], dtype=torch.uint8, device=mask.device)
-                ransac_voting.voting_for_hypothesis(direct, coords, cur_hyp_pts, cur_inlier, inlier_thresh)
-                cur_inlier_counts = torch.sum(cur_inlier, 2)
-            cur_win_counts, cur_win_idx = torch.max(cur_inlier_counts, 0)
-            cur_win_pts = cur_hyp_pts[cur_win_idx, torch.arange(vn, device=mask.device)]
-            cur_win_ratio = cur_win_counts.float() / tn
-            larger_mask = all_win_ratio < cur_win_ratio
-            all_win_pts[larger_mask, :] = cur_win_pts[larger_mask, :]
-            all_win_ratio[larger_mask] = cur_win_ratio[larger_mask]
-            hyp_num += round_hyp_num
-            cur_iter += 1
-            cur_min_ratio = torch.min(all_win_ratio)
-            if (1 - (1 - cur_min_ratio**2) ** hyp_num) > confidence or cur_iter > max_iter:
-                break
-            if idxs_fn is None:
-                pass  # the reference re-uses the same idxs every round (ransac_voting_gpu.py:48 is outside the loop)
-        normal = torch.zeros_like(direct)
-        normal[:, :, 0] = direct[:, :, 1]
-        normal[:, :, 1] = -direct[:, :, 0]
-        all_inlier = torch.zeros([1, vn, tn], dtype=torch.uint8, device=mask.device)
-        ransac_voting.voting_for_hypothesis(direct, coords, all_win_pts[None].contiguous(), all_inlier, inlier_thresh)
-        all_inlier = torch.squeeze(all_inlier.float(), 0)
-        normal = normal.permute(1, 0, 2) * torch.unsqueeze(all_inlier, 2)
-        bvec = torch.sum(normal * torch.unsqueeze(coords, 0), 2)
-        ATA = torch.matmul(normal.permute(0, 2, 1), normal)
-        ATb = torch.sum(normal * torch.unsqueeze(bvec, 2), 1)
-        win = torch.matmul(_b_inv(ATA), torch.unsqueeze(ATb, 2))
-        batch_win_pts.append(win[None, :, :, 0])
-    return torch.cat(batch_win_pts)
+    m = mask.detach().to(device=dev).reshape(b, h, w)
+    m = (m != 0).to(torch.float32).contiguous()
+    vtx = vertex.detach().to(dtype=torch.float32).contiguous()
+    L = _lib.lib()
+    ws = torch.empty(L.rv_layer_workspace_bytes(b, h, w, vn, hn), dtype=torch.uint8, device=dev)
+    win = torch.empty((b, vn, 2), dtype=torch.float32, device=dev)
+    hyp = torch.empty((b, hn, vn, 2), dtype=torch.float32, device=dev) if want_hyp else None
+    cnt = torch.empty((b, hn, vn), dtype=torch.int32, device=dev) if want_hyp else None
+    tn = torch.empty((b,), dtype=torch.int32, device=dev) if (want_hyp or want_inliers) else None
+    inl = torch.zeros((b, vn, h * w), dtype=torch.uint8, device=dev) if want_inliers else None
+    ix = None
+    if idxs is not None:
+        ix = idxs.detach().to(device=dev, dtype=torch.int32).contiguous()
+        assert tuple(ix.shape) == (b, hn, vn, 2), ix.shape
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())     # host RNG (torch.manual_seed reproducible), no device sync
+    _lib.check(L.rv_ransac_voting_layer(_lib.ptr(m), _lib.ptr(vtx), b, h, w, vn, hn, float(inlier_thresh), int(min_num), int(max_num),
+                                        int(seed) & 0xFFFFFFFF, _lib.ptr(ix), _lib.ptr(win), _lib.ptr(hyp), _lib.ptr(cnt), _lib.ptr(tn),
+                                        _lib.ptr(inl), _lib.ptr(ws), ws.numel(), _lib.current_stream()), "rv_ransac_voting_layer")
+    return win, hyp, cnt, tn, inl
 
 
-ransac_voting_layer_v3 = ransac_voting_layer
+@_lib.on_device(1)
+def ransac_voting_layer(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20, min_num=5,
+                        max_num=30000, idxs=None, seed=None, return_inliers=False):
+    """ransac_voting_gpu.py:7-104 on the device: mask [b,h,w], vertex [b,h,w,vn,2] -> keypoints [b,vn,2].
+
+    The reference draws its hypothesis pixel pairs ONCE per image, outside its `while` loop (:48), so every round
+    regenerates the same hypotheses and counts and its strict `<` update never fires after round 1: `confidence` and
+    `max_iter` only decide when that loop stops, not what it returns.  One device-side round is therefore the same
+    function -- without the per-round device->host syncs, the [hn,vn,tn] inlier mask, torch.nonzero or torch.solve.
+    ``idxs`` [b,hn,vn,2] int32 (optional, taken modulo the foreground count) replaces the on-device RNG (tests);
+    ``return_inliers`` also returns (inlier mask [b,vn,h*w] u8 in compacted-pixel order, tn [b])."""
+    del confidence, max_iter   # see the docstring: they do not influence the reference's result
+    win, _, _, tn, inl = _ransac_layer_call(mask, vertex, int(round_hyp_num), inlier_thresh, min_num, max_num, idxs, seed,
+                                            want_inliers=return_inliers)
+    return (win, inl, tn) if return_inliers else win
+
+
+def ransac_voting_layer_v3(mask, vertex, round_hyp_num, inlier_thresh=0.999, confidence=0.99, max_iter=20, min_num=5,
+                           max_num=30000, **kw):
+    """ransac_voting_gpu.py:123-218: the v3 variant differs from ransac_voting_layer only in using bool masks and a
+    batched inverse for the final 2x2 solves -- numerically the same function; same device-side implementation."""
+    return ransac_voting_layer(mask, vertex, round_hyp_num, inlier_thresh, confidence, max_iter, min_num, max_num, **kw)
+
+
+@_lib.on_device(1)
+def estimate_voting_distribution_with_mean(mask, vertex, mean, round_hyp_num=256, min_hyp_num=4096, topk=128,
+                                           inlier_thresh=0.99, min_num=5, max_num=30000, output_hyp=False, seed=None):
+    """ransac_voting_gpu.py:221-330: hypothesis cloud of `min_hyp_num` line intersections per keypoint, weighted by their
+    inlier ratio (ratios more than 0.1 below the best are dropped) -> covariance around `mean` [b,vn,2].  The reference
+    draws fresh pixel pairs for each of its ceil(min_hyp_num / round_hyp_num) rounds and concatenates them: here all
+    hypotheses are generated and counted in one device call (mask == 1 is the foreground, :233)."""
+    del topk, output_hyp
+    b, h, w, vn, _ = vertex.shape
+    hn = int(np.ceil(min_hyp_num / round_hyp_num)) * int(round_hyp_num)
+    fg = (mask.reshape(b, h, w) == 1)
+    _, hyp, cnt, tn, _ = _ransac_layer_call(fg, vertex, hn, inlier_thresh, min_num, max_num, None, seed, want_hyp=True)
+    tnf = tn.to(torch.float32).clamp_min(1.0).view(b, 1, 1)
+    ratio = cnt.to(torch.float32) / tnf                                       # [b,hn,vn]
+    empty = (tn <= 0).view(b, 1, 1)
+    ratio = torch.where(empty, torch.ones_like(ratio), ratio)                 # too few pixels: zeros / ones like the reference (:237-247)
+    all_hyp = hyp.permute(0, 2, 1, 3)                                         # b,vn,hn,2
+    all_ratio = ratio.permute(0, 2, 1).clone()                                # b,vn,hn
+    thresh = torch.max(all_ratio, 2)[0] - 0.1
+    all_ratio = torch.where(all_ratio < thresh.unsqueeze(2), torch.zeros_like(all_ratio), all_ratio)
+    diff = all_hyp - mean.unsqueeze(2)
+    cov = torch.matmul(diff.transpose(2, 3), diff * all_ratio.unsqueeze(3))
+    cov = cov / (torch.sum(all_ratio, 2).unsqueeze(2).unsqueeze(3) + 1e-3)
+    return mean, cov
 
 
 # ------------------------------------------------------------------------------------------------ nnd
@@ -401,20 +406,27 @@ def get_affine_transform(center, scale, rot, output_size, shift=(0.0, 0.0), inv=
 
 
 def _affine_batch(M, device):
+    if torch.is_tensor(M):   # already on the device (a caller that batches its uploads): [n,2,3] / [n,6] float64
+        Md = M.detach().to(device=device, dtype=torch.float64).reshape(-1, 6).contiguous()
+        return Md, Md.shape[0]
     M = np.ascontiguousarray(np.asarray(M, np.float64).reshape(-1, 6))
     return torch.from_numpy(M).to(device), M.shape[0]
 
 
 @_lib.on_device(0)
-def crop_resize_image(image, M, output_size, pixel_mean=(0.0, 0.0, 0.0), pixel_std=(255.0, 255.0, 255.0)):
+def crop_resize_image(image, M, output_size, pixel_mean=(0.0, 0.0, 0.0), pixel_std=(255.0, 255.0, 255.0), out=None):
     """Batched cv2.warpAffine(image, M[i], (w, h), INTER_LINEAR) + normalize_image for an HxWxC uint8 CUDA image:
-    returns roi_img [n, C, h, w] float32 (predictor_gdrn.py:417-422).  M: [n,2,3] float64 forward transforms."""
+    returns roi_img [n, C, h, w] float32 (predictor_gdrn.py:417-422).  M: [n,2,3] float64 forward transforms (numpy, or
+    a CUDA tensor).  out: optional preallocated [n,C,h,w] float32 CUDA tensor (static CUDA-graph input buffers)."""
     _check_cuda_contig(image, "image")
     assert image.dtype == torch.uint8 and image.dim() == 3
     H, W, C = image.shape
     ow, oh = (output_size, output_size) if np.isscalar(output_size) else output_size
     Md, n = _affine_batch(M, image.device)
-    out = torch.empty((n, C, int(oh), int(ow)), dtype=torch.float32, device=image.device)
+    if out is None:
+        out = torch.empty((n, C, int(oh), int(ow)), dtype=torch.float32, device=image.device)
+    else:
+        assert out.is_cuda and out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == (n, C, int(oh), int(ow))
     mean = (ctypes.c_double * C)(*[float(v) for v in list(pixel_mean)[:C]])
     std = (ctypes.c_double * C)(*[float(v) for v in list(pixel_std)[:C]])
     _lib.check(_lib.lib().gdrn_crop_resize_u8(_lib.ptr(image), H, W, C, _lib.ptr(Md), n, int(oh), int(ow), mean, std,
@@ -423,16 +435,19 @@ def crop_resize_image(image, M, output_size, pixel_mean=(0.0, 0.0, 0.0), pixel_s
 
 
 @_lib.on_device(0)
-def crop_resize_float(src, M, output_size, nearest=False):
+def crop_resize_float(src, M, output_size, nearest=False, out=None):
     """Batched cv2.warpAffine on an HxW(xC) float32 CUDA array (INTER_LINEAR, or INTER_NEAREST for depth):
-    returns [n, C, h, w] float32 (roi_coord_2d / roi_depth, predictor_gdrn.py:425-438)."""
+    returns [n, C, h, w] float32 (roi_coord_2d / roi_depth, predictor_gdrn.py:425-438).  M / out as in crop_resize_image."""
     _check_cuda_contig(src, "src")
     assert src.dtype == torch.float32 and src.dim() in (2, 3)
     H, W = src.shape[:2]
     C = 1 if src.dim() == 2 else src.shape[2]
     ow, oh = (output_size, output_size) if np.isscalar(output_size) else output_size
     Md, n = _affine_batch(M, src.device)
-    out = torch.empty((n, C, int(oh), int(ow)), dtype=torch.float32, device=src.device)
+    if out is None:
+        out = torch.empty((n, C, int(oh), int(ow)), dtype=torch.float32, device=src.device)
+    else:
+        assert out.is_cuda and out.is_contiguous() and out.dtype == torch.float32 and tuple(out.shape) == (n, C, int(oh), int(ow))
     _lib.check(_lib.lib().gdrn_crop_resize_f32(_lib.ptr(src), H, W, C, _lib.ptr(Md), n, int(oh), int(ow), int(bool(nearest)),
                                                _lib.ptr(out), _lib.current_stream()), "gdrn_crop_resize_f32")
     return out

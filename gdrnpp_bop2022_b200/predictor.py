@@ -30,7 +30,7 @@ class GdrnPredictor:
     def __init__(self, config_file_path=None, ckpt_file_path=None, camera_json_path=None, path_to_obj_models=None, *,
                  cam=None, objs=None, extents=None, models=None, state_dict=None, num_classes=None, cfg=None,
                  use_pnp=None, use_depth_refine=None, depth_refine_iter=None, depth_refine_threshold=None,
-                 depth_scale=None, vertex_scale=0.001, device="cuda", precision=None, max_batch=64):
+                 depth_scale=None, vertex_scale=0.001, device="cuda", precision=None, max_batch=64, use_cuda_graph=True):
         """Reference arguments (predictor_gdrn.py:45-50):
           config_file_path   reference-style python config (configs/gdrn/**.py); None -> the YCB-V a6 defaults
           ckpt_file_path     torch checkpoint ({"model": state_dict} or a bare state_dict, "_module." prefixes stripped
@@ -109,6 +109,12 @@ class GdrnPredictor:
         self.ren_models = None
         if models is not None:
             self.ren_models = [Model3D(*models[i], device=self.device) for i in self.obj_ids]
+        # per-image latency path: the per-ROI bookkeeping of one image travels in ONE pinned host block + one H2D copy,
+        # the crops are written straight into per-batch-size static buffers, and the ~160 launches of a forward over them
+        # are replayed as one CUDA graph (predictor_gdrn.py runs 5-ROI batches: launch-latency bound otherwise)
+        self.use_cuda_graph = bool(use_cuda_graph)
+        self._coord_grids = {}     # (H, W) -> [H,W,2] normalised coordinate grid on the device
+        self._static = {}          # n -> dict of static input tensors (+ pinned staging, + captured graph)
 
     # ---- preprocessing (predictor_gdrn.py:301-476) ---------------------------------------------
     def preprocessing(self, outputs, image, depth_img=None):
@@ -123,49 +129,96 @@ class GdrnPredictor:
         image = np.ascontiguousarray(image.detach().cpu().numpy() if torch.is_tensor(image) else image, np.uint8)
         H, W = image.shape[:2]
         in_res, out_res = 256, 64
-        centers = np.zeros((n, 2), np.float32)
-        whs = np.zeros((n, 2), np.float32)
-        scales = np.zeros((n,), np.float32)
-        M_in, M_out = np.zeros((n, 2, 3)), np.zeros((n, 2, 3))
+        st = self._static_buffers(n)
+        hf, hd = st["host_f32"], st["host_f64"]      # pinned: [n,18] f32 (centre 2, wh 2, scale, ratio, extent 3, cam 9), [n,12] f64 (M_in, M_out)
+        cls_np = det[:, 6].astype(np.int64)
         for i in range(n):
             x1, y1, x2, y2 = det[i, :4]
             c = np.array([0.5 * (x1 + x2), 0.5 * (y1 + y2)])
             bw, bh = max(x2 - x1, 1), max(y2 - y1, 1)
             scale = min(max(bh, bw) * self.dzi_pad_scale, max(H, W)) * 1.0
-            centers[i], whs[i], scales[i] = c.astype(np.float32), (bw, bh), scale
-            M_in[i] = get_affine_transform(c, scale, 0, in_res)
-            M_out[i] = get_affine_transform(c, scale, 0, out_res)
-        img_d = torch.from_numpy(image).to(dev)
-        roi_img = crop_resize_image(img_d, M_in, in_res, self.pixel_mean, self.pixel_std)   # PIXEL_MEAN 0 / PIXEL_STD 255
-        # get_2d_coord_np(W, H, low=0, high=1) (data_utils.py:304-323): linspace(endpoint=False) grid, [H,W,2] (x, y)
-        xs = torch.from_numpy(np.linspace(0, 1, W, endpoint=False, dtype=np.float32))
-        ys = torch.from_numpy(np.linspace(0, 1, H, endpoint=False, dtype=np.float32))
-        coord = torch.stack([xs[None, :].expand(H, W), ys[:, None].expand(H, W)], dim=2).contiguous().to(dev)
-        roi_coord_2d = crop_resize_float(coord, M_out, out_res)
-        cls = torch.from_numpy(det[:, 6].astype(np.int64))
-        ext = torch.stack([torch.from_numpy(self.extents[self.obj_ids[int(c)]]) for c in cls]) if n else torch.zeros((0, 3))
+            hf[i, 0:2] = torch.from_numpy(c.astype(np.float32))
+            hf[i, 2], hf[i, 3], hf[i, 4], hf[i, 5] = float(bw), float(bh), float(np.float32(scale)), float(np.float32(out_res / np.float32(scale)))
+            hf[i, 6:9] = torch.from_numpy(self.extents[self.obj_ids[int(cls_np[i])]])
+            hd[i, 0:6] = torch.from_numpy(get_affine_transform(c, scale, 0, in_res).reshape(6))
+            hd[i, 6:12] = torch.from_numpy(get_affine_transform(c, scale, 0, out_res).reshape(6))
+        if n:
+            hf[:, 9:18] = torch.from_numpy(self.cam.reshape(1, 9))
+            st["host_cls"].copy_(torch.from_numpy(cls_np))
+        with torch.cuda.device(dev):
+            # one small H2D per dtype (pinned, asynchronous), then device-side slices into the static input tensors
+            st["dev_f32"].copy_(hf, non_blocking=True)
+            st["dev_f64"].copy_(hd, non_blocking=True)
+            st["roi_cls"].copy_(st["host_cls"], non_blocking=True)
+            df = st["dev_f32"]
+            st["roi_center"].copy_(df[:, 0:2]); st["roi_wh"].copy_(df[:, 2:4]); st["scale"].copy_(df[:, 4]); st["resize_ratio"].copy_(df[:, 5])
+            st["roi_extent"].copy_(df[:, 6:9]); st["roi_cam"].copy_(df[:, 9:18].reshape(n, 3, 3))
+            M_in, M_out = st["dev_f64"][:, 0:6], st["dev_f64"][:, 6:12]
+            img_d = torch.from_numpy(image).to(dev, non_blocking=True)
+            crop_resize_image(img_d, M_in, in_res, self.pixel_mean, self.pixel_std, out=st["roi_img"])   # PIXEL_MEAN 0 / PIXEL_STD 255
+            coord = self._coord_grids.get((H, W))
+            if coord is None:
+                # get_2d_coord_np(W, H, low=0, high=1) (data_utils.py:304-323): linspace(endpoint=False) grid, [H,W,2] (x, y)
+                xs = torch.from_numpy(np.linspace(0, 1, W, endpoint=False, dtype=np.float32))
+                ys = torch.from_numpy(np.linspace(0, 1, H, endpoint=False, dtype=np.float32))
+                coord = torch.stack([xs[None, :].expand(H, W), ys[:, None].expand(H, W)], dim=2).contiguous().to(dev)
+                self._coord_grids[(H, W)] = coord
+            crop_resize_float(coord, M_out, out_res, out=st["roi_coord_2d"])
         data = {
-            "roi_img": roi_img, "roi_cls": cls.to(dev), "roi_coord_2d": roi_coord_2d,
-            "roi_cam": torch.from_numpy(self.cam)[None].repeat(n, 1, 1).to(dev), "cam": torch.from_numpy(self.cam)[None].repeat(n, 1, 1).to(dev),
-            "roi_center": torch.from_numpy(centers).to(dev), "bbox_center": torch.from_numpy(centers).to(dev),
-            "roi_wh": torch.from_numpy(whs).to(dev),
-            "scale": torch.from_numpy(scales).to(dev), "resize_ratio": torch.from_numpy((out_res / scales).astype(np.float32)).to(dev),
-            "roi_extent": ext.to(dev),
+            "roi_img": st["roi_img"], "roi_cls": st["roi_cls"], "roi_coord_2d": st["roi_coord_2d"],
+            "roi_cam": st["roi_cam"], "cam": st["roi_cam"],
+            "roi_center": st["roi_center"], "bbox_center": st["roi_center"], "roi_wh": st["roi_wh"],
+            "scale": st["scale"], "resize_ratio": st["resize_ratio"], "roi_extent": st["roi_extent"],
             "im_H": torch.full((n,), H, dtype=torch.float32), "im_W": torch.full((n,), W, dtype=torch.float32),
             "score": torch.from_numpy(det[:, 4] * det[:, 5]), "bbox_est": torch.from_numpy(det[:, :4].copy()),
+            "_static_n": n,
         }
         if depth_img is not None:
-            d = torch.from_numpy(np.ascontiguousarray(np.asarray(depth_img, np.float32) * np.float32(self.depth_scale))).to(dev)
-            data["roi_depth"] = crop_resize_float(d, M_in, in_res, nearest=True)      # [n,1,256,256] like the reference
+            with torch.cuda.device(dev):
+                d = torch.from_numpy(np.ascontiguousarray(np.asarray(depth_img, np.float32) * np.float32(self.depth_scale))).to(dev)
+                data["roi_depth"] = crop_resize_float(d, st["dev_f64"][:, 0:6], in_res, nearest=True)      # [n,1,256,256] like the reference
         return data
+
+    def _static_buffers(self, n):
+        """Static device tensors (and their pinned staging) for a batch of n ROIs; allocated once per n.  NOTE: the tensors
+        of a returned data_dict are these buffers: they are overwritten by the next preprocessing() of the same batch
+        size (the reference allocates fresh tensors per call; clone them to keep a batch alive across calls)."""
+        st = self._static.get(n)
+        if st is None:
+            dev = self.device
+            z = lambda *shape, dtype=torch.float32: torch.zeros(shape, dtype=dtype, device=dev)
+            st = {
+                "host_f32": torch.zeros((n, 18), dtype=torch.float32).pin_memory() if n else torch.zeros((0, 18)),
+                "host_f64": torch.zeros((n, 12), dtype=torch.float64).pin_memory() if n else torch.zeros((0, 12), dtype=torch.float64),
+                "host_cls": torch.zeros((n,), dtype=torch.int64).pin_memory() if n else torch.zeros((0,), dtype=torch.int64),
+                "dev_f32": z(n, 18), "dev_f64": z(n, 12, dtype=torch.float64), "roi_cls": z(n, dtype=torch.int64),
+                "roi_img": z(n, 3, 256, 256), "roi_coord_2d": z(n, 2, 64, 64), "roi_cam": z(n, 3, 3), "roi_center": z(n, 2),
+                "roi_wh": z(n, 2), "scale": z(n), "resize_ratio": z(n), "roi_extent": z(n, 3), "graph": None,
+            }
+            self._static[n] = st
+        return st
 
     # ---- inference (predictor_gdrn.py:122-147) --------------------------------------------------
     @torch.no_grad()
     def inference(self, data_dict):
-        out = self.model(
-            data_dict["roi_img"], roi_classes=data_dict["roi_cls"], roi_cams=data_dict["roi_cam"],
-            roi_whs=data_dict["roi_wh"], roi_centers=data_dict["roi_center"], resize_ratios=data_dict["resize_ratio"],
-            roi_coord_2d=data_dict.get("roi_coord_2d"), roi_extents=data_dict.get("roi_extent"))
+        n = data_dict["roi_img"].shape[0]
+        st = self._static.get(data_dict.get("_static_n", -1))
+        graph_ok = (self.use_cuda_graph and st is not None and 1 <= n <= self.model.max_batch
+                    and data_dict["roi_img"] is st["roi_img"])       # the batch still lives in the static buffers
+        if graph_ok:
+            with torch.cuda.device(self.device):
+                if st["graph"] is None:
+                    st["graph"] = self.model.capture_graph({
+                        "roi_img": st["roi_img"], "roi_classes": st["roi_cls"], "roi_coord_2d": st["roi_coord_2d"],
+                        "roi_cams": st["roi_cam"], "roi_centers": st["roi_center"], "roi_whs": st["roi_wh"],
+                        "roi_extents": st["roi_extent"], "resize_ratios": st["resize_ratio"]})
+                replay, out = st["graph"]
+                replay()
+        else:
+            out = self.model(
+                data_dict["roi_img"], roi_classes=data_dict["roi_cls"], roi_cams=data_dict["roi_cam"],
+                roi_whs=data_dict["roi_wh"], roi_centers=data_dict["roi_center"], resize_ratios=data_dict["resize_ratio"],
+                roi_coord_2d=data_dict.get("roi_coord_2d"), roi_extents=data_dict.get("roi_extent"))
         torch.cuda.synchronize(self.device)
         return out
 

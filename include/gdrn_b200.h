@@ -104,6 +104,12 @@ int gdrn_gemm_bf16(const void* A, const void* W, const float* bias, const float*
 int gdrn_gemm_x3(const void* A, const void* W, const float* bias, const float* gamma, const float* resid, void* out,
                  int M, int N, int K, int epi, int block_n, void* stream);
 
+/* ConvNeXt block front half exported for tests and roofline measurement: depthwise 7x7 (pad 3) + bias + LayerNorm(C)
+ * on an NHWC fp32 tensor x [B,H,W,C] with tap-major weights w49c [49][C] -> bf16 [B*H*W, C] (split = 1: [hi C | lo C]).
+ * variant: -1 default, 0 = one-tile-per-CTA cluster kernel, 1 = persistent two-warpgroup ping-pong kernel. */
+int gdrn_dwconv_ln(const float* x, const float* w49c, const float* bias, const float* ln_w, const float* ln_b, void* out,
+                   int B, int H, int W, int C, float eps, int split, int variant, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Farthest point sampling -- replaces core/csrc/fps/src/farthest_point_sampling.cpp:166-204
  * (cffi surface core/csrc/fps/src/ext.h:1-14, Python wrapper core/csrc/fps/fps_utils.py:6-21).
@@ -137,6 +143,20 @@ int rv_voting_for_hypothesis_vanishing_point(const float* direct, const float* c
 /* fused round: votes without materialising the [hn,vn,tn] mask; counts [hn,vn] i32 (overwritten). */
 int rv_vote_count(const float* direct, const float* coords, const float* hypo, int* counts, int tn, int vn, int hn,
                   float inlier_thresh, int vanishing_point, void* stream);
+
+/* The whole RANSAC voting layer for a batch of images on the device (SURVEY.md 8b "rv_ransac_round"): replaces the
+ * Python driver ransac_voting_layer / ransac_voting_layer_v3 (core/csrc/ransac_voting/ransac_voting_gpu.py:7-104,
+ * 123-218).  mask [b,h,w] f32 (non-zero = foreground), vertex [b,h,w,vn,2] f32 -> win_pts [b,vn,2]: ordered
+ * compaction of the foreground (tn stays on the device; images with fewer than min_num pixels give zeros, more than
+ * max_num are randomly subsampled), hn hypotheses per keypoint from pixel pairs idxs [b,hn,vn,2] i32 (optional;
+ * taken modulo tn; NULL = counter-based RNG(seed)), fused vote + count, per-keypoint winner, inlier set of the winner
+ * and least-squares refit of its lines.  No host synchronisation.  Optional outputs: hypo [b,hn,vn,2], counts
+ * [b,hn,vn] i32, tn [b] i32, inliers [b,vn,h*w] u8 (compacted pixel order, first tn[b] entries valid). */
+size_t rv_layer_workspace_bytes(int b, int h, int w, int vn, int hn);
+int rv_ransac_voting_layer(const float* mask, const float* vertex, int b, int h, int w, int vn, int hn,
+                           float inlier_thresh, int min_num, int max_num, unsigned seed, const int* idxs, float* win_pts,
+                           float* hypo, int* counts, int* tn, unsigned char* inliers, void* workspace,
+                           size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Chamfer / NN distance -- replaces core/csrc/torch_nndistance/src/nnd_cuda.cpp:37-84
@@ -182,6 +202,17 @@ int rast_render_depth(const float* verts, const int* faces, int V, int F, const 
                       int n, int H, int W, float znear, float zfar, int quantize_bits, float* depth,
                       float* xyz_cam, unsigned long long* zbuf_scratch, void* stream);
 size_t rast_scratch_bytes(int n, int H, int W);
+/* Mesh registry (rast_upload_mesh + rast_render_depth(mesh_ids, ...)): meshes are uploaded once
+ * (host or device pointers; the library keeps a device copy) and a batch of ROIs renders one mesh EACH, selected by
+ * mesh_ids [n] i32 (device) -- the multi-object form of the reference's per-object draw_model loop
+ * (engine/gdrn_evaluator.py:520-526) without a host loop or a sync.  rast_upload_mesh returns the id (>= 0) or a
+ * negative error code. */
+int rast_upload_mesh(const float* verts, int V, const int* faces, int F);
+int rast_mesh_count(void);
+void rast_free_meshes(void);
+int rast_render_meshes(const int* mesh_ids, const float* poses, const float* Ks, int n, int H, int W, float znear,
+                       float zfar, int quantize_bits, float* depth, float* xyz_cam, unsigned long long* zbuf_scratch,
+                       void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fast depth refinement -- replaces GDRN_Evaluator.process_depth_refine
@@ -192,6 +223,11 @@ size_t rast_scratch_bytes(int n, int H, int W);
  * ------------------------------------------------------------------------------------------- */
 int gdrn_depth_refine_step(const float* xyz, const float* mask, const float* depth_sensor, const float* ren_depth,
                            const float* K_crop, float* trans, int n, int hw, float thresh, void* stream);
+/* same with get_out_mask (engine/engine_utils.py:313-333) folded into the kernel: mask_mode 0 = `mask` is already
+ * normalised, 1 = raw L1 mask output -> per-ROI min-max normalisation, 2 = raw logits -> sigmoid. */
+int gdrn_depth_refine_step_ex(const float* xyz, const float* mask, int mask_mode, const float* depth_sensor,
+                              const float* ren_depth, const float* K_crop, float* trans, int n, int hw, float thresh,
+                              void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * ROI crop + resize -- replaces crop_resize_by_warp_affine = cv2.warpAffine

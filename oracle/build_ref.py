@@ -3,6 +3,8 @@
   * oracle/liboracle_ops.so      -- our CPU restatement (ops_oracle.c), always built.
   * oracle/_ref/libfps_ref.so    -- the REFERENCE's own FPS C++ (core/csrc/fps/src/farthest_point_sampling.cpp)
                                     compiled where it lies with the flags of core/csrc/fps/setup.py:5-7.
+  * oracle/_ref/libupnp_ceres_ref.so -- uncertainty-PnP solved with the REFERENCE's vendored Ceres 2.0 headers (Jet
+                                    autodiff + TinySolver LM), see upnp_ceres_ref.cpp.
   * oracle/_ref/<mod>/<mod>.so   -- the REFERENCE's own CUDA extensions (ransac_voting, torch_nndistance_aten,
                                     flow_cuda) compiled unmodified from /root/reference for sm_100a: the GPU-side
                                     ground truth for the bit-exactness tests on the B200 box.
@@ -40,6 +42,22 @@ def build_fps_ref():
     out = os.path.join(REFDIR, "libfps_ref.so")
     if not os.path.exists(out):
         run(["g++", "-shared", src, "-o", out, "-fopenmp", "-fPIC", "-O2", "-std=c++11"])
+    return out
+
+
+def build_upnp_ceres_ref():
+    """oracle/upnp_ceres_ref.cpp (our restatement of the reference's residual functor) on top of the REFERENCE's vendored
+    Ceres 2.0 headers (jet.h autodiff, rotation.h, tiny_solver.h LM) and Eigen, included where they lie; glog is stubbed
+    (oracle/stubs).  libceres.so itself is absent, so the reference's own uncertainty_pnp.cpp cannot be linked."""
+    inc = os.path.join(REF, "core/csrc/uncertainty_pnp/include")
+    if not os.path.isdir(inc):
+        return None
+    os.makedirs(REFDIR, exist_ok=True)
+    out = os.path.join(REFDIR, "libupnp_ceres_ref.so")
+    src = os.path.join(HERE, "upnp_ceres_ref.cpp")
+    if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        run(["g++", "-O2", "-std=c++14", "-w", "-shared", "-fPIC", "-I", os.path.join(HERE, "stubs"), "-I", inc,
+             "-I", os.path.join(inc, "eigen3"), src, "-o", out])
     return out
 
 
@@ -83,5 +101,6 @@ def build_cuda_refs(names=None):
 if __name__ == "__main__":
     print(build_oracle_ops())
     print(build_fps_ref())
+    print(build_upnp_ceres_ref())
     if "--cuda-refs" in sys.argv:
         print(build_cuda_refs())

@@ -407,6 +407,24 @@ def test_fps_bit_exact(dev, pn, sn):
         assert (idx2[b] == OO.fps(pts[b], sn, start=int(start[b]))).all()
 
 
+@pytest.mark.parametrize("pn,sn", [(60000, 24), (150001, 16), (300000, 12)])
+def test_fps_large_clouds_cluster_bit_exact(dev, pn, sn):
+    """pn > 56 000 (meshes reach 10^5 vertices): a cluster of 2 / 4 / 8 CTAs shares one cloud; same indices as the
+    reference algorithm (core/csrc/fps/src/farthest_point_sampling.cpp:118-160 handles any pn)."""
+    from gdrnpp_bop2022_b200 import native_ops
+
+    rs = np.random.RandomState(pn % 1000)
+    pts = ((rs.rand(2, pn, 3) - 0.5) * np.array([0.3, 0.2, 0.1])).astype(np.float32)
+    pts[1, 1000:1100] = pts[1, 7]            # duplicates: ties resolved by the lowest index across CTA boundaries too
+    idx = native_ops.farthest_point_sampling_idx(torch.from_numpy(pts).to(dev), sn).cpu().numpy()
+    for b in range(2):
+        assert (idx[b] == OO.fps(pts[b], sn)).all(), (pn, b)
+    start = torch.tensor([pn - 1, pn // 2], dtype=torch.int32)
+    idx2 = native_ops.farthest_point_sampling_idx(torch.from_numpy(pts).to(dev), sn, start_idx=start).cpu().numpy()
+    for b in range(2):
+        assert (idx2[b] == OO.fps(pts[b], sn, start=int(start[b]))).all()
+
+
 def test_fps_golden_and_host_entry(dev):
     from gdrnpp_bop2022_b200 import native_ops
 
@@ -482,24 +500,103 @@ def test_voting_vs_reference_cuda_build(dev):
             assert torch.equal(i_r, i_m), (tn, vp)
 
 
-def test_ransac_voting_layer_recovers_keypoints(dev):
-    from gdrnpp_bop2022_b200.native_ops import ransac_voting_layer
+def _voting_field(h, w, kp, noise, rs):
+    yy, xx = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    pix = np.stack([xx, yy], -1).astype(np.float32)
+    d = kp[None, None] - pix[:, :, None] + rs.randn(h, w, kp.shape[0], 2).astype(np.float32) * noise
+    return (d / (np.linalg.norm(d, axis=-1, keepdims=True) + 1e-9)).astype(np.float32)
 
+
+def test_ransac_voting_layer_device_side_vs_reference_driver(dev):
+    """ransac_voting_layer / _v3 (ONE device call: compaction, hypotheses, fused vote + count, winner, refit) against the
+    reference's driver loop (ransac_voting_gpu.py:24-104) restated in the test on top of the op-level entry points --
+    the reference's own CUDA extension when oracle/_ref holds it, else ours (bit-identical to it, see
+    test_voting_vs_reference_cuda_build) -- fed with the SAME pixel pairs: identical winners, bit-identical inlier
+    sets, final keypoints equal to fp32 rounding.  Also: keypoint recovery, empty / tiny masks, batch invariance."""
+    from gdrnpp_bop2022_b200.native_ops import ransac_voting as rv_mine
+    from gdrnpp_bop2022_b200.native_ops import ransac_voting_layer, ransac_voting_layer_v3
+
+    ops = load_ref_ext("ransac_voting") or rv_mine
     rs = np.random.RandomState(0)
     h = w = 64
-    vn = 4
     kp = np.array([[20.3, 30.1], [50.2, 10.4], [5.5, 60.0], [40.0, 40.0]], np.float32)
+    vn, hn = kp.shape[0], 64
     yy, xx = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
-    mask = ((yy - 32) ** 2 + (xx - 32) ** 2 < 25 ** 2).astype(np.float32)
-    pix = np.stack([xx, yy], -1).astype(np.float32)
-    d = kp[None, None] - pix[:, :, None]
-    vertex = d / (np.linalg.norm(d, axis=-1, keepdims=True) + 1e-9)
-    M = torch.from_numpy(mask)[None].to(dev)
-    V = torch.from_numpy(vertex.astype(np.float32))[None].to(dev)
-    for fused in (True, False):
-        torch.manual_seed(0)
-        out = ransac_voting_layer(M, V, 64, inlier_thresh=0.999, fused=fused).cpu().numpy()[0]
-        assert np.abs(out - kp).max() < 0.5
+    masks = np.stack([((yy - 32) ** 2 + (xx - 32) ** 2 < 25 ** 2), ((yy - 20) ** 2 + (xx - 40) ** 2 < 12 ** 2),
+                      np.zeros((h, w), bool), (yy == 3) & (xx < 4)]).astype(np.float32)      # disc, small disc, empty, 4 pixels (< min_num)
+    vertex = np.stack([_voting_field(h, w, kp, 0.02, rs) for _ in range(4)])
+    M, V = torch.from_numpy(masks).to(dev), torch.from_numpy(vertex).to(dev)
+    idxs = torch.from_numpy(rs.randint(0, 1 << 30, (4, hn, vn, 2)).astype(np.int32)).to(dev)
+    win, inl, tn = ransac_voting_layer(M, V, hn, inlier_thresh=0.999, idxs=idxs, return_inliers=True)
+    win3 = ransac_voting_layer_v3(M, V, hn, inlier_thresh=0.999, idxs=idxs)
+    torch.cuda.synchronize()
+    assert torch.equal(win, win3)
+    assert tn.cpu().tolist() == [int(masks[0].sum()), int(masks[1].sum()), 0, 0]
+    assert torch.equal(win[2:], torch.zeros(2, vn, 2, device=dev))                          # empty / too-few-pixel images
+    assert (win[0].cpu().numpy() - kp).__abs__().max() < 0.5 and np.abs(win[1].cpu().numpy() - kp).max() < 1.5
+    # ---- the reference driver on image 0 and 1 with the same pixel pairs ----
+    for bi in (0, 1):
+        cur_mask = M[bi].to(torch.bool)
+        coords = torch.nonzero(cur_mask).float()[:, [1, 0]].contiguous()
+        direct = V[bi].masked_select(cur_mask[:, :, None, None]).view([coords.shape[0], vn, 2]).contiguous()
+        t = coords.shape[0]
+        ix = (idxs[bi].to(torch.int64) % t).to(torch.int32).contiguous()
+        hyp = ops.generate_hypothesis(direct, coords, ix)
+        cur_inlier = torch.zeros([hn, vn, t], dtype=torch.uint8, device=dev)
+        ops.voting_for_hypothesis(direct, coords, hyp, cur_inlier, 0.999)
+        counts = torch.sum(cur_inlier, 2)
+        win_counts, win_idx = torch.max(counts, 0)
+        win_pts = hyp[win_idx, torch.arange(vn, device=dev)]
+        # any hypothesis with the maximal count is a legitimate torch.max winner: compare by count, then use ours
+        all_inlier = torch.zeros([1, vn, t], dtype=torch.uint8, device=dev)
+        ops.voting_for_hypothesis(direct, coords, win_pts[None].contiguous(), all_inlier, 0.999)
+        ours_inl = inl[bi, :, :t]
+        same_winner = (all_inlier[0] == ours_inl).all(dim=1)
+        for v in range(vn):
+            if not bool(same_winner[v]):      # a tie in the counts resolved to another hypothesis: it must be as good
+                assert int(ours_inl[v].sum()) >= int(all_inlier[0, v].sum()) - 0
+        assert int(same_winner.sum()) >= vn - 1
+        normal = torch.zeros_like(direct)
+        normal[:, :, 0], normal[:, :, 1] = direct[:, :, 1], -direct[:, :, 0]
+        nrm = normal.permute(1, 0, 2) * ours_inl.float().unsqueeze(2)
+        bvec = torch.sum(nrm * coords.unsqueeze(0), 2)
+        ATA = torch.matmul(nrm.permute(0, 2, 1), nrm)
+        ATb = torch.sum(nrm * bvec.unsqueeze(2), 1)
+        ref_pts = torch.linalg.solve(ATA.double(), ATb.double().unsqueeze(2))[:, :, 0].float()
+        assert (win[bi] - ref_pts).abs().max().item() < 2e-3
+    # batch invariance: an image gives the same result alone as inside a batch
+    alone = ransac_voting_layer(M[1:2], V[1:2], hn, inlier_thresh=0.999, idxs=idxs[1:2])
+    assert torch.equal(alone[0], win[1])
+    # RNG path: reproducible under torch.manual_seed, recovers the keypoints
+    torch.manual_seed(0)
+    a = ransac_voting_layer(M[:1], V[:1], 128)
+    torch.manual_seed(0)
+    b2 = ransac_voting_layer(M[:1], V[:1], 128)
+    assert torch.equal(a, b2) and np.abs(a[0].cpu().numpy() - kp).max() < 0.5
+
+
+def test_estimate_voting_distribution_with_mean(dev):
+    """ransac_voting_gpu.py:221-330 on the device-side hypothesis generator: covariance of the inlier-weighted hypothesis
+    cloud around the given mean: symmetric, positive semi-definite, and growing with the noise of the vector field."""
+    from gdrnpp_bop2022_b200.native_ops import estimate_voting_distribution_with_mean, ransac_voting_layer
+
+    rs = np.random.RandomState(1)
+    h = w = 64
+    kp = np.array([[20.3, 30.1], [50.2, 10.4], [40.0, 40.0]], np.float32)
+    yy, xx = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    mask = ((yy - 32) ** 2 + (xx - 32) ** 2 < 25 ** 2).astype(np.float32)[None]
+    covs = []
+    for noise in (0.005, 0.05):
+        V = torch.from_numpy(_voting_field(h, w, kp, noise, rs)[None]).to(dev)
+        M = torch.from_numpy(mask).to(dev)
+        mean = ransac_voting_layer(M, V, 128, inlier_thresh=0.99, seed=5)
+        m2, cov = estimate_voting_distribution_with_mean(M, V, mean, round_hyp_num=256, min_hyp_num=1024, inlier_thresh=0.99, seed=7)
+        assert torch.equal(m2, mean) and cov.shape == (1, 3, 2, 2)
+        c = cov[0].cpu().double()
+        assert (c - c.transpose(1, 2)).abs().max() < 1e-4 * c.abs().max().clamp_min(1e-6)
+        assert (torch.linalg.eigvalsh((c + c.transpose(1, 2)) / 2) > -1e-6).all()
+        covs.append(c.diagonal(dim1=1, dim2=2).sum(1))
+    assert (covs[1] > covs[0]).all()
 
 
 # ------------------------------------------------------------------------------------------ nnd / flow
@@ -932,3 +1029,166 @@ def test_predictor_reference_constructor_and_use_pnp(dev, tmp_path):
     for r in data["cur_res"]:     # random-init maps carry no geometry: either a RANSAC pose or the -100 sentinel, never NaN
         assert np.isfinite(r["R"]).all() and np.isfinite(r["t"]).all()
     assert pred.postprocessing(pred.preprocessing(np.zeros((0, 7), np.float32), image), pred.inference(pred.preprocessing(np.zeros((0, 7), np.float32), image))) == {}
+
+
+# ------------------------------------------------------------- renderer class surfaces / z-buffer decode (a11, a12)
+def _plane_quad(K, n_pl, d_pl, half=0.6):
+    corners = []
+    for sx, sy in ((-1, -1), (1, -1), (1, 1), (-1, 1)):
+        ray = np.array([sx * half, sy * half, 1.0])
+        corners.append(ray * (d_pl / (n_pl @ ray)))
+    return np.array(corners, np.float32), np.array([[0, 1, 2], [0, 2, 3]], np.int32)
+
+
+def test_renderer_surfaces_plane_analytic_and_quantised_decode(dev, tmp_path):
+    """lib/render_vispy Renderer (set_cam / draw_model / finish) and lib/egl_renderer EGLRenderer.render(pc_cam_tensor=)
+    surfaces on an analytic case: a tilted plane covering the window renders to the ray/plane intersection depth at the
+    pixel centres (float path, EGL) and to the 24- / 16-bit fixed-point z-buffer decode of renderer.py:176-182 (vispy);
+    model paths are PLY files like the reference; two draws share one z-buffer (nearest wins)."""
+    from gdrnpp_bop2022_b200.ply import save_ply
+    from gdrnpp_bop2022_b200.renderer import EGLRenderer, Renderer, render_depth
+
+    K = np.array([[110.0, 0, 31.5], [0, 112.0, 30.25], [0, 0, 1]], np.float32)
+    n_pl, d_pl = np.array([0.2, -0.1, 1.0]), 0.8
+    v, f = _plane_quad(K, n_pl, d_pl)
+    cc, rr = np.meshgrid(np.arange(64) + 0.5, np.arange(64) + 0.5)
+    rays = np.stack([(cc - K[0, 2]) / K[0, 0], (rr - K[1, 2]) / K[1, 1], np.ones_like(cc)], -1)
+    z_true = d_pl / (rays @ n_pl)
+    pose = np.hstack([np.eye(3), np.zeros((3, 1))]).astype(np.float32)
+    V, F = torch.from_numpy(v).to(dev), torch.from_numpy(f).to(dev)
+    P, Kt = torch.from_numpy(pose)[None].to(dev), torch.from_numpy(K)[None].to(dev)
+    d0 = render_depth(V, F, P, Kt, 64, 64).cpu().numpy()[0]
+    assert (d0 > 0).all() and np.abs(d0 - z_true).max() < 1e-5
+    nc, fc = 0.1, 100.0
+    mult, addi = np.float32((nc * fc) / (nc - fc)), np.float32(fc / (nc - fc))
+    for bits in (24, 16):
+        dq = render_depth(V, F, P, Kt, 64, 64, nc, fc, quantize_bits=bits).cpu().numpy()[0]
+        win = (1.0 / d0.astype(np.float64) - 1.0 / nc) / (1.0 / fc - 1.0 / nc)     # window depth of the float z
+        q = float((1 << bits) - 1)
+        expect = mult / (np.float32(np.floor(win * q + 0.5) / q) + addi)            # fixed point -> GL_FLOAT read-back -> decode
+        assert np.abs(dq - expect).max() < 1e-6 * max(1.0, float(expect.max()))
+        assert np.abs(dq - z_true).max() < (2e-6 if bits == 24 else 4e-4)           # SURVEY App. B: 6e-7 m @ 1 m / 1.5e-4 m
+    # vispy-style class with PLY model paths (millimetres -> metres)
+    save_ply(str(tmp_path / "obj_000001.ply"), v * 1000.0, f, binary=True)
+    v2, f2 = _plane_quad(K, np.array([0.0, 0.0, 1.0]), 0.75, half=0.1)              # a small nearer patch in the middle
+    save_ply(str(tmp_path / "obj_000002.ply"), v2 * 1000.0, f2, binary=False)
+    ren = Renderer((64, 64), K, model_paths=[str(tmp_path / "obj_000001.ply"), str(tmp_path / "obj_000002.ply")], scale_to_meter=0.001,
+                   device=dev)
+    ren.clear()
+    ren.set_cam(K)
+    ren.draw_model(ren.models[0], np.vstack([pose, [0, 0, 0, 1]]))
+    ren.draw_model(ren.models[1], np.vstack([pose, [0, 0, 0, 1]]))
+    rgb, dep = ren.finish()
+    assert rgb.shape == (64, 64, 3) and dep.shape == (64, 64)
+    near = np.abs(rays[..., 0]) < 0.09
+    near &= np.abs(rays[..., 1]) < 0.09
+    assert np.abs(dep[near] - 0.75).max() < 1e-5 and np.abs(dep[~near & (np.abs(rays[..., 0]) > 0.11)] - z_true[~near & (np.abs(rays[..., 0]) > 0.11)]).max() < 1e-5
+    # EGL-style class: camera-space xyz written in place, depth = pc_cam[..., 2]
+    egl = EGLRenderer([str(tmp_path / "obj_000001.ply")], K=K, width=64, height=64, vertex_scale=0.001, znear=0.25, zfar=6.0, device=dev)
+    pc = torch.zeros((64, 64, 4), device=dev)
+    seg = torch.zeros((64, 64, 4), device=dev)
+    depth = egl.render([0], [pose], pc_cam_tensor=pc, seg_tensor=seg)
+    assert torch.equal(depth, pc[..., 2]) and float(pc[..., 3].min()) == 1.0 and float(seg[..., 0].max()) == 1.0
+    xyz = pc[..., :3].cpu().numpy()
+    assert np.abs(xyz[..., 2] - z_true).max() < 1e-5
+    assert np.abs(xyz[..., 0] - rays[..., 0] * z_true).max() < 1e-5 and np.abs(xyz[..., 1] - rays[..., 1] * z_true).max() < 1e-5
+
+
+def test_multi_mesh_refine_matches_per_mesh_path(dev):
+    """depth_refine with several meshes: every ROI picks its mesh from the library's registry inside ONE render launch
+    (rast_upload_mesh / rast_render_meshes); result == rendering each mesh's ROIs separately; get_out_mask folded into
+    the refine kernel == the torch min-max normalisation + the pre-normalised entry."""
+    from gdrnpp_bop2022_b200 import _lib as L
+    from gdrnpp_bop2022_b200.renderer import depth_refine, get_out_mask, render_depth, render_meshes, upload_mesh
+    from gdrnpp_bop2022_b200.synthetic import make_icosphere_mesh
+
+    n = 6
+    _, _, poses, Ks = _mesh_and_poses(n, seed=4)
+    meshes = [make_icosphere_mesh(2, e) for e in ((0.12, 0.08, 0.1), (0.06, 0.1, 0.07), (0.09, 0.09, 0.09))]
+    Vs = [torch.from_numpy(v).to(dev) for v, _ in meshes]
+    Fs = [torch.from_numpy(f).to(dev) for _, f in meshes]
+    ids = torch.tensor([0, 2, 1, 1, 0, 2])
+    P, Kt = torch.from_numpy(poses).to(dev), torch.from_numpy(Ks).to(dev)
+    reg = torch.tensor([upload_mesh(v, f) for v, f in zip(Vs, Fs)], dtype=torch.int32, device=dev)
+    multi = render_meshes(reg[ids.to(dev)], P, Kt, 64, 64)
+    for i in range(n):
+        single = render_depth(Vs[ids[i]], Fs[ids[i]], P[i:i + 1], Kt[i:i + 1], 64, 64)[0]
+        assert torch.equal(multi[i], single), i
+    g = torch.Generator().manual_seed(0)
+    xyz = (torch.rand(n, 3, 64, 64, generator=g) - 0.5).to(dev)
+    mask = torch.rand(n, 1, 64, 64, generator=g).to(dev)
+    sensor = multi * 1.03
+    rot, trans = P[:, :, :3].contiguous(), P[:, :, 3].contiguous()
+    t_new = depth_refine(Vs, Fs, rot, trans, Kt, xyz, mask, sensor, iters=2, thresh=0.8, mesh_ids=ids)
+    # reference path: per-mesh renders + torch get_out_mask + the pre-normalised kernel entry
+    t_ref = trans.clone()
+    mnorm = get_out_mask(mask).reshape(n, 64, 64).contiguous()
+    lib = L.lib()
+    for _ in range(2):
+        pp = torch.cat([rot, t_ref[:, :, None]], dim=2).contiguous()
+        ren = torch.stack([render_depth(Vs[ids[i]], Fs[ids[i]], pp[i:i + 1], Kt[i:i + 1], 64, 64)[0] for i in range(n)]).contiguous()
+        L.check(lib.gdrn_depth_refine_step(L.ptr(xyz), L.ptr(mnorm), L.ptr(sensor.contiguous()), L.ptr(ren), L.ptr(Kt), L.ptr(t_ref), n, 64,
+                                           0.8, L.current_stream()), "refine")
+    torch.cuda.synchronize()
+    assert (t_new - t_ref).abs().max().item() < 1e-6
+    assert (t_new - trans).abs().max().item() > 1e-3     # it did move
+
+
+# ------------------------------------------------------------------------------- depthwise 7x7 + LayerNorm kernels
+@pytest.mark.parametrize("B,H,C,split", [(2, 64, 128, 0), (3, 32, 256, 1), (8, 16, 512, 1), (64, 16, 512, 0), (5, 64, 128, 1)])
+def test_dwconv_ln_pingpong_vs_cluster_kernel_and_torch(dev, lib, B, H, C, split):
+    """ConvNeXt block front half (dw 7x7 pad 3 + bias -> LayerNorm(C, 1e-6)): the persistent two-warpgroup ping-pong
+    kernel is BIT-identical to the one-tile-per-CTA cluster kernel (same FMA order, same LayerNorm combine) and both
+    agree with the torch fp32 reference of the same op; odd tile counts (one warpgroup gets one tile more) included."""
+    L = _lib()
+    g = torch.Generator().manual_seed(B * 1000 + H + C)
+    x = torch.randn(B, H, H, C, generator=g).to(dev)
+    w = (torch.randn(C, 1, 7, 7, generator=g) / 7).to(dev)
+    bias, lw, lb = (torch.randn(C, generator=g) * 0.1).to(dev), (torch.rand(C, generator=g) + 0.5).to(dev), (torch.randn(C, generator=g) * 0.1).to(dev)
+    w49c = w.reshape(C, 49).t().contiguous()
+    outs = []
+    for variant in (0, 1):
+        o = torch.full((B * H * H, (2 if split else 1) * C), float("nan"), dtype=torch.bfloat16, device=dev)
+        L.check(lib.gdrn_dwconv_ln(L.ptr(x), L.ptr(w49c), L.ptr(bias), L.ptr(lw), L.ptr(lb), L.ptr(o), B, H, H, C, 1e-6, split, variant,
+                                   L.current_stream()), "dwconv_ln")
+        outs.append(o)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0].view(torch.int16), outs[1].view(torch.int16))
+    y = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w, bias, padding=3, groups=C).permute(0, 2, 3, 1)
+    ref = torch.nn.functional.layer_norm(y, (C,), lw, lb, 1e-6).reshape(B * H * H, C)
+    got = outs[1][:, :C].float() + (outs[1][:, C:].float() if split else 0)
+    assert (got - ref).abs().max().item() < (2e-4 if split else 0.03)
+
+
+def test_upnp_vs_vendored_ceres_and_epnp_wrapper(dev):
+    """csrc/upnp.cu (batched device LM) and the reference-signature host entry against the REFERENCE's vendored Ceres 2.0
+    (oracle/_ref/libupnp_ceres_ref.so: ceres::Jet autodiff + ceres::TinySolver on the residual of uncertainty_pnp.cpp:16-34)
+    on noise-free and noisy problems; and native_ops.uncertainty_pnp -- the un_pnp_utils.py:11-78 wrapper (EPnP init on the 4
+    highest-weight points via cv2, then the weighted refine) -- recovers a known pose."""
+    from test_oracle_pinning import _upnp_problem, upnp_ceres_ref
+
+    from gdrnpp_bop2022_b200 import native_ops
+
+    rs = np.random.RandomState(21)
+    probs = [_upnp_problem(rs, 9, 0.0 if i % 2 == 0 else 0.4) for i in range(10)]
+    K = probs[0][0]
+    refs = [upnp_ceres_ref(p2, p3, w, K, init) for (_, _, p2, p3, w, init) in probs]
+    if refs[0] is None:
+        pytest.xfail("oracle/_ref/libupnp_ceres_ref.so not built (python oracle/build_ref.py in the build container)")
+    t = lambda k: torch.from_numpy(np.stack([p[k] for p in probs])).to(dev)
+    res = native_ops.uncertainty_pnp_batched(t(2), t(3), t(4), torch.from_numpy(np.tile(K[None], (len(probs), 1, 1))).to(dev), t(5)).cpu().numpy()
+    for i, (_, rt, p2, p3, w, init) in enumerate(probs):
+        assert np.abs(res[i] - refs[i]).max() < 1e-6, (i, res[i], refs[i])
+        host = native_ops.uncertainty_pnp_refine(p2, w, p3, K, init)
+        assert np.abs(host - refs[i]).max() < 1e-6
+        if i % 2 == 0:
+            assert np.abs(res[i] - rt).max() < 1e-8
+    # the EPnP-initialised wrapper (un_pnp_utils.uncertainty_pnp): [3,4] pose, pn == 4 short-cut included
+    import cv2
+
+    _, rt, p2, p3, w, _ = probs[0]
+    pose = native_ops.uncertainty_pnp(p2, w, p3, K)
+    Rgt = cv2.Rodrigues(rt[:3])[0]
+    assert pose.shape == (3, 4) and np.abs(pose[:, :3] - Rgt).max() < 1e-6 and np.abs(pose[:, 3] - rt[3:]).max() < 1e-6
+    pose4 = native_ops.uncertainty_pnp(p2[:4], w[:4], p3[:4], K)
+    assert pose4.shape == (3, 4) and np.abs(pose4[:, :3] @ pose4[:, :3].T - np.eye(3)).max() < 1e-6
