@@ -1,6 +1,6 @@
 // Depthwise 7x7 + bias + LayerNorm(C) -> GEMM A operand: PERSISTENT, two-warpgroup ping-pong version for the
 // 16x8-pixel x 64-channel tiles of ConvNeXt stages 0-2 (33 of the 36 blocks).  Reference op: timm ConvNeXtBlock
-// conv_dw (7x7, groups = C) -> LayerNorm(C, eps 1e-6) (third-party timm 0.6.7; restated in oracle/gdrn_model_oracle.py).
+// conv_dw (7x7, groups = C) -> LayerNorm(C, eps 1e-6) (third-party timm 0.6.7, un-vendored).
 //
 // Why: the one-tile-per-CTA kernel (dense_ops.cu, dwconv_ln_cluster_kernel) spends only ~40 % of a CTA's life in the
 // convolution (FMA pipe); TMA load wait, the LayerNorm exchange across the channel-slice cluster and the output stores do
