@@ -268,6 +268,32 @@ int gdrn_pnp_ransac_points(const float* pts3d, const float* pts2d, const float* 
                            int iters, float reproj_thr, unsigned seed, float* poses, int* n_inliers,
                            unsigned char* inlier_mask, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Online training targets -- after rast_render_meshes, replaces the torch ops of
+ * core/gdrn_modeling/engine/engine_utils.py:131-187: misc.calc_xyz_bp_batch (lib/pysixd/misc.py:412-457),
+ * roi_mask_obj, xyz_to_region_batch (core/utils/data_utils.py:283-301) and the xyz normalisation, in one kernel.
+ *   depth [n,H,W], R [n,3,3] (ego rotation), T [n,3], K [n,3,3] (zoomed intrinsics), fps_points [n,F,3], extents [n,3]
+ *   -> roi_xyz [n,3,H,W] (xyz / extent + 0.5), xyz_raw [n,H,W,3] (object-space xyz), mask_obj [n,H,W] f32,
+ *      region [n,H,W] i64 (1..F, 0 = background).  Any output may be NULL.
+ * ------------------------------------------------------------------------------------------- */
+int gdrn_xyz_region_targets(const float* depth, const float* R, const float* T, const float* K, const float* fps_points,
+                            const float* extents, int n, int H, int W, int F, float* roi_xyz, float* xyz_raw,
+                            float* mask_obj, long long* region, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * YOLOX head post-processing -- replaces YOLOXHead.decode_outputs
+ * (det/yolox/models/yolo_head.py:239-255) and postprocess (det/yolox/utils/boxes.py:34-80: cxcywh -> xyxy, class
+ * max, obj * cls_conf >= conf_thre, torchvision batched_nms / nms) for a batch of images, no host synchronisation.
+ *   preds [B, A, 5 + num_classes] f32 (obj / class scores already sigmoid-ed like the head emits them);
+ *   n_levels > 0: raw head outputs, decoded here with hw [n_levels,2] i32 (rows, cols per level) and strides [n_levels]
+ *   i32 (both device arrays); n_levels = 0: preds are already decoded (cx, cy, w, h).
+ *   dets [B, max_out, 7] = (x1, y1, x2, y2, obj_conf, class_conf, class) in descending score order, n_det [B] i32.
+ * ------------------------------------------------------------------------------------------- */
+size_t yolox_postprocess_workspace_bytes(int B, int A);
+int yolox_postprocess(const float* preds, int B, int A, int num_classes, const int* hw, const int* strides, int n_levels,
+                      float conf_thre, float nms_thre, int class_agnostic, int max_out, float* dets, int* n_det,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,7 +9,9 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-rows = list(csv.reader(open(os.path.join(ROOT, "gpurun_out", "traffic.csv"))))
+src_csv = sys.argv[2] if len(sys.argv) > 2 else "traffic.csv"
+build = sys.argv[3] if len(sys.argv) > 3 else ""
+rows = list(csv.reader(open(os.path.join(ROOT, "gpurun_out", src_csv))))
 hdr, data = None, []
 for r in rows:
     if len(r) > 5 and r[0] == "ID":
@@ -39,14 +41,15 @@ assert len(st) >= 2, "need at least one full step in the capture"
 step = [per[k] for k in ids[st[0]:st[1]]]
 agg = collections.defaultdict(lambda: {"launches": 0, "dram_read": 0.0, "dram_write": 0.0, "us": 0.0})
 for k in step:
-    fam = "gemm (gemm_tc_kernel + gemm_pair_kernel, all tcgen05 launches)" if k["name"].startswith(("gemm_tc_kernel", "gemm_pair_kernel")) else k["name"]
+    fam = ("gemm (gemm_tc_kernel + gemm_pair_kernel + gemm_pair_x3_kernel + mlp_fused_kernel, all tcgen05 launches)"
+           if k["name"].startswith(("gemm_tc_kernel", "gemm_pair_kernel", "gemm_pair_x3_kernel", "mlp_fused_kernel")) else k["name"])
     a = agg[fam]
     a["launches"] += 1
     a["dram_read"] += k.get("dram__bytes_read.sum", 0)
     a["dram_write"] += k.get("dram__bytes_write.sum", 0)
     a["us"] += k.get("us", 0)
 out = {"source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none, "
-                 "one bench step (B=64), cold caches", "step_kernels": len(step), "families": {}}
+                 "one bench step (B=64), cold caches", "build": build, "step_kernels": len(step), "families": {}}
 for f, a in agg.items():
     out["families"][f] = {"launches": a["launches"],
                           "dram_bytes_per_launch": (a["dram_read"] + a["dram_write"]) / a["launches"],
