@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/gdrn_b200.h"
 
@@ -58,8 +59,47 @@ static inline int gdrn_num_sms() {
     }                                                                                                            \
   } while (0)
 
+
+// ---- programmatic dependent launch (PDL) ----
+// Every kernel of the per-ROI step is launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel's
+// CTAs are placed on SMs as the previous kernel's CTAs retire and run their prologue (barrier init, TMEM allocation,
+// tensor-map prefetch, filter-tap loads) under the previous kernel's tail; ptx::griddep_wait() then holds them until the
+// previous grid has completed and flushed.  CONTRACT: a kernel launched through gdrn_launch_dep() executes
+// ptx::griddep_launch() first and ptx::griddep_wait() in EVERY thread before its first access to global memory that another
+// kernel of the stream writes or reads (and before any early return), so that completion stays transitive along the chain.
+// Works under stream capture (programmatic graph edges).  GDRN_PDL=0: plain stream-ordered launches.
+inline bool gdrn_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GDRN_PDL"); v = e ? atoi(e) : 1; }
+  return v != 0;
+}
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t gdrn_launch_dep(void (*kfn)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int n = 0;
+  if (gdrn_pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kfn, static_cast<KArgs>(args)...);
+}
+#endif
+
 #ifdef __CUDACC__
 namespace ptx {
+
+// PDL (see gdrn_launch_dep): let the dependent grid start its prologue / wait for the prerequisite grid's results
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -347,6 +387,69 @@ __device__ __forceinline__ float gelu_erf(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * (z * -1.4426950408889634f)));
   const float h = p * e;
   return x * (x >= 0.0f ? 1.0f - h : h);
+}
+
+// ---- packed fp32 (sm_100: FFMA2 / FMUL2 / FADD2, two lanes per instruction on the FMA pipe) ----
+// A three-register scalar FFMA issues every second cycle per scheduler; the packed forms carry two results per issue, so
+// FMA-pipe-bound epilogues and the depthwise convolution evaluate element PAIRS.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2_t f2_dup(float v) { return f2_pack(v, v); }
+__device__ __forceinline__ float2 f2_unpack(f32x2_t v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2_t f2_mul(f32x2_t a, f32x2_t b) {
+  f32x2_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2_t f2_add(f32x2_t a, f32x2_t b) {
+  f32x2_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2_t f2_sub(f32x2_t a, f32x2_t b) {
+  f32x2_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// gelu_erf for an element pair: the same A&S 7.1.26 evaluation, 16 packed FMA-pipe instructions per PAIR (incl. none of
+// the selects: Phi = 0.5 + copysign(0.5 - h, x), the sign moved with one LOP3 per element on the ALU pipe) + 4 MUFU.
+__device__ __forceinline__ f32x2_t gelu_erf2(f32x2_t x) {
+  const float2 xf = f2_unpack(x);
+  const f32x2_t z = f2_mul(x, f2_dup(0.70710678118654752440f));                 // signed; only z^2 and |z| are used
+  const float2 zf = f2_unpack(z);
+  const f32x2_t ta = f2_fma(f2_pack(fabsf(zf.x), fabsf(zf.y)), f2_dup(0.3275911f), f2_dup(1.0f));
+  const float2 taf = f2_unpack(ta);
+  float t0, t1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(taf.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(taf.y));
+  const f32x2_t t = f2_pack(t0, t1);
+  f32x2_t p = f2_fma(f2_dup(0.5f * 1.061405429f), t, f2_dup(0.5f * -1.453152027f));
+  p = f2_fma(p, t, f2_dup(0.5f * 1.421413741f));
+  p = f2_fma(p, t, f2_dup(0.5f * -0.284496736f));
+  p = f2_fma(p, t, f2_dup(0.5f * 0.254829592f));
+  p = f2_mul(p, t);
+  const float2 ea = f2_unpack(f2_mul(f2_mul(z, z), f2_dup(-1.4426950408889634f)));
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(ea.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(ea.y));
+  const float2 a = f2_unpack(f2_sub(f2_dup(0.5f), f2_mul(p, f2_pack(e0, e1))));   // 0.5 - h >= 0 (h <= 0.5)
+  const float s0 = __uint_as_float(__float_as_uint(a.x) | (__float_as_uint(xf.x) & 0x80000000u));
+  const float s1 = __uint_as_float(__float_as_uint(a.y) | (__float_as_uint(xf.y) & 0x80000000u));
+  return f2_mul(x, f2_add(f2_pack(s0, s1), f2_dup(0.5f)));
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {

@@ -18,6 +18,8 @@ namespace {
 
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_kernel(const float* __restrict__ src, void* __restrict__ dst, int dst_is_bf16, PackDesc d) {
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   // d.lo_delta > 0 (bf16 only): also write lo = bf16(v - float(bf16(v))) at offset + lo_delta (split-bf16 weights)
   const long long total = d.dims[0] * d.dims[1] * d.dims[2] * d.dims[3];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -43,6 +45,8 @@ __global__ void pack_kernel(const float* __restrict__ src, void* __restrict__ ds
 // stem patchify: one thread per output pixel writes one 128-byte row.
 __global__ void stem_patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int H,
                                      int W, int split) {
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   const int OW = W / 4, OH = H / 4;
   const long long total = (long long)B * OH * OW;
   const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -92,6 +96,8 @@ __global__ void __launch_bounds__(256)
 dwconv_ln_kernel(const float* __restrict__ x, const float* __restrict__ w49c, const float* __restrict__ bias,
                  const float* __restrict__ ln_w, const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out,
                  int B, int H, int W, int C, float eps) {
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   __shared__ float red[8][TW];  // [warp][pixel]
   const int cq = C >> 2;                 // threads per strip
   const int S = 256 / cq;                // strips per block
@@ -232,6 +238,8 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                          const float* __restrict__ bias, const float* __restrict__ ln_w,
                          const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out, int B, int H, int W, int C,
                          float eps, int split, long long* trace) {
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   static_assert(R == 1 || R == 2, "rows per thread");
   const bool trc = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == B / 2 && threadIdx.x == 0;
   long long tt[6];
@@ -413,6 +421,8 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 ln_patchify2_kernel(const float* __restrict__ x, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                     __nv_bfloat16* __restrict__ out, int B, int H, int W, float eps, int split) {
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   constexpr int C = 128 * NV;
   const int OW = W / 2, OH = H / 2;
   const long long m2 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -511,6 +521,8 @@ __device__ __forceinline__ void store8_split(__nv_bfloat16* dst, const float (&o
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n;
        i += (long long)gridDim.x * blockDim.x * 4) {
     if (i + 3 < n) {
@@ -528,6 +540,8 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
 
 // fp32 [rows, C] -> split bf16 [rows, 2C] = [hi C | lo C]
 __global__ void cast_split_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long rows, int C) {
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   const long long total = rows * (C / 8);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / (C / 8);
@@ -539,6 +553,8 @@ __global__ void cast_split_kernel(const float* __restrict__ src, __nv_bfloat16* 
 }
 
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n) {
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     dst[i] = __bfloat162float(src[i]);
 }
@@ -548,6 +564,8 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, float*
 // per-(image, group) mean / rstd from the double sums accumulated by the conv epilogue
 __global__ void gn_finalize_kernel(const double* __restrict__ stats, float2* __restrict__ mr, int n_bg, double count,
                                    float eps) {
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_bg) return;
   const double mean = stats[2 * i] / count;
@@ -563,6 +581,8 @@ __global__ void __launch_bounds__(256)
 gn_gelu_kernel(const void* __restrict__ raw, int raw_is_f32, const float2* __restrict__ mr,
                const float* __restrict__ gn_w, const float* __restrict__ gn_b, __nv_bfloat16* __restrict__ out, int B,
                int hw, int C, int groups, int split) {
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   const int cv = C >> 3;
   const unsigned total = (unsigned)B * (hw / GN_PPT) * cv;  // < 2^31 (checked by the launcher)
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -616,6 +636,8 @@ gn_gelu_kernel(const void* __restrict__ raw, int raw_is_f32, const float2* __res
 __global__ void gn_gelu_f32_kernel(const float* __restrict__ raw, const float2* __restrict__ mr,
                                    const float* __restrict__ gn_w, const float* __restrict__ gn_b,
                                    float* __restrict__ out, int B, int hw, int C, int groups) {
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   const long long total = (long long)B * hw * C;
   const int cpg = C / groups;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -630,6 +652,8 @@ __global__ void gn_gelu_f32_kernel(const float* __restrict__ raw, const float2* 
 // 8.7 MMAC per ROI, irrelevant for throughput).  One warp per output element.
 __global__ void fc_f32_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
                               float* __restrict__ y, int B, int N, int K, int ldy, int gelu) {
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= B * N) return;
   const int b = warp / N, n = warp % N;
@@ -652,6 +676,8 @@ __global__ void fc_f32_kernel(const float* __restrict__ x, const float* __restri
 __global__ void __launch_bounds__(256)
 upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int h, int w, int C,
                   int split) {
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   const int cv = C >> 3;
   const int oh = 2 * h, ow = 2 * w;
   const unsigned total = (unsigned)B * oh * ow * cv;
@@ -704,6 +730,8 @@ __global__ void pose_lift_kernel(const float* __restrict__ raw, int ld, const fl
                                  const float* __restrict__ centers, const float* __restrict__ whs,
                                  const float* __restrict__ ratios, float* __restrict__ out_rot,
                                  float* __restrict__ out_trans, float* __restrict__ out_raw9, int B) {
+  ptx::griddep_launch();
+  ptx::griddep_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
   const float* r = raw + (long long)i * ld;
@@ -773,7 +801,7 @@ int launch_pack(const float* src, void* dst, int dst_is_bf16, const PackDesc& d,
   if (total <= 0) return GDRN_OK;
   long long blocks = (total + 255) / 256;
   if (blocks > 4096) blocks = 4096;
-  pack_kernel<<<(int)blocks, 256, 0, st>>>(src, dst, dst_is_bf16, d);
+  GDRN_CHECK_CUDA(gdrn_launch_dep(pack_kernel, dim3((int)blocks), dim3(256), 0, st, src, dst, dst_is_bf16, d));
   GDRN_CHECK_CUDA(cudaGetLastError());
   gdrn_count_launch(1);
   return GDRN_OK;
@@ -782,7 +810,7 @@ int launch_pack(const float* src, void* dst, int dst_is_bf16, const PackDesc& d,
 int launch_stem_patchify(const float* img, __nv_bfloat16* out, int B, int H, int W, int split, cudaStream_t st) {
   GDRN_REQUIRE(H % 4 == 0 && W % 4 == 0, "stem: H, W must be multiples of 4");
   long long total = (long long)B * (H / 4) * (W / 4);
-  stem_patchify_kernel<<<(int)((total + 127) / 128), 128, 0, st>>>(img, out, B, H, W, split);
+  GDRN_CHECK_CUDA(gdrn_launch_dep(stem_patchify_kernel, dim3((int)((total + 127) / 128)), dim3(128), 0, st, img, out, B, H, W, split));
   GDRN_CHECK_CUDA(cudaGetLastError());
   gdrn_count_launch(1);
   return GDRN_OK;
@@ -819,13 +847,15 @@ static int launch_dwconv_cluster(const float* x, const float* w49c, const float*
   cfg.blockDim = dim3(NTHREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = C / CPC;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see gdrn_launch_dep (common.cuh)
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = gdrn_pdl_enabled() ? 2 : 1;
   static int trace_on = -1;  // GDRN_DW_TRACE=1: phase cycle counts of one mid-grid CTA on stderr (synchronises)
   if (trace_on < 0) trace_on = getenv("GDRN_DW_TRACE") ? 1 : 0;
   static long long* d_trace = nullptr;
@@ -880,11 +910,11 @@ int launch_dwconv_ln_variant(const float* x, const float* w49c, const float* bia
   const int S = 256 / (C / 4);
   if (W % 16 == 0) {
     long long strips = (long long)B * H * (W / 16);
-    dwconv_ln_kernel<16><<<(int)((strips + S - 1) / S), 256, 0, st>>>(x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps);
+    GDRN_CHECK_CUDA(gdrn_launch_dep(dwconv_ln_kernel<16>, dim3((int)((strips + S - 1) / S)), dim3(256), 0, st, x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps));
   } else {
     GDRN_REQUIRE(W % 8 == 0, "dwconv: W must be a multiple of 8");
     long long strips = (long long)B * H * (W / 8);
-    dwconv_ln_kernel<8><<<(int)((strips + S - 1) / S), 256, 0, st>>>(x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps);
+    GDRN_CHECK_CUDA(gdrn_launch_dep(dwconv_ln_kernel<8>, dim3((int)((strips + S - 1) / S)), dim3(256), 0, st, x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps));
   }
   GDRN_CHECK_CUDA(cudaGetLastError());
   gdrn_count_launch(1);
@@ -896,10 +926,10 @@ int launch_ln_patchify2(const float* x, const float* ln_w, const float* ln_b, __
   GDRN_REQUIRE(C % 128 == 0 && C <= 512 && H % 2 == 0 && W % 2 == 0, "ln_patchify2: unsupported shape");
   const long long total = (long long)B * (H / 2) * (W / 2);
   const int blocks = (int)((total + 7) / 8);
-  if (C == 128) ln_patchify2_kernel<1><<<blocks, 256, 0, st>>>(x, ln_w, ln_b, out, B, H, W, eps, split);
-  else if (C == 256) ln_patchify2_kernel<2><<<blocks, 256, 0, st>>>(x, ln_w, ln_b, out, B, H, W, eps, split);
-  else if (C == 384) ln_patchify2_kernel<3><<<blocks, 256, 0, st>>>(x, ln_w, ln_b, out, B, H, W, eps, split);
-  else ln_patchify2_kernel<4><<<blocks, 256, 0, st>>>(x, ln_w, ln_b, out, B, H, W, eps, split);
+  if (C == 128) GDRN_CHECK_CUDA(gdrn_launch_dep(ln_patchify2_kernel<1>, dim3(blocks), dim3(256), 0, st, x, ln_w, ln_b, out, B, H, W, eps, split));
+  else if (C == 256) GDRN_CHECK_CUDA(gdrn_launch_dep(ln_patchify2_kernel<2>, dim3(blocks), dim3(256), 0, st, x, ln_w, ln_b, out, B, H, W, eps, split));
+  else if (C == 384) GDRN_CHECK_CUDA(gdrn_launch_dep(ln_patchify2_kernel<3>, dim3(blocks), dim3(256), 0, st, x, ln_w, ln_b, out, B, H, W, eps, split));
+  else GDRN_CHECK_CUDA(gdrn_launch_dep(ln_patchify2_kernel<4>, dim3(blocks), dim3(256), 0, st, x, ln_w, ln_b, out, B, H, W, eps, split));
   GDRN_CHECK_CUDA(cudaGetLastError());
   gdrn_count_launch(1);
   return GDRN_OK;
@@ -909,7 +939,7 @@ int launch_cast_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStre
   long long blocks = (n / 4 + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 8192) blocks = 8192;
-  cast_bf16_kernel<<<(int)blocks, 256, 0, st>>>(src, dst, n);
+  GDRN_CHECK_CUDA(gdrn_launch_dep(cast_bf16_kernel, dim3((int)blocks), dim3(256), 0, st, src, dst, n));
   GDRN_CHECK_CUDA(cudaGetLastError());
   gdrn_count_launch(1);
   return GDRN_OK;
@@ -918,7 +948,7 @@ int launch_cast_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStre
 int launch_bf16_to_f32(const __nv_bfloat16* src, float* dst, long long n, cudaStream_t st) {
   long long blocks = (n + 255) / 256;
   if (blocks > 8192) blocks = 8192;
-  bf16_to_f32_kernel<<<(int)blocks, 256, 0, st>>>(src, dst, n);
+  GDRN_CHECK_CUDA(gdrn_launch_dep(bf16_to_f32_kernel, dim3((int)blocks), dim3(256), 0, st, src, dst, n));
   GDRN_CHECK_CUDA(cudaGetLastError());
   gdrn_count_launch(1);
   return GDRN_OK;
@@ -929,12 +959,12 @@ int launch_gn_gelu(const void* raw, int raw_is_f32, const double* stats, float* 
                    cudaStream_t st) {
   GDRN_REQUIRE(C % 8 == 0 && (h * w) % GN_PPT == 0, "gn_gelu: unsupported shape");
   const int n_bg = B * groups;
-  gn_finalize_kernel<<<(n_bg + 127) / 128, 128, 0, st>>>(stats, reinterpret_cast<float2*>(mean_rstd_scratch), n_bg,
-                                                        (double)h * w * (C / groups), eps);
+  GDRN_CHECK_CUDA(gdrn_launch_dep(gn_finalize_kernel, dim3((n_bg + 127) / 128), dim3(128), 0, st, stats, reinterpret_cast<float2*>(mean_rstd_scratch), n_bg,
+                                                        (double)h * w * (C / groups), eps));
   long long total = (long long)B * (h * w / GN_PPT) * (C / 8);
   GDRN_REQUIRE(total < (1LL << 31), "gn_gelu: tensor too large for 32-bit indexing");
-  gn_gelu_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(raw, raw_is_f32, reinterpret_cast<const float2*>(mean_rstd_scratch),
-                                                            gn_w, gn_b, out, B, h * w, C, groups, split);
+  GDRN_CHECK_CUDA(gdrn_launch_dep(gn_gelu_kernel, dim3((int)((total + 255) / 256)), dim3(256), 0, st, raw, raw_is_f32, reinterpret_cast<const float2*>(mean_rstd_scratch),
+                                                            gn_w, gn_b, out, B, h * w, C, groups, split));
   GDRN_CHECK_CUDA(cudaGetLastError());
   gdrn_count_launch(2);
   return GDRN_OK;
@@ -943,11 +973,11 @@ int launch_gn_gelu(const void* raw, int raw_is_f32, const double* stats, float* 
 int launch_gn_gelu_f32(const float* raw, const double* stats, float* mean_rstd_scratch, const float* gn_w,
                        const float* gn_b, float* out, int B, int h, int w, int C, int groups, float eps, cudaStream_t st) {
   const int n_bg = B * groups;
-  gn_finalize_kernel<<<(n_bg + 127) / 128, 128, 0, st>>>(stats, reinterpret_cast<float2*>(mean_rstd_scratch), n_bg,
-                                                        (double)h * w * (C / groups), eps);
+  GDRN_CHECK_CUDA(gdrn_launch_dep(gn_finalize_kernel, dim3((n_bg + 127) / 128), dim3(128), 0, st, stats, reinterpret_cast<float2*>(mean_rstd_scratch), n_bg,
+                                                        (double)h * w * (C / groups), eps));
   long long total = (long long)B * h * w * C;
-  gn_gelu_f32_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(raw, reinterpret_cast<const float2*>(mean_rstd_scratch), gn_w,
-                                                                gn_b, out, B, h * w, C, groups);
+  GDRN_CHECK_CUDA(gdrn_launch_dep(gn_gelu_f32_kernel, dim3((int)((total + 255) / 256)), dim3(256), 0, st, raw, reinterpret_cast<const float2*>(mean_rstd_scratch), gn_w,
+                                                                gn_b, out, B, h * w, C, groups));
   GDRN_CHECK_CUDA(cudaGetLastError());
   gdrn_count_launch(2);
   return GDRN_OK;
@@ -957,7 +987,7 @@ int launch_fc_f32(const float* x, const float* W, const float* bias, float* y, i
                   cudaStream_t st) {
   GDRN_REQUIRE(K % 128 == 0, "fc_f32: K must be a multiple of 128");
   const long long warps = (long long)B * N;
-  fc_f32_kernel<<<(int)((warps * 32 + 255) / 256), 256, 0, st>>>(x, W, bias, y, B, N, K, ldy, gelu);
+  GDRN_CHECK_CUDA(gdrn_launch_dep(fc_f32_kernel, dim3((int)((warps * 32 + 255) / 256)), dim3(256), 0, st, x, W, bias, y, B, N, K, ldy, gelu));
   GDRN_CHECK_CUDA(cudaGetLastError());
   gdrn_count_launch(1);
   return GDRN_OK;
@@ -968,7 +998,7 @@ int launch_cast_split(const float* src, __nv_bfloat16* dst, long long rows, int 
   long long total = rows * (C / 8);
   long long blocks = (total + 255) / 256;
   if (blocks > 8192) blocks = 8192;
-  cast_split_kernel<<<(int)blocks, 256, 0, st>>>(src, dst, rows, C);
+  GDRN_CHECK_CUDA(gdrn_launch_dep(cast_split_kernel, dim3((int)blocks), dim3(256), 0, st, src, dst, rows, C));
   GDRN_CHECK_CUDA(cudaGetLastError());
   gdrn_count_launch(1);
   return GDRN_OK;
@@ -978,7 +1008,7 @@ int launch_upsample2x(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int h,
   GDRN_REQUIRE(C % 8 == 0 && h > 1 && w > 1, "upsample2x: unsupported shape");
   long long total = (long long)B * 4 * h * w * (C / 8);
   GDRN_REQUIRE(total < (1LL << 31), "upsample2x: tensor too large for 32-bit indexing");
-  upsample2x_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(in, out, B, h, w, C, split);
+  GDRN_CHECK_CUDA(gdrn_launch_dep(upsample2x_kernel, dim3((int)((total + 255) / 256)), dim3(256), 0, st, in, out, B, h, w, C, split));
   GDRN_CHECK_CUDA(cudaGetLastError());
   gdrn_count_launch(1);
   return GDRN_OK;
@@ -986,7 +1016,7 @@ int launch_upsample2x(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int h,
 
 int launch_pose_lift(const float* raw, int ld, const float* cams, const float* centers, const float* whs,
                      const float* ratios, float* out_rot, float* out_trans, float* out_raw9, int B, cudaStream_t st) {
-  pose_lift_kernel<<<(B + 63) / 64, 64, 0, st>>>(raw, ld, cams, centers, whs, ratios, out_rot, out_trans, out_raw9, B);
+  GDRN_CHECK_CUDA(gdrn_launch_dep(pose_lift_kernel, dim3((B + 63) / 64), dim3(64), 0, st, raw, ld, cams, centers, whs, ratios, out_rot, out_trans, out_raw9, B));
   GDRN_CHECK_CUDA(cudaGetLastError());
   gdrn_count_launch(1);
   return GDRN_OK;

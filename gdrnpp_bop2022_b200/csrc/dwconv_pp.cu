@@ -59,6 +59,7 @@ dwconv_ln_pp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(parts + 2 * 2 * PP_MAX_RANKS * NPIX);
   // bars: [0] weights, [1..2] tile loaded (per wg), [3..6] partials (wg * 2 + buf)
 
+  ptx::griddep_launch();
   cg::cluster_group cluster = cg::this_cluster();
   const int nrank = (int)cluster.num_blocks();
   const int rank = (int)cluster.block_rank();
@@ -96,6 +97,7 @@ dwconv_ln_pp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     ptx::mbar_arrive_expect_tx(bar_w, (uint32_t)(49 * CPC * sizeof(float)));
     ptx::tma_load_2d(ptx::smem_u32(wsm), &tmap_w, bar_w, c0, 0);          // this CTA's 49 x 64 filter taps, once
   }
+  ptx::griddep_wait();   // barriers and the (constant) filter taps were set up under the previous kernel's tail
   if (tidw == 0 && n_w > 0) {
     int b, y0, x0;
     tile_coords(wg, b, y0, x0);
@@ -255,13 +257,15 @@ int launch_dwconv_ln_pp(const float* x, const float* w49c, const float* bias, co
   cfg.blockDim = dim3(2 * PP_WG_THREADS);
   cfg.dynamicSmemBytes = PP_SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = csize;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see gdrn_launch_dep (common.cuh)
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = gdrn_pdl_enabled() ? 2 : 1;
   if (max_clusters[dev][csize] == 0) {
     int n = 0;
     cfg.gridDim = dim3(gdrn_num_sms() / csize * csize);

@@ -774,32 +774,43 @@ __device__ __forceinline__ void epilogue_tile_tma_split(const GemmPlan& p, int m
     long long tq0 = trc ? clock64() : 0;
     tmem_load_chunk<CH>(tmem_row + c, v);
     if (trc) { const long long t = clock64(); tq_tmem += t - tq0; tq0 = t; }
+    // element PAIRS in packed fp32 (FADD2 / FFMA2 / FMUL2): this epilogue is FMA-pipe bound, see gelu_erf2
+    f32x2_t v2[CH / 2];
+#pragma unroll
+    for (int j = 0; j < CH / 2; ++j) v2[j] = f2_pack(v[2 * j], v[2 * j + 1]);
     if (p.bias) {
 #pragma unroll
       for (int j = 0; j < CH; j += 4) {
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col + j));
-        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        v2[j / 2] = f2_add(v2[j / 2], f2_pack(b4.x, b4.y));
+        v2[j / 2 + 1] = f2_add(v2[j / 2 + 1], f2_pack(b4.z, b4.w));
       }
     }
     if constexpr (EPI == EPI_GELU) {
       if (p.gelu_mode == 3) {
 #pragma unroll
-        for (int j = 0; j < CH; ++j) v[j] = gelu_erf(v[j]);
-      } else if (p.gelu_mode == 4) {   // A/B knob: libm erff (data-dependent branch inside)
+        for (int j = 0; j < CH / 2; ++j) v2[j] = gelu_erf2(v2[j]);
+      } else {                         // A/B knobs: 5 = scalar A&S form, 4 = libm erff, else the bf16-mode fit
 #pragma unroll
-        for (int j = 0; j < CH; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752440f));
-      } else {
-#pragma unroll
-        for (int j = 0; j < CH; ++j) v[j] = gelu_fast(v[j]);
+        for (int j = 0; j < CH / 2; ++j) {
+          float2 f = f2_unpack(v2[j]);
+          if (p.gelu_mode == 5) { f.x = gelu_erf(f.x); f.y = gelu_erf(f.y); }
+          else if (p.gelu_mode == 4) {
+            f.x = 0.5f * f.x * (1.0f + erff(f.x * 0.70710678118654752440f));
+            f.y = 0.5f * f.y * (1.0f + erff(f.y * 0.70710678118654752440f));
+          } else { f.x = gelu_fast(f.x); f.y = gelu_fast(f.y); }
+          v2[j] = f2_pack(f.x, f.y);
+        }
       }
     }
     uint32_t hi[CH / 2], lo[CH / 2];
 #pragma unroll
     for (int j = 0; j < CH / 2; ++j) {
-      const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-      const float2 hf = __bfloat1622float2(h2);
-      hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
-      lo[j] = pack_bf16(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+      const float2 f = f2_unpack(v2[j]);
+      const uint32_t hb = pack_bf16(f.x, f.y);
+      hi[j] = hb;
+      const float2 d = f2_unpack(f2_sub(v2[j], f2_pack(__uint_as_float(hb << 16), __uint_as_float(hb & 0xffff0000u))));
+      lo[j] = pack_bf16(d.x, d.y);
     }
     if (trc) { const long long t = clock64(); tq_comp += t - tq0; tq0 = t; }
     if (lane == 0) ptx::bulk_wait_read0();   // the previous chunk's stores have read the staging tiles

@@ -45,6 +45,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P2Cfg<NEW>::THREADS,
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();   // 0 = leader
+  ptx::griddep_launch();
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.tmap_a);
     ptx::prefetch_tmap(&p.tmap_b);
@@ -64,6 +65,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P2Cfg<NEW>::THREADS,
   ptx::cluster_sync_all();   // both CTAs' barriers and TMEM exist before anything crosses the pair
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  ptx::griddep_wait();
 
   const int m_pairs = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
   const int total_tiles = m_pairs * p.n_tiles;
@@ -160,8 +162,7 @@ int launch_pair(const GemmPlan& plan, cudaStream_t stream) {
   if (total <= 0) return GDRN_OK;
   int pairs = gdrn_num_sms() / 2;
   if (pairs > total) pairs = total;
-  kfn<<<2 * pairs, NUM_THREADS, P2_SMEM_BYTES, stream>>>(plan);
-  GDRN_CHECK_CUDA(cudaGetLastError());
+  GDRN_CHECK_CUDA(gdrn_launch_dep(kfn, dim3(2 * pairs), dim3(NUM_THREADS), P2_SMEM_BYTES, stream, plan));
   gdrn_count_launch(1);
   return GDRN_OK;
 }

@@ -23,21 +23,23 @@
 
 namespace {
 
-template <int BLOCK_N>
+// NEWARPS = epilogue warps per CTA: 8 (3-stage ring at BLOCK_N 256) or 16 (2-stage ring; four warps per scheduler for the
+// GELU epilogue of the short-K fc1 GEMMs, which is issue bound at ~0.5 IPC with two warps per scheduler)
+template <int BLOCK_N, int NEWARPS>
 struct X3Cfg {
   static constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;             // this CTA's half of the W rows, hi OR lo
   static constexpr int STAGE_BYTES = 2 * A_STAGE_BYTES + 2 * B_BYTES;     // 64 KB (BLOCK_N 256) / 48 KB (128)
-  static constexpr int STAGES = BLOCK_N == 256 ? 3 : 4;
-  static constexpr int NEW = 8;                                           // epilogue warps
+  static constexpr int NEW = NEWARPS;
+  static constexpr int STAGES = BLOCK_N == 256 ? (NEWARPS == 16 ? 2 : 3) : (NEWARPS == 16 ? 3 : 4);
   static constexpr int THREADS = 128 + 32 * NEW;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;                           // two accumulator stages (512 / 256)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NEW * EPI_STAGE_BYTES + 256 + 1024;
 };
 
-template <int BLOCK_N, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X3Cfg<BLOCK_N>::THREADS, 1)
+template <int BLOCK_N, int EPI, int NEWARPS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X3Cfg<BLOCK_N, NEWARPS>::THREADS, 1)
 gemm_pair_x3_kernel(const __grid_constant__ GemmPlan p) {
-  using C = X3Cfg<BLOCK_N>;
+  using C = X3Cfg<BLOCK_N, NEWARPS>;
   constexpr int STAGES = C::STAGES;
   constexpr int NEW = C::NEW;
   extern __shared__ uint8_t smem_raw[];
@@ -55,6 +57,7 @@ gemm_pair_x3_kernel(const __grid_constant__ GemmPlan p) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();   // 0 = leader
+  ptx::griddep_launch();
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.tmap_a);
     ptx::prefetch_tmap(&p.tmap_b);
@@ -74,6 +77,7 @@ gemm_pair_x3_kernel(const __grid_constant__ GemmPlan p) {
   ptx::cluster_sync_all();   // both CTAs' barriers and TMEM exist before anything crosses the pair
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  ptx::griddep_wait();       // the prologue above ran under the previous kernel's tail; its results are needed from here on
 
   const int m_pairs = (p.m_tiles + 1) >> 1;
   const int total_tiles = m_pairs * p.n_tiles;
@@ -197,18 +201,17 @@ gemm_pair_x3_kernel(const __grid_constant__ GemmPlan p) {
   }
 }
 
-template <int BLOCK_N, int EPI>
+template <int BLOCK_N, int EPI, int NEWARPS = 8>
 int launch_x3(const GemmPlan& plan, cudaStream_t stream) {
-  using C = X3Cfg<BLOCK_N>;
-  auto kfn = gemm_pair_x3_kernel<BLOCK_N, EPI>;
+  using C = X3Cfg<BLOCK_N, NEWARPS>;
+  auto kfn = gemm_pair_x3_kernel<BLOCK_N, EPI, NEWARPS>;
   GDRN_OPT_IN_SMEM(kfn, C::SMEM_BYTES);
   const int m_pairs = (plan.m_tiles + 1) / 2;
   const int total = m_pairs * plan.n_tiles;
   if (total <= 0) return GDRN_OK;
   int pairs = gdrn_num_sms() / 2;
   if (pairs > total) pairs = total;
-  kfn<<<2 * pairs, C::THREADS, C::SMEM_BYTES, stream>>>(plan);
-  GDRN_CHECK_CUDA(cudaGetLastError());
+  GDRN_CHECK_CUDA(gdrn_launch_dep(kfn, dim3(2 * pairs), dim3(C::THREADS), C::SMEM_BYTES, stream, plan));
   gdrn_count_launch(1);
   return GDRN_OK;
 }
@@ -232,6 +235,15 @@ int gemm_pair_x3_supported(const GemmPlan& plan, int block_n) {
 }
 
 int gemm_pair_x3_launch(const GemmPlan& plan, int block_n, cudaStream_t stream) {
+  if (plan.epi == EPI_GELU) {
+    // 16 epilogue warps for the short-K GELU GEMMs (stages 0 / 1: the epilogue, not the mainloop, sets their time)
+    static int gelu16_max_k = -1;   // GDRN_X3_GELU16_MAX_KITERS: use the 16-warp variant up to this many k-iterations (0 = never)
+    if (gelu16_max_k < 0) { const char* e = getenv("GDRN_X3_GELU16_MAX_KITERS"); gelu16_max_k = e ? atoi(e) : 4; }
+    if (plan.num_taps * plan.k_chunks <= gelu16_max_k) {
+      if (block_n == 256) return launch_x3<256, EPI_GELU, 16>(plan, stream);
+      if (block_n == 128) return launch_x3<128, EPI_GELU, 16>(plan, stream);
+    }
+  }
 #define GDRN_X3_CASE(BN, E) if (block_n == BN && plan.epi == E) return launch_x3<BN, E>(plan, stream);
   GDRN_X3_CASE(256, EPI_GELU)
   GDRN_X3_CASE(256, EPI_RESID)

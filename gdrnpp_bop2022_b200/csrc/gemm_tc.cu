@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   constexpr bool kStaged = (BLOCK_N >= 64) && (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_RESID || EPI == EPI_GNSTATS);
   uint8_t* stage_base = smem_gen + C::STAGES * C::STAGE_BYTES;  // 1024-aligned (TMA-store tiles are 128B-swizzled)
 
+  ptx::griddep_launch();
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.tmap_a);
     ptx::prefetch_tmap(&p.tmap_b);
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  ptx::griddep_wait();
 
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int k_iters = p.num_taps * p.k_chunks;
@@ -241,8 +243,7 @@ int launch_inst(const GemmPlan& plan, cudaStream_t stream) {
   int total = plan.m_tiles * plan.n_tiles;
   if (total <= 0) return GDRN_OK;
   int grid = total < gdrn_num_sms() ? total : gdrn_num_sms();
-  kfn<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(plan);
-  GDRN_CHECK_CUDA(cudaGetLastError());
+  GDRN_CHECK_CUDA(gdrn_launch_dep(kfn, dim3(grid), dim3(NUM_THREADS), C::SMEM_BYTES, stream, plan));
   gdrn_count_launch(1);
   return GDRN_OK;
 }

@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_fused_kernel(const __grid_
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_gen + stg_off + NUM_EPI_WARPS * EPI_STAGE_BYTES + 8 * B_END);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ptx::griddep_launch();
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&fp.tmap_a); ptx::prefetch_tmap(&fp.tmap_w1); ptx::prefetch_tmap(&fp.tmap_w2);
     ptx::prefetch_tmap(&p.tmap_out);
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_fused_kernel(const __grid_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  ptx::griddep_wait();
   const int my_tiles = (int)blockIdx.x < fp.m_tiles ? (fp.m_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const uint32_t total_rounds = (uint32_t)my_tiles * ROUNDS;
   const bool tr = p.trace != nullptr && blockIdx.x == 0;   // GDRN_MLP_TRACE: cycle accounting of CTA 0
@@ -303,8 +305,7 @@ int mlp_fused_launch(const void* A, const void* W1, const float* b1, const void*
     GDRN_CHECK_CUDA(cudaMemsetAsync(d_trace, 0, 16 * sizeof(long long), stream));
     fp.g.trace = d_trace;
   }
-  kfn<<<grid, NUM_THREADS, SMEM, stream>>>(fp);
-  GDRN_CHECK_CUDA(cudaGetLastError());
+  GDRN_CHECK_CUDA(gdrn_launch_dep(kfn, dim3(grid), dim3(NUM_THREADS), SMEM, stream, fp));
   gdrn_count_launch(1);
   if (trace_on) {
     long long h[16];
