@@ -78,6 +78,13 @@ extern "C" int gdrn_gemm_bf16(const void* A, const void* W, const float* bias, c
   return GDRN_OK;
 }
 
+extern "C" int gdrn_mlp_fused_x3(const void* A, const void* W1, const float* b1, const void* W2, const float* b2,
+                                 const float* gamma, float* x, long long M, int C, void* stream) {
+  GDRN_REQUIRE(A && W1 && b1 && W2 && b2 && gamma && x, "mlp_fused_x3: null argument");
+  GDRN_REQUIRE(mlp_fused_x3_supported(C, M), "mlp_fused_x3: needs C == 128 and M a multiple of 128, M >= 128 * 148");
+  return mlp_fused_x3_launch(A, W1, b1, W2, b2, gamma, x, M, C, (cudaStream_t)stream);
+}
+
 extern "C" int gdrn_gemm_x3(const void* A, const void* W, const float* bias, const float* gamma, const float* resid,
                             void* out, int M, int N, int K, int epi, int block_n, void* stream) {
   GDRN_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_x3: empty problem");

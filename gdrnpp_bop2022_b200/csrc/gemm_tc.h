@@ -98,6 +98,10 @@ int gemm_pair_x3_launch(const GemmPlan& plan, int block_n, cudaStream_t stream);
 
 // Fused ConvNeXt MLP block (C = 128): x += gamma * (W2 . gelu(W1 . A + b1) + b2), hidden activation kept on chip.
 // A bf16 [M, C]; W1 bf16 [4C, C]; W2 bf16 [C, 4C]; x fp32 [M, C] updated in place.
+// split-bf16 (parity mode) twin, mlp_fused_x3.cu: A [M,2C], W1 [4C,2C], W2 [C,8C] hold [hi | lo] halves
+int mlp_fused_x3_supported(int C, long long M);
+int mlp_fused_x3_launch(const void* A, const void* W1, const float* b1, const void* W2, const float* b2, const float* gamma,
+                        float* x, long long M, int C, cudaStream_t stream);
 int mlp_fused_supported(int C, long long M);
 int mlp_fused_launch(const void* A, const void* W1, const float* b1, const void* W2, const float* b2, const float* gamma,
                      float* x, long long M, int C, cudaStream_t stream);

@@ -67,6 +67,7 @@ struct GdrnModel {
   int max_batch;
   int in_res = 256, out_res = 64;
   int fuse_mlp = 1;   // fused fc1->GELU->fc2 kernel where supported (env GDRN_MLP_FUSED=0 disables)
+  int fuse_mlp_x3 = 1;  // the same in split-bf16 mode, stage 0 (env GDRN_MLP_FUSED_X3=0 disables)
   int precise = 0;    // 0: bf16 operands (fast); 1: split-bf16 x3 products, fp32 FC stack, erf GELU
   int gelu_mode = 1;  // fc1 epilogue GELU: 1 = packed-half2 tanh.approx (default, fastest), 0 = fp32 ex2/rcp form, 2 = fp32 tanh.approx; env GDRN_GELU_MODE
   // ---- weights (device) ----
@@ -445,6 +446,7 @@ extern "C" int gdrn_model_create_ex(GdrnModel** out, const char* arch, int num_c
   m->precise = precision;
   if (const char* e = getenv("GDRN_GELU_MODE")) m->gelu_mode = atoi(e);
   if (const char* e = getenv("GDRN_MLP_FUSED")) m->fuse_mlp = atoi(e);
+  if (const char* e = getenv("GDRN_MLP_FUSED_X3")) m->fuse_mlp_x3 = atoi(e);
   if (!build_weights(m)) {
     gdrn_model_destroy(m);
     gdrn_set_last_error(__FILE__, __LINE__, "model_create: cudaMalloc failed");
@@ -570,6 +572,10 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
       if (!PR && m->fuse_mlp && m->gelu_mode == 1 && mlp_fused_supported(C, M)) {
         // stage 0: fc1 -> GELU -> fc2 -> residual in one kernel (no 4C-wide Hb round trip through HBM)
         RCP(0, mlp_fused_launch(w.A, bw.fc1_w, bw.fc1_b, bw.fc2_w, bw.fc2_b, bw.gamma, w.X, M, C, st));
+        continue;
+      }
+      if (PR && m->fuse_mlp_x3 && mlp_fused_x3_supported(C, M)) {
+        RCP(0, mlp_fused_x3_launch(w.A, bw.fc1_w, bw.fc1_b, bw.fc2_w, bw.fc2_b, bw.gamma, w.X, M, C, st));
         continue;
       }
       reset();

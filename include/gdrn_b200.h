@@ -104,6 +104,13 @@ int gdrn_gemm_bf16(const void* A, const void* W, const float* bias, const float*
 int gdrn_gemm_x3(const void* A, const void* W, const float* bias, const float* gamma, const float* resid, void* out,
                  int M, int N, int K, int epi, int block_n, void* stream);
 
+/* Fused ConvNeXt MLP half-block of the split-bf16 mode (stage 0, C = 128), exported for tests and measurement:
+ * x [M,C] fp32 += gamma * (W2 . gelu(W1 . a + b1) + b2) with a [M,2C], W1 [4C,2C], W2 [C,8C] in [hi | lo] bf16 rows; the
+ * 4C-wide hidden activation stays on chip.  Replaces two gdrn_gemm_x3 calls (epi 1 then epi 2); same arithmetic.
+ * Reference op: timm ConvNeXtBlock.mlp + layer scale + shortcut (models/GDRN_double_mask.py:102 via the backbone). */
+int gdrn_mlp_fused_x3(const void* A, const void* W1, const float* b1, const void* W2, const float* b2, const float* gamma,
+                      float* x, long long M, int C, void* stream);
+
 /* ConvNeXt block front half exported for tests and roofline measurement: depthwise 7x7 (pad 3) + bias + LayerNorm(C)
  * on an NHWC fp32 tensor x [B,H,W,C] with tap-major weights w49c [49][C] -> bf16 [B*H*W, C] (split = 1: [hi C | lo C]).
  * variant: -1 default, 0 = one-tile-per-CTA cluster kernel, 1 = persistent two-warpgroup ping-pong kernel. */

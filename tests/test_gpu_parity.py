@@ -141,6 +141,39 @@ def test_gemm_x3_vs_fp64(dev, lib, M, N, K, bn, epi):
     assert err < 4e-5 * max(1.0, ref.abs().max().item()), err
 
 
+@pytest.mark.gpu
+def test_mlp_fused_x3_vs_unfused_and_fp64(dev, lib):
+    """Fused fc1 -> GELU -> fc2 -> residual of the split-bf16 mode (ConvNeXt stage 0, C = 128; the hidden activation stays on
+    chip) against (a) the two-kernel path it replaces -- same products in the same accumulation order -- and (b) an fp64
+    torch reference of timm's ConvNeXtBlock MLP half on the original fp32 operands."""
+    L = _lib()
+    C, M = 128, 128 * 148 * 2 + 128 * 5          # two full waves + a ragged third
+    g = torch.Generator().manual_seed(11)
+    A = (torch.randn(M, C, generator=g) * 0.7).to(dev)
+    W1 = (torch.randn(4 * C, C, generator=g) / np.sqrt(C)).to(dev)
+    W2 = (torch.randn(C, 4 * C, generator=g) / np.sqrt(4 * C)).to(dev)
+    b1, b2, gamma = torch.randn(4 * C, generator=g).to(dev), torch.randn(C, generator=g).to(dev), torch.rand(C, generator=g).to(dev)
+    x0 = torch.randn(M, C, generator=g).to(dev)
+    h = torch.nn.functional.gelu(A.double() @ W1.double().t() + b1.double())
+    ref = x0.double() + gamma.double() * (h @ W2.double().t() + b2.double())
+    A2, W12, W22 = _split_bf16(A), _split_bf16(W1), _split_bf16(W2)
+    # unfused: fc1 (epi 1 -> split hidden) then fc2 (epi 2, in place)
+    Hb = torch.empty(M, 8 * C, dtype=torch.bfloat16, device=dev)
+    x_un = x0.clone()
+    L.check(lib.gdrn_gemm_x3(L.ptr(A2), L.ptr(W12), L.ptr(b1), None, None, L.ptr(Hb), M, 4 * C, C, 1, 256, L.current_stream()), "fc1")
+    L.check(lib.gdrn_gemm_x3(L.ptr(Hb), L.ptr(W22), L.ptr(b2), L.ptr(gamma), L.ptr(x_un), L.ptr(x_un), M, C, 4 * C, 2, 128,
+                             L.current_stream()), "fc2")
+    x_fu = torch.cat([x0.clone(), torch.full((64, C), 7.0, device=dev)])       # canary rows behind the matrix
+    L.check(lib.gdrn_mlp_fused_x3(L.ptr(A2), L.ptr(W12), L.ptr(b1), L.ptr(W22), L.ptr(b2), L.ptr(gamma), L.ptr(x_fu), M, C,
+                                  L.current_stream()), "mlp_fused_x3")
+    torch.cuda.synchronize()
+    assert torch.equal(x_fu[M:], torch.full((64, C), 7.0, device=dev))
+    err = (x_fu[:M].double() - ref).abs().max().item()
+    assert err < 4e-5 * max(1.0, ref.abs().max().item()), err
+    d = (x_fu[:M] - x_un).abs().max().item()
+    assert d < 2e-6 * max(1.0, ref.abs().max().item()), d     # same math; fp32 reduce-add order aside, the two paths agree
+
+
 # ----------------------------------------------------------------------------------------------- model
 def _run_model(dev, B, seed, with_maps=True, precision="bf16"):
     from gdrnpp_bop2022_b200.gdrn_model import GDRN_DoubleMask, default_cfg

@@ -4,6 +4,7 @@ independent formulations elsewhere."""
 import ctypes
 import math
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -119,6 +120,19 @@ def test_gelu_epilogue_fit_accuracy():
     g = x / (1 + np.exp2(xc * p))
     ref = torch.nn.functional.gelu(torch.from_numpy(x)).numpy()
     assert np.abs(g - ref).max() < 3e-5
+
+
+def test_gelu_erf_epilogue_forms_accuracy():
+    """The parity-mode (split-bf16) epilogue GELU: both evaluation orders of the A&S 7.1.26 erfc form (scalar gelu_erf and the
+    packed gelu_erf2 the fc1 epilogue runs), emulated in float32, stay within 6e-7 of the float64 erf GELU."""
+    pytest.importorskip("scipy")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import check_erf as CE
+    from scipy.special import erf as erf64
+    x = np.linspace(-12, 12, 400001).astype(np.float32)
+    ref = 0.5 * x.astype(np.float64) * (1 + erf64(x.astype(np.float64) / np.sqrt(2)))
+    assert np.abs(CE.gelu_as(x) - ref).max() < 6e-7
+    assert np.abs(CE.gelu_as_packed(x) - ref).max() < 6e-7
 
 
 def test_nnd_oracle_vs_cdist():
