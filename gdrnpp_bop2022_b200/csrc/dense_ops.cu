@@ -237,7 +237,7 @@ __global__ void __launch_bounds__((CPC / 2) * TH / R, MINB)
 dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                          const float* __restrict__ bias, const float* __restrict__ ln_w,
                          const float* __restrict__ ln_b, __nv_bfloat16* __restrict__ out, int B, int H, int W, int C,
-                         float eps, int split, long long* trace) {
+                         int c_real, float eps, int split, long long* trace) {
   ptx::griddep_launch();
   ptx::griddep_wait();
   static_assert(R == 1 || R == 2, "rows per thread");
@@ -376,14 +376,15 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
   {
     float tot = 0.f;
     for (int k = 0; k < nparts; ++k) tot += s_parts[k * NPIX + pix].x;
-    mean_p = tot / (float)C;
+    mean_p = tot / (float)c_real;
     float m2 = 0.f;
     for (int k = 0; k < nparts; ++k) {
       const float2 v = s_parts[k * NPIX + pix];
       const float d = v.x * INV_W - mean_p;
       m2 += fmaf(64.0f * d, d, v.y);
     }
-    rstd_p = rsqrtf(m2 / (float)C + eps);
+    m2 = fmaf(-(float)(C - c_real) * mean_p, mean_p, m2);   // zero pad channels each added mean^2 (exact no-op when c_real == C)
+    rstd_p = rsqrtf(m2 / (float)c_real + eps);
   }
   // ---- normalise + affine, bf16x2 out (a warp writes 128 contiguous bytes per pixel) ----
   const float gw0 = __ldg(ln_w + c0 + cl), gw1 = __ldg(ln_w + c0 + cl + 1);
@@ -417,13 +418,14 @@ dwconv_ln_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
 // source pixels of the 2x2 patch up front (4 x C fp32 in flight per warp -- the one-pixel-per-warp form was latency
 // bound at 1.4 TB/s), normalises each over its C channels with interleaved shuffle reductions, and writes the
 // patch row [p00 C | p01 C | p10 C | p11 C] (bf16, plus the lo halves in split mode).  C = 128 * NV.
-template <int NV>
+template <int NV, int VW>
 __global__ void __launch_bounds__(256)
 ln_patchify2_kernel(const float* __restrict__ x, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                    __nv_bfloat16* __restrict__ out, int B, int H, int W, float eps, int split) {
+                    __nv_bfloat16* __restrict__ out, int B, int H, int W, float eps, int split, int c_real) {
   ptx::griddep_launch();
   ptx::griddep_wait();
-  constexpr int C = 128 * NV;
+  // C = 32 * VW * NV: lane owns VW consecutive channels of every 32 * VW-channel group (VW = 4: C % 128 == 0; VW = 2: C % 64 == 0)
+  constexpr int C = 32 * VW * NV;
   const int OW = W / 2, OH = H / 2;
   const long long m2 = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (m2 >= (long long)B * OH * OW) return;
@@ -431,19 +433,30 @@ ln_patchify2_kernel(const float* __restrict__ x, const float* __restrict__ ln_w,
   const int ox = (int)(m2 % OW);
   const int oy = (int)((m2 / OW) % OH);
   const int b = (int)(m2 / ((long long)OW * OH));
-  float4 v[4][NV];
+  float v[4][NV][VW];
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
     const float* src = x + (((long long)b * H + (2 * oy + (p >> 1))) * W + (2 * ox + (p & 1))) * C;
 #pragma unroll
-    for (int k = 0; k < NV; ++k) v[p][k] = *reinterpret_cast<const float4*>(src + (k * 32 + lane) * 4);
+    for (int k = 0; k < NV; ++k) {
+      if constexpr (VW == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(src + (k * 32 + lane) * 4);
+        v[p][k][0] = t.x; v[p][k][1] = t.y; v[p][k][2] = t.z; v[p][k][3] = t.w;
+      } else {
+        const float2 t = *reinterpret_cast<const float2*>(src + (k * 32 + lane) * 2);
+        v[p][k][0] = t.x; v[p][k][1] = t.y;
+      }
+    }
   }
   float s[4], q[4];
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
     s[p] = 0.f;
 #pragma unroll
-    for (int k = 0; k < NV; ++k) s[p] += (v[p][k].x + v[p][k].y) + (v[p][k].z + v[p][k].w);
+    for (int k = 0; k < NV; ++k) {
+      if constexpr (VW == 4) s[p] += (v[p][k][0] + v[p][k][1]) + (v[p][k][2] + v[p][k][3]);
+      else s[p] += v[p][k][0] + v[p][k][1];
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
@@ -451,12 +464,17 @@ ln_patchify2_kernel(const float* __restrict__ x, const float* __restrict__ ln_w,
     for (int p = 0; p < 4; ++p) s[p] += __shfl_xor_sync(0xffffffffu, s[p], o);
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
-    s[p] = s[p] / (float)C;   // mean
+    s[p] = s[p] / (float)c_real;   // mean (zero pad channels do not contribute to the sum)
     q[p] = 0.f;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      const float dx = v[p][k].x - s[p], dy = v[p][k].y - s[p], dz = v[p][k].z - s[p], dw = v[p][k].w - s[p];
-      q[p] += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+      if constexpr (VW == 4) {
+        const float dx = v[p][k][0] - s[p], dy = v[p][k][1] - s[p], dz = v[p][k][2] - s[p], dw = v[p][k][3] - s[p];
+        q[p] += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+      } else {
+        const float dx = v[p][k][0] - s[p], dy = v[p][k][1] - s[p];
+        q[p] += dx * dx + dy * dy;
+      }
     }
   }
 #pragma unroll
@@ -466,25 +484,25 @@ ln_patchify2_kernel(const float* __restrict__ x, const float* __restrict__ ln_w,
   __nv_bfloat16* dst = out + m2 * ((split ? 8LL : 4LL) * C);
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
-    const int c = (k * 32 + lane) * 4;
-    const float4 gw = *reinterpret_cast<const float4*>(ln_w + c);
-    const float4 gb = *reinterpret_cast<const float4*>(ln_b + c);
+    const int c = (k * 32 + lane) * VW;
+    float gw[VW], gb[VW];
+#pragma unroll
+    for (int e = 0; e < VW; ++e) { gw[e] = __ldg(ln_w + c + e); gb[e] = __ldg(ln_b + c + e); }
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
-      const float r = rsqrtf(q[p] / (float)C + eps);
-      const float o0 = fmaf((v[p][k].x - s[p]) * r, gw.x, gb.x), o1 = fmaf((v[p][k].y - s[p]) * r, gw.y, gb.y);
-      const float o2 = fmaf((v[p][k].z - s[p]) * r, gw.z, gb.z), o3 = fmaf((v[p][k].w - s[p]) * r, gw.w, gb.w);
-      const __nv_bfloat162 p0 = __floats2bfloat162_rn(o0, o1), p1 = __floats2bfloat162_rn(o2, o3);
-      uint2 u;
-      u.x = *reinterpret_cast<const uint32_t*>(&p0);
-      u.y = *reinterpret_cast<const uint32_t*>(&p1);
-      *reinterpret_cast<uint2*>(dst + p * C + c) = u;
-      if (split) {
-        const float2 f0 = __bfloat1622float2(p0), f1 = __bfloat1622float2(p1);
-        uint2 ul;
-        ul.x = pack_bf16(o0 - f0.x, o1 - f0.y);
-        ul.y = pack_bf16(o2 - f1.x, o3 - f1.y);
-        *reinterpret_cast<uint2*>(dst + 4LL * C + p * C + c) = ul;   // lo half of the [hi 4C | lo 4C] row
+      // each zero pad channel added mean^2 to q (exact no-op when c_real == C)
+      const float r = rsqrtf(fmaf(-(float)(C - c_real) * s[p], s[p], q[p]) / (float)c_real + eps);
+      float o[VW];
+#pragma unroll
+      for (int e = 0; e < VW; ++e) o[e] = fmaf((v[p][k][e] - s[p]) * r, gw[e], gb[e]);
+#pragma unroll
+      for (int e = 0; e < VW; e += 2) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(o[e], o[e + 1]);
+        *reinterpret_cast<__nv_bfloat162*>(dst + p * C + c + e) = h2;
+        if (split) {
+          const float2 f = __bfloat1622float2(h2);
+          *reinterpret_cast<uint32_t*>(dst + 4LL * C + p * C + c + e) = pack_bf16(o[e] - f.x, o[e + 1] - f.y);   // lo half of [hi 4C | lo 4C]
+        }
       }
     }
   }
@@ -819,7 +837,7 @@ int launch_stem_patchify(const float* img, __nv_bfloat16* out, int B, int H, int
 template <int TW, int TH, int CPC, int R, int MINB>
 static int launch_dwconv_cluster(const float* x, const float* w49c, const float* bias, const float* ln_w,
                                  const float* ln_b, __nv_bfloat16* out, int B, int H, int W, int C, float eps,
-                                 int split, cudaStream_t st) {
+                                 int split, cudaStream_t st, int c_real) {
   constexpr int IW = TW + 6, IH = TH + 6;
   constexpr int NPIX = TW * TH;
   constexpr int NTHREADS = (CPC / 2) * TH / R;
@@ -861,7 +879,7 @@ static int launch_dwconv_cluster(const float* x, const float* w49c, const float*
   static long long* d_trace = nullptr;
   if (trace_on && !d_trace) GDRN_CHECK_CUDA(cudaMalloc(&d_trace, 8 * sizeof(long long)));
   long long* trp = trace_on ? d_trace : nullptr;
-  GDRN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kfn, tmap, tmap_w, bias, ln_w, ln_b, out, B, H, W, C, eps, split, trp));
+  GDRN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kfn, tmap, tmap_w, bias, ln_w, ln_b, out, B, H, W, C, c_real, eps, split, trp));
   gdrn_count_launch(1);
   if (trace_on) {
     long long h[5];
@@ -874,21 +892,23 @@ static int launch_dwconv_cluster(const float* x, const float* w49c, const float*
 }
 
 int launch_dwconv_ln(const float* x, const float* w49c, const float* bias, const float* ln_w, const float* ln_b,
-                     __nv_bfloat16* out, int B, int H, int W, int C, float eps, int split, cudaStream_t st) {
-  return launch_dwconv_ln_variant(x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps, split, -1, st);
+                     __nv_bfloat16* out, int B, int H, int W, int C, float eps, int split, cudaStream_t st, int c_real) {
+  return launch_dwconv_ln_variant(x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps, split, -1, st, c_real);
 }
 
 // variant: -1 = default choice (env GDRN_DW_PP), 0 = one-tile-per-CTA cluster kernel, 1 = persistent ping-pong kernel
 int launch_dwconv_ln_variant(const float* x, const float* w49c, const float* bias, const float* ln_w, const float* ln_b,
                              __nv_bfloat16* out, int B, int H, int W, int C, float eps, int split, int variant,
-                             cudaStream_t st) {
-  GDRN_REQUIRE(C % 128 == 0 && C <= 1024, "dwconv: C must be a multiple of 128 and <= 1024");
+                             cudaStream_t st, int c_real) {
+  GDRN_REQUIRE(C % 64 == 0 && C <= 1024, "dwconv: C must be a multiple of 64 and <= 1024");
+  if (c_real <= 0) c_real = C;
+  GDRN_REQUIRE(c_real <= C && C - c_real < 64, "dwconv: c_real must be within the last 64-channel slice of C");
   // cluster kernel: 16x8 tiles x 64 channels (cluster C/64 <= 8) or 8x8 tiles x 128 channels (cluster C/128 <= 8)
   static int rows = -1;  // GDRN_DW_ROWS=2: two output rows per thread (half the LDS traffic, half the warps: measured 4 % slower)
   if (rows < 0) { const char* e = getenv("GDRN_DW_ROWS"); rows = (e && atoi(e) == 2) ? 2 : 1; }
   static int var = -1;   // GDRN_DW_VARIANT: tile-shape experiments
   if (var < 0) { const char* e = getenv("GDRN_DW_VARIANT"); var = e ? atoi(e) : 0; }
-#define DW_ARGS x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps, split, st
+#define DW_ARGS x, w49c, bias, ln_w, ln_b, out, B, H, W, C, eps, split, st, c_real
   static int pp = -1;    // GDRN_DW_PP=0: one-tile-per-CTA kernel instead of the persistent ping-pong kernel (A/B experiments)
   if (pp < 0) { const char* e = getenv("GDRN_DW_PP"); pp = e ? atoi(e) : 1; }
   const bool want_pp = variant == 1 || (variant < 0 && pp && var == 0 && rows == 1 && (long long)B * (H / 8) * (W / 16) >= 32);
@@ -903,10 +923,11 @@ int launch_dwconv_ln_variant(const float* x, const float* w49c, const float* bia
     if (var == 3) return launch_dwconv_cluster<8, 4, 64, 1, 4>(DW_ARGS);    // 50 KB: 4 CTAs / SM, 128 threads
     return rows == 2 ? launch_dwconv_cluster<16, 8, 64, 2, 2>(DW_ARGS) : launch_dwconv_cluster<16, 8, 64, 1, 2>(DW_ARGS);
   }
-  if (H % 8 == 0 && W % 8 == 0 && C / 128 <= 8)
+  if (H % 8 == 0 && W % 8 == 0 && C % 128 == 0 && C / 128 <= 8)
     return rows == 2 ? launch_dwconv_cluster<8, 8, 128, 2, 1>(DW_ARGS) : launch_dwconv_cluster<8, 8, 128, 1, 1>(DW_ARGS);
 #undef DW_ARGS
   GDRN_REQUIRE(!split, "dwconv: the non-cluster fallback kernel has no split-bf16 output");
+  GDRN_REQUIRE(c_real == C && C % 128 == 0, "dwconv: the non-cluster fallback kernel needs C % 128 == 0 and no pad channels");
   const int S = 256 / (C / 4);
   if (W % 16 == 0) {
     long long strips = (long long)B * H * (W / 16);
@@ -922,17 +943,24 @@ int launch_dwconv_ln_variant(const float* x, const float* w49c, const float* bia
 }
 
 int launch_ln_patchify2(const float* x, const float* ln_w, const float* ln_b, __nv_bfloat16* out, int B, int H, int W,
-                        int C, float eps, int split, cudaStream_t st) {
-  GDRN_REQUIRE(C % 128 == 0 && C <= 512 && H % 2 == 0 && W % 2 == 0, "ln_patchify2: unsupported shape");
+                        int C, float eps, int split, cudaStream_t st, int c_real) {
+  GDRN_REQUIRE(C % 64 == 0 && C <= 512 && H % 2 == 0 && W % 2 == 0, "ln_patchify2: unsupported shape");
+  if (c_real <= 0) c_real = C;
+  GDRN_REQUIRE(c_real <= C, "ln_patchify2: c_real > C");
   const long long total = (long long)B * (H / 2) * (W / 2);
   const int blocks = (int)((total + 7) / 8);
-  if (C == 128) GDRN_CHECK_CUDA(gdrn_launch_dep(ln_patchify2_kernel<1>, dim3(blocks), dim3(256), 0, st, x, ln_w, ln_b, out, B, H, W, eps, split));
-  else if (C == 256) GDRN_CHECK_CUDA(gdrn_launch_dep(ln_patchify2_kernel<2>, dim3(blocks), dim3(256), 0, st, x, ln_w, ln_b, out, B, H, W, eps, split));
-  else if (C == 384) GDRN_CHECK_CUDA(gdrn_launch_dep(ln_patchify2_kernel<3>, dim3(blocks), dim3(256), 0, st, x, ln_w, ln_b, out, B, H, W, eps, split));
-  else GDRN_CHECK_CUDA(gdrn_launch_dep(ln_patchify2_kernel<4>, dim3(blocks), dim3(256), 0, st, x, ln_w, ln_b, out, B, H, W, eps, split));
-  GDRN_CHECK_CUDA(cudaGetLastError());
-  gdrn_count_launch(1);
-  return GDRN_OK;
+#define LNP_CASE(CC, NV, VW)                                                                                              \
+  if (C == CC) {                                                                                                        \
+    GDRN_CHECK_CUDA(gdrn_launch_dep(ln_patchify2_kernel<NV, VW>, dim3(blocks), dim3(256), 0, st, x, ln_w, ln_b, out, B, H, W, eps, \
+                                    split, c_real));                                                                    \
+    gdrn_count_launch(1);                                                                                               \
+    return GDRN_OK;                                                                                                     \
+  }
+  LNP_CASE(128, 1, 4) LNP_CASE(256, 2, 4) LNP_CASE(384, 3, 4) LNP_CASE(512, 4, 4)
+  LNP_CASE(64, 1, 2) LNP_CASE(192, 3, 2) LNP_CASE(320, 5, 2) LNP_CASE(448, 7, 2)
+#undef LNP_CASE
+  GDRN_REQUIRE(false, "ln_patchify2: unsupported channel count");
+  return GDRN_ERR_INVALID;
 }
 
 int launch_cast_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t st) {

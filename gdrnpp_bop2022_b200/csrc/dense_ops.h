@@ -19,19 +19,21 @@ int launch_stem_patchify(const float* img, __nv_bfloat16* out, int B, int H, int
 
 // ConvNeXt block front half: depthwise 7x7 (pad 3) + bias, LayerNorm over C (eps) -> bf16 [B*H*W, C]
 // x: fp32 NHWC; w: [49][C] (tap-major, repacked); all fp32.
+// c_real (0 = C): the tensor carries C - c_real trailing zero PAD channels (zero filter taps / bias / LN affine), e.g. the
+// 96-channel stage of convnext_tiny/small stored 128 wide; LayerNorm statistics are taken over the c_real channels.
 int launch_dwconv_ln(const float* x, const float* w49c, const float* bias, const float* ln_w, const float* ln_b,
-                     __nv_bfloat16* out, int B, int H, int W, int C, float eps, int split, cudaStream_t st);
+                     __nv_bfloat16* out, int B, int H, int W, int C, float eps, int split, cudaStream_t st, int c_real = 0);
 int launch_dwconv_ln_variant(const float* x, const float* w49c, const float* bias, const float* ln_w, const float* ln_b,
                              __nv_bfloat16* out, int B, int H, int W, int C, float eps, int split, int variant,
-                             cudaStream_t st);
+                             cudaStream_t st, int c_real = 0);
 // persistent two-warpgroup ping-pong version (dwconv_pp.cu) for 16x8x64 tiles; returns 1 if the shape is not handled
 int launch_dwconv_ln_pp(const float* x, const float* w49c, const float* bias, const float* ln_w, const float* ln_b,
-                        __nv_bfloat16* out, int B, int H, int W, int C, float eps, int split, cudaStream_t st);
+                        __nv_bfloat16* out, int B, int H, int W, int C, float eps, int split, cudaStream_t st, int c_real = 0);
 
 // downsample front half: per-pixel LayerNorm over C then 2x2/s2 patchify -> bf16 [B*(H/2)*(W/2), 4*C]
 // (k = (ky*2+kx)*C + c)
 int launch_ln_patchify2(const float* x, const float* ln_w, const float* ln_b, __nv_bfloat16* out, int B, int H, int W,
-                        int C, float eps, int split, cudaStream_t st);
+                        int C, float eps, int split, cudaStream_t st, int c_real = 0);
 
 int launch_cast_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t st);
 

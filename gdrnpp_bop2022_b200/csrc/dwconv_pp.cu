@@ -47,8 +47,8 @@ constexpr size_t PP_SMEM = (size_t)(2 * PP_SLOT_FLOATS + 49 * PP_CPC) * 4 + (siz
 __global__ void __launch_bounds__(2 * PP_WG_THREADS, 1)
 dwconv_ln_pp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                     const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                    __nv_bfloat16* __restrict__ out, int B, int H, int W, int C, float eps, int split, int use_token,
-                    long long* trace) {
+                    __nv_bfloat16* __restrict__ out, int B, int H, int W, int C, int c_real, float eps, int split,
+                    int use_token, long long* trace) {
   constexpr int TW = PP_TW, TH = PP_TH, CPC = PP_CPC, IW = PP_IW, NPIX = PP_NPIX;
   constexpr int NV = TW;              // pixels per thread (one output row)
   constexpr int LPP = 32 / NV;        // lanes per pixel after the transposing reduction (2)
@@ -192,14 +192,15 @@ dwconv_ln_pp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     {
       float tot = 0.f;
       for (int r = 0; r < nrank; ++r) tot += my_parts[r * NPIX + pix].x;
-      mean_p = tot / (float)C;
+      mean_p = tot / (float)c_real;
       float m2 = 0.f;
       for (int r = 0; r < nrank; ++r) {
         const float2 v = my_parts[r * NPIX + pix];
         const float d = v.x * INV_W - mean_p;
         m2 += fmaf(64.0f * d, d, v.y);
       }
-      rstd_p = rsqrtf(m2 / (float)C + eps);
+      m2 = fmaf(-(float)(C - c_real) * mean_p, mean_p, m2);   // zero pad channels each added mean^2 (exact no-op when c_real == C)
+      rstd_p = rsqrtf(m2 / (float)c_real + eps);
     }
     // re-arm this (wg, buffer) barrier for its next use (tile i + 2): strictly before this CTA's own push of tile i + 1,
     // which is what a peer needs before it can push tile i + 2 (see the banner)
@@ -229,7 +230,8 @@ dwconv_ln_pp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 
 // returns GDRN_OK when launched, 1 when the shape is not handled by this kernel (caller falls back)
 int launch_dwconv_ln_pp(const float* x, const float* w49c, const float* bias, const float* ln_w, const float* ln_b,
-                        __nv_bfloat16* out, int B, int H, int W, int C, float eps, int split, cudaStream_t st) {
+                        __nv_bfloat16* out, int B, int H, int W, int C, float eps, int split, cudaStream_t st, int c_real) {
+  if (c_real <= 0) c_real = C;
   if (!(H % PP_TH == 0 && W % PP_TW == 0 && C % PP_CPC == 0 && C / PP_CPC <= PP_MAX_RANKS && C / PP_CPC >= 1)) return 1;
   const int csize = C / PP_CPC;
   auto kfn = dwconv_ln_pp_kernel;
@@ -283,7 +285,7 @@ int launch_dwconv_ln_pp(const float* x, const float* w49c, const float* bias, co
   long long* trp = trace_on ? d_trace : nullptr;
   static int token = -1;     // GDRN_DW_TOKEN=0: no hand-over of the FMA pipe between the warpgroups (measured 3-4 % slower)
   if (token < 0) { const char* e = getenv("GDRN_DW_TOKEN"); token = e ? atoi(e) : 1; }
-  GDRN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kfn, tmap, tmap_w, bias, ln_w, ln_b, out, B, H, W, C, eps, split, token, trp));
+  GDRN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kfn, tmap, tmap_w, bias, ln_w, ln_b, out, B, H, W, C, c_real, eps, split, token, trp));
   gdrn_count_launch(1);
   if (trace_on) {
     long long h[8];

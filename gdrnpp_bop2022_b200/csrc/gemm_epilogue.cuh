@@ -220,7 +220,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmPlan& p, int m_tile, int
 #pragma unroll
       for (int j = 0; j < CH; ++j) sum += v[j] + bias[j];
     }
-    const float mean = sum / (float)p.N;
+    const int ln_n = p.ln_n > 0 ? p.ln_n : p.N;
+    const float mean = sum / (float)ln_n;
     float sq = 0.f;
 #pragma unroll 1
     for (int c = 0; c < p.N; c += CH) {
@@ -230,7 +231,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmPlan& p, int m_tile, int
 #pragma unroll
       for (int j = 0; j < CH; ++j) { float d = v[j] + bias[j] - mean; sq = fmaf(d, d, sq); }
     }
-    const float rstd = rsqrtf(sq / (float)p.N + p.ln_eps);
+    sq = fmaf(-(float)(p.N - ln_n) * mean, mean, sq);   // each zero pad column added mean^2 (exact no-op without padding)
+    const float rstd = rsqrtf(sq / (float)ln_n + p.ln_eps);
 #pragma unroll 1
     for (int c = 0; c < p.N; c += CH) {
       float v[CH], bias[CH], w[CH], bb[CH];

@@ -357,6 +357,7 @@ int gemm_tc_launch(const GemmPlan& plan_in, int block_n, cudaStream_t stream) {
   GDRN_GEMM_CASE(128, EPI_GNSTATS)
   GDRN_GEMM_CASE(128, EPI_BIAS_LN)
   GDRN_GEMM_CASE(64, EPI_GELU)
+  GDRN_GEMM_CASE(64, EPI_RESID)
   GDRN_GEMM_CASE(64, EPI_STORE)
   GDRN_GEMM_CASE(64, EPI_GNSTATS)
   GDRN_GEMM_CASE(16, EPI_STORE)

@@ -68,6 +68,7 @@ struct GemmPlan {
   double* gn_stats;     // EPI_GNSTATS [B, groups, 2]
   int gn_groups, gn_cpg;    // groups per image, channels per group
   const float* ln_w; const float* ln_b; float ln_eps;  // EPI_BIAS_LN
+  int ln_n;             // EPI_BIAS_LN: LayerNorm width (0 = N); columns [ln_n, N) are zero PAD channels (zero weight rows / bias / affine)
   // EPI_OUTCONV
   const long long* roi_classes;  // [B]
   int num_classes;               // roi_classes are clamped to [0, num_classes)

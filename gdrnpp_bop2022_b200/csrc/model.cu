@@ -31,14 +31,18 @@ namespace {
 
 struct Arch {
   int depths[4];
-  int dims[4];
+  int dims[4];   // channels of the reference model
+  int cp[4];     // stored channel width: dims rounded up to a multiple of 64 (GEMM k-chunk / depthwise channel slice); the pad
+                 // channels carry zero weights, biases and affines everywhere, so they stay exactly zero through the network
 };
 
 bool get_arch(const char* name, Arch* a) {
-  if (!strcmp(name, "convnext_base")) { *a = {{3, 3, 27, 3}, {128, 256, 512, 1024}}; return true; }
-  if (!strcmp(name, "convnext_small")) { *a = {{3, 3, 27, 3}, {96, 192, 384, 768}}; return true; }
-  if (!strcmp(name, "convnext_tiny")) { *a = {{3, 3, 9, 3}, {96, 192, 384, 768}}; return true; }
-  return false;
+  if (!strcmp(name, "convnext_base")) *a = {{3, 3, 27, 3}, {128, 256, 512, 1024}, {0, 0, 0, 0}};
+  else if (!strcmp(name, "convnext_small")) *a = {{3, 3, 27, 3}, {96, 192, 384, 768}, {0, 0, 0, 0}};
+  else if (!strcmp(name, "convnext_tiny")) *a = {{3, 3, 9, 3}, {96, 192, 384, 768}, {0, 0, 0, 0}};
+  else return false;
+  for (int s = 0; s < 4; ++s) a->cp[s] = (a->dims[s] + 63) / 64 * 64;
+  return true;
 }
 
 struct BlockW {
@@ -146,50 +150,50 @@ void add_copy(GdrnModel* m, const std::string& key, void* dst, int is_bf16, long
 
 bool build_weights(GdrnModel* m) {
   const Arch& a = m->arch;
-  const int C0 = a.dims[0], C3 = a.dims[3];
+  const int C0 = a.dims[0], C0p = a.cp[0], C3 = a.dims[3], C3p = a.cp[3];
   const int nc = m->num_classes;
   const int S = m->precise ? 2 : 1;  // bf16 weight rows are [hi Ktot | lo Ktot] in precise mode
   auto LO = [&](long long ktot) { return S == 2 ? ktot : 0LL; };
   bool ok = true;
 #define ALLOC(ptr, T, n) ok = ok && ((ptr = dalloc<T>(m, (n))) != nullptr)
   // ---- stem ----
-  ALLOC(m->stem_w, __nv_bfloat16, (size_t)S * C0 * 64);
-  ALLOC(m->stem_b, float, C0); ALLOC(m->stem_ln_w, float, C0); ALLOC(m->stem_ln_b, float, C0);
+  ALLOC(m->stem_w, __nv_bfloat16, (size_t)S * C0p * 64);
+  ALLOC(m->stem_b, float, C0p); ALLOC(m->stem_ln_w, float, C0p); ALLOC(m->stem_ln_b, float, C0p);
   if (!ok) return false;
   add_copy(m, "backbone.stem_0.weight", m->stem_w, 1, C0, 48, S * 64, 0, LO(64));
   add_copy(m, "backbone.stem_0.bias", m->stem_b, 0, 1, C0, C0);
   add_copy(m, "backbone.stem_1.weight", m->stem_ln_w, 0, 1, C0, C0);
   add_copy(m, "backbone.stem_1.bias", m->stem_ln_b, 0, 1, C0, C0);
   for (int s = 0; s < 4; ++s) {
-    const int C = a.dims[s];
+    const int C = a.dims[s], Cp = a.cp[s];
     char buf[160];
     if (s > 0) {
-      const int Ci = a.dims[s - 1];
-      ALLOC(m->down[s].ln_w, float, Ci); ALLOC(m->down[s].ln_b, float, Ci);
-      ALLOC(m->down[s].w, __nv_bfloat16, (size_t)S * C * 4 * Ci);
-      ALLOC(m->down[s].b, float, C);
+      const int Ci = a.dims[s - 1], Cip = a.cp[s - 1];
+      ALLOC(m->down[s].ln_w, float, Cip); ALLOC(m->down[s].ln_b, float, Cip);
+      ALLOC(m->down[s].w, __nv_bfloat16, (size_t)S * Cp * 4 * Cip);
+      ALLOC(m->down[s].b, float, Cp);
       if (!ok) return false;
       snprintf(buf, sizeof(buf), "backbone.stages_%d.downsample.0.weight", s); add_copy(m, buf, m->down[s].ln_w, 0, 1, Ci, Ci);
       snprintf(buf, sizeof(buf), "backbone.stages_%d.downsample.0.bias", s); add_copy(m, buf, m->down[s].ln_b, 0, 1, Ci, Ci);
       // [C][Ci][2][2] -> [C][tap][Ci]
       snprintf(buf, sizeof(buf), "backbone.stages_%d.downsample.1.weight", s);
-      add_loader(m, buf, m->down[s].w, 1, pd(1, C, 4, Ci, 0, (long long)Ci * 4, 1, 4, 0, (long long)S * 4 * Ci, Ci, 1, 0, 0, LO(4 * Ci)), (long long)C * Ci * 4);
+      add_loader(m, buf, m->down[s].w, 1, pd(1, C, 4, Ci, 0, (long long)Ci * 4, 1, 4, 0, (long long)S * 4 * Cip, Cip, 1, 0, 0, LO(4 * Cip)), (long long)C * Ci * 4);
       snprintf(buf, sizeof(buf), "backbone.stages_%d.downsample.1.bias", s); add_copy(m, buf, m->down[s].b, 0, 1, C, C);
     }
     m->blocks[s].resize(a.depths[s]);
     for (int i = 0; i < a.depths[s]; ++i) {
       BlockW& w = m->blocks[s][i];
-      ALLOC(w.dw_w, float, (size_t)49 * C); ALLOC(w.dw_b, float, C); ALLOC(w.ln_w, float, C); ALLOC(w.ln_b, float, C);
-      ALLOC(w.fc1_w, __nv_bfloat16, (size_t)S * 4 * C * C); ALLOC(w.fc1_b, float, 4 * C);
-      ALLOC(w.fc2_w, __nv_bfloat16, (size_t)S * 4 * C * C); ALLOC(w.fc2_b, float, C); ALLOC(w.gamma, float, C);
+      ALLOC(w.dw_w, float, (size_t)49 * Cp); ALLOC(w.dw_b, float, Cp); ALLOC(w.ln_w, float, Cp); ALLOC(w.ln_b, float, Cp);
+      ALLOC(w.fc1_w, __nv_bfloat16, (size_t)S * 4 * C * Cp); ALLOC(w.fc1_b, float, 4 * C);   // hidden width stays 4 * C
+      ALLOC(w.fc2_w, __nv_bfloat16, (size_t)S * 4 * C * Cp); ALLOC(w.fc2_b, float, Cp); ALLOC(w.gamma, float, Cp);
       if (!ok) return false;
       std::string p = "backbone.stages_" + std::to_string(s) + ".blocks." + std::to_string(i) + ".";
       // conv_dw.weight [C][1][7][7] -> [49][C]
-      add_loader(m, p + "conv_dw.weight", w.dw_w, 0, pd(1, 1, 49, C, 0, 0, 1, 49, 0, 0, C, 1), (long long)C * 49);
+      add_loader(m, p + "conv_dw.weight", w.dw_w, 0, pd(1, 1, 49, C, 0, 0, 1, 49, 0, 0, Cp, 1), (long long)C * 49);
       add_copy(m, p + "conv_dw.bias", w.dw_b, 0, 1, C, C);
       add_copy(m, p + "norm.weight", w.ln_w, 0, 1, C, C);
       add_copy(m, p + "norm.bias", w.ln_b, 0, 1, C, C);
-      add_copy(m, p + "mlp.fc1.weight", w.fc1_w, 1, 4 * C, C, S * C, 0, LO(C));
+      add_copy(m, p + "mlp.fc1.weight", w.fc1_w, 1, 4 * C, C, S * Cp, 0, LO(Cp));
       add_copy(m, p + "mlp.fc1.bias", w.fc1_b, 0, 1, 4 * C, 4 * C);
       add_copy(m, p + "mlp.fc2.weight", w.fc2_w, 1, C, 4 * C, S * 4 * C, 0, LO(4 * C));
       add_copy(m, p + "mlp.fc2.bias", w.fc2_b, 0, 1, C, C);
@@ -202,13 +206,13 @@ bool build_weights(GdrnModel* m) {
     for (int px = 0; px < 2; ++px) {
       const int nty = py ? 2 : 1, ntx = px ? 2 : 1;
       const int par = py * 2 + px;
-      ALLOC(m->deconv_w[par], __nv_bfloat16, (size_t)S * 256 * nty * ntx * C3);
+      ALLOC(m->deconv_w[par], __nv_bfloat16, (size_t)S * 256 * nty * ntx * C3p);
       if (!ok) return false;
       // dst [o][jy][jx][i]; src index = i*256*9 + o*9 + (ky*3+kx), ky = py ? 2*jy : 1, kx = px ? 2*jx : 1
       const long long soff = (py ? 0 : 3) + (px ? 0 : 1);
       // dims (o, jy, jx, i)
-      PackDesc d = pd(256, nty, ntx, C3, 9, 6, 2, (long long)256 * 9, (long long)S * nty * ntx * C3, (long long)ntx * C3, C3, 1, soff, 0,
-                      LO((long long)nty * ntx * C3));
+      PackDesc d = pd(256, nty, ntx, C3, 9, 6, 2, (long long)256 * 9, (long long)S * nty * ntx * C3p, (long long)ntx * C3p, C3p, 1, soff, 0,
+                      LO((long long)nty * ntx * C3p));
       add_loader(m, "geo_head_net.features.0.weight", m->deconv_w[par], 1, d, (long long)C3 * 256 * 9);
     }
   const char* gn_names[7] = {"features.1", "features.3.gn", "features.4.gn", "features.6.gn",
@@ -306,14 +310,14 @@ Workspace carve(const GdrnModel* m, int B, void* base) {
   size_t x_el = 0, a_el = M0 * 64, h_el = 0;
   for (int s = 0; s < 4; ++s) {
     size_t Ms = M0 >> (2 * s);
-    x_el = std::max(x_el, Ms * a.dims[s]);
-    a_el = std::max(a_el, Ms * a.dims[s]);
+    x_el = std::max(x_el, Ms * a.cp[s]);
+    a_el = std::max(a_el, Ms * a.cp[s]);
     h_el = std::max(h_el, Ms * a.dims[s] * 4);
   }
   w.X = reinterpret_cast<float*>(take(x_el * 4));
   w.A = reinterpret_cast<__nv_bfloat16*>(take(S * a_el * 2));
   w.Hb = reinterpret_cast<__nv_bfloat16*>(take(S * h_el * 2));
-  w.feat = reinterpret_cast<__nv_bfloat16*>(take(S * B * 64 * a.dims[3] * 2));
+  w.feat = reinterpret_cast<__nv_bfloat16*>(take(S * B * 64 * a.cp[3] * 2));
   w.R = reinterpret_cast<__nv_bfloat16*>(take(S * M0 * 256 * 2));  // precise: fp32 [M0,256]
   w.P = reinterpret_cast<__nv_bfloat16*>(take(S * M0 * 256 * 2));
   w.Q = reinterpret_cast<__nv_bfloat16*>(take(S * M0 * 256 * 2));
@@ -534,66 +538,71 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
   const long long M0 = (long long)B * 64 * 64;
   RCP(2, launch_stem_patchify(roi_img, w.A, B, 256, 256, PR, st));
   {
-    const int C0 = a.dims[0];
+    const int C0 = a.dims[0], C0p = a.cp[0];
     reset();
     RC(plan_a2d(p, w.A, M0, 64, S));
-    if (C0 == 128) {
-      RC(plan_b(p, m->stem_w, C0, 64, 128, C0, S));
+    if (C0p == 128) {   // convnext_base (128) and tiny / small (96 stored 128 wide: pad rows of stem_w are zero)
+      RC(plan_b(p, m->stem_w, C0p, 64, 128, C0p, S));
       if (PR) set_x3(p, 64, 64);
-      p.epi = EPI_BIAS_LN; p.out = w.X; p.ldo = C0; p.bias = m->stem_b;
-      p.ln_w = m->stem_ln_w; p.ln_b = m->stem_ln_b; p.ln_eps = 1e-6f;
+      p.epi = EPI_BIAS_LN; p.out = w.X; p.ldo = C0p; p.bias = m->stem_b;
+      p.ln_w = m->stem_ln_w; p.ln_b = m->stem_ln_b; p.ln_eps = 1e-6f; p.ln_n = C0;
       RCP(0, gemm_tc_launch(p, 128, st));
     } else {
-      gdrn_set_last_error(__FILE__, __LINE__, "forward: only convnext_base (C0=128) has a fused stem epilogue so far");
+      gdrn_set_last_error(__FILE__, __LINE__, "forward: the fused stem epilogue needs a 128-wide (padded) first stage");
       return GDRN_ERR_INVALID;
     }
   }
+  // largest tile width the N dimension divides into (the CTA-pair kernels need N % block_n == 0)
+  auto pick_bn = [](int N) { return N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64); };
   // ---------------- stages ----------------
   int res = 64;
   for (int s = 0; s < 4; ++s) {
-    const int C = a.dims[s];
+    const int Cr = a.dims[s];   // channels of the reference model
+    const int C = a.cp[s];      // stored width (pad channels are zero)
     if (s > 0) {
-      const int Ci = a.dims[s - 1];
-      RCP(2, launch_ln_patchify2(w.X, m->down[s].ln_w, m->down[s].ln_b, w.A, B, res, res, Ci, 1e-6f, PR, st));
+      const int Ci = a.cp[s - 1];
+      RCP(2, launch_ln_patchify2(w.X, m->down[s].ln_w, m->down[s].ln_b, w.A, B, res, res, Ci, 1e-6f, PR, st, a.dims[s - 1]));
       res /= 2;
       const long long M = (long long)B * res * res;
       reset();
       RC(plan_a2d(p, w.A, M, 4 * Ci, S));
-      const int bn = 256;
+      const int bn = pick_bn(C);
       RC(plan_b(p, m->down[s].w, C, 4 * Ci, bn, C, S));
       if (PR) set_x3(p, 4 * Ci, 4 * Ci);
       p.epi = EPI_STORE; p.out_f32 = 1; p.out = w.X; p.ldo = C; p.bias = m->down[s].b;
       RCP(0, gemm_tc_launch(p, bn, st));
     }
+    const int H4 = 4 * Cr;      // hidden width of the MLP
     const long long M = (long long)B * res * res;
     for (int i = 0; i < a.depths[s]; ++i) {
       const BlockW& bw = m->blocks[s][i];
-      RCP(1, launch_dwconv_ln(w.X, bw.dw_w, bw.dw_b, bw.ln_w, bw.ln_b, w.A, B, res, res, C, 1e-6f, PR, st));
-      if (!PR && m->fuse_mlp && m->gelu_mode == 1 && mlp_fused_supported(C, M)) {
+      RCP(1, launch_dwconv_ln(w.X, bw.dw_w, bw.dw_b, bw.ln_w, bw.ln_b, w.A, B, res, res, C, 1e-6f, PR, st, Cr));
+      if (!PR && m->fuse_mlp && m->gelu_mode == 1 && Cr == C && mlp_fused_supported(C, M)) {
         // stage 0: fc1 -> GELU -> fc2 -> residual in one kernel (no 4C-wide Hb round trip through HBM)
         RCP(0, mlp_fused_launch(w.A, bw.fc1_w, bw.fc1_b, bw.fc2_w, bw.fc2_b, bw.gamma, w.X, M, C, st));
         continue;
       }
-      if (PR && m->fuse_mlp_x3 && mlp_fused_x3_supported(C, M)) {
+      if (PR && m->fuse_mlp_x3 && Cr == C && mlp_fused_x3_supported(C, M)) {
         RCP(0, mlp_fused_x3_launch(w.A, bw.fc1_w, bw.fc1_b, bw.fc2_w, bw.fc2_b, bw.gamma, w.X, M, C, st));
         continue;
       }
       reset();
       RC(plan_a2d(p, w.A, M, C, S));
-      RC(plan_b(p, bw.fc1_w, 4 * C, C, 256, 4 * C, S));
+      const int bn1 = pick_bn(H4);
+      RC(plan_b(p, bw.fc1_w, H4, C, bn1, H4, S));
       if (PR) set_x3(p, C, C);
-      p.epi = EPI_GELU; p.gelu_mode = gelu_mode; p.out = w.Hb; p.ldo = S * 4 * C; p.bias = bw.fc1_b;
-      RCP(0, gemm_tc_launch(p, 256, st));
+      p.epi = EPI_GELU; p.gelu_mode = gelu_mode; p.out = w.Hb; p.ldo = S * H4; p.bias = bw.fc1_b;
+      RCP(0, gemm_tc_launch(p, bn1, st));
       reset();
-      RC(plan_a2d(p, w.Hb, M, 4 * C, S));
-      const int bn2 = C >= 256 ? 256 : 128;
-      RC(plan_b(p, bw.fc2_w, C, 4 * C, bn2, C, S));
-      if (PR) set_x3(p, 4 * C, 4 * C);
+      RC(plan_a2d(p, w.Hb, M, H4, S));
+      const int bn2 = pick_bn(C);
+      RC(plan_b(p, bw.fc2_w, C, H4, bn2, C, S));
+      if (PR) set_x3(p, H4, H4);
       p.epi = EPI_RESID; p.out_f32 = 1; p.out = w.X; p.resid = w.X; p.ldo = C; p.bias = bw.fc2_b; p.gamma = bw.gamma;
       RCP(0, gemm_tc_launch(p, bn2, st));
     }
   }
-  const int C3 = a.dims[3];
+  const int C3 = a.cp[3];
   if (PR) RCP(2, launch_cast_split(w.X, w.feat, (long long)B * 64, C3, st));
   else RCP(2, launch_cast_bf16(w.X, w.feat, (long long)B * 64 * C3, st));
 

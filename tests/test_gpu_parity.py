@@ -257,6 +257,47 @@ def test_forward_vs_oracle_north_star_tolerance(dev, B):
     assert terr < 1e-3, terr                           # north_star: t within 1e-3
 
 
+@pytest.mark.parametrize("arch,B", [("convnext_tiny", 4), ("convnext_small", 2)])
+def test_forward_vs_oracle_convnext_tiny_small(dev, arch, B):
+    """The other ConvNeXt widths the reference's backbone factory accepts (models/net_factory.py:73-74; BASELINE configs[0]
+    names convnext_tiny): dims 96/192/384/768.  The 96-channel first stage is stored 128 wide with zero pad channels and the
+    LayerNorms take their statistics over the 96 real channels; both precision modes against the fp32 oracle (whose backbone
+    is pinned to torchvision's convnext_tiny / convnext_small in test_oracle_pinning.py)."""
+    from gdrnpp_bop2022_b200.gdrn_model import GDRN_DoubleMask, default_cfg
+    from gdrnpp_bop2022_b200.synthetic import make_batch, make_state_dict
+
+    sd = make_state_dict(arch=arch)
+    batch = make_batch(B=B, seed=90 + B)
+    with torch.no_grad():
+        ref = O.gdrn_forward(sd, batch, arch=arch, return_maps=True, return_intermediate=True)
+    gb = {k: v.to(dev) for k, v in batch.items()}
+    for precision in ("bf16x3", "bf16"):
+        model = GDRN_DoubleMask(default_cfg(arch=arch, with_maps=True), arch=arch, max_batch=max(B, 2), precision=precision)
+        model.load_state_dict(sd)
+        model.to(dev)
+        out = model(gb["roi_img"], roi_classes=gb["roi_classes"], roi_coord_2d=gb["roi_coord_2d"], roi_cams=gb["roi_cams"],
+                    roi_centers=gb["roi_centers"], roi_whs=gb["roi_whs"], roi_extents=gb["roi_extents"],
+                    resize_ratios=gb["resize_ratios"], return_raw=True)
+        torch.cuda.synchronize()
+        x3 = model.debug_read("stage3_x", B, B * 64 * 768).reshape(B, 8, 8, 768).permute(0, 3, 1, 2).cpu()
+        rel = ((x3 - ref["conv_feat"]).norm() / ref["conv_feat"].norm()).item()
+        raw = out["raw"].cpu()
+        rerr = _rot_err(out["rot"].cpu(), ref["rot"])
+        terr = (out["trans"].cpu() - ref["trans"]).abs().max().item()
+        if precision == "bf16x3":
+            assert rel < 1e-4, rel
+            for k in ("mask", "full_mask", "coor_x", "coor_y", "coor_z", "region"):
+                assert (out[k].cpu() - ref[k]).abs().max().item() < 2e-3, k
+            assert (raw[:, :6] - ref["rot6d"]).abs().max().item() < 1e-4
+            assert (raw[:, 6:] - ref["t_"]).abs().max().item() < 1e-4
+            kappa = _rot6d_conditioning(ref["rot6d"]).clamp_min(1.0)
+            assert (rerr < 1e-4 * kappa).all(), (rerr, kappa)
+            assert terr < 1e-3, terr
+        else:
+            assert rel < 0.02, rel
+            assert rerr.max().item() < 0.1 and terr < 1e-2, (rerr, terr)
+
+
 @pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
 def test_forward_vs_oracle_b64(dev, precision):
     """BASELINE.json configs[1] at its full size: the bench's own first batch (B = 64, seed 0, unmodified
