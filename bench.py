@@ -463,7 +463,7 @@ def main():
                          "tensor_executed_frac": 3 * gemm_tflops / peaks["bf16_tflops"]})
 
     # ---------------- secondary records (rank 0, one GPU): bf16 throughput mode, eager-GPU stand-in, native ops ----------------
-    alt, eager, native = None, None, None
+    alt, eager, native, backbones = None, None, None, None
     if world == 1 and not args.no_secondary:
         other = "bf16" if x3 else "bf16x3"
         m2 = GDRN_DoubleMask(default_cfg(), max_batch=BATCH, precision=other)
@@ -487,6 +487,31 @@ def main():
                        "split-bf16 parity mode (R within 1e-4 rad / t within 1e-3)"}
         del m2, g2
         torch.cuda.empty_cache()
+        # the other ConvNeXt widths the reference's backbone factory accepts (BASELINE configs[0] names convnext_tiny), same batch,
+        # same precision mode; parity: tests/test_gpu_parity.py::test_forward_vs_oracle_convnext_tiny_small
+        backbones = []
+        for arch in ("convnext_tiny", "convnext_small"):
+            try:
+                m3 = GDRN_DoubleMask(default_cfg(arch=arch), arch=arch, max_batch=BATCH, precision=args.precision)
+                m3.load_state_dict(make_state_dict(arch=arch))
+                m3.to(dev)
+                g3 = make_graphed(m3)
+                for i in range(NB):
+                    g3(resident[i])
+                torch.cuda.synchronize()
+                n3 = min(args.steps, 20)
+                e0.record()
+                for i in range(n3):
+                    g3(resident[i % NB])
+                e1.record()
+                torch.cuda.synchronize()
+                ms3 = e0.elapsed_time(e1) / n3
+                backbones.append({"arch": arch, "precision": args.precision, "value": BATCH / ms3 * 1e3, "unit": "ROIs/s",
+                                  "ms_per_step": ms3, "steps": n3, "graph_replay": bool(use_graphs)})
+                del m3, g3
+                torch.cuda.empty_cache()
+            except Exception as e:  # noqa: BLE001
+                backbones.append({"arch": arch, "error": "%s: %s" % (type(e).__name__, e)})
         try:
             eager = gpu_eager_baseline(dev)
         except Exception as e:  # noqa: BLE001
@@ -535,6 +560,7 @@ def main():
                        "bar": "R within 1e-4 rad, t within 1e-3 of the fp32 reference path (BASELINE.json north_star)",
                        "met": bool(x3), "test": "tests/test_gpu_parity.py::test_forward_vs_oracle_b64 (this batch, these weights)"},
             "bf16_mode" if x3 else "bf16x3_mode": alt,
+            "other_backbones": backbones,
             "gpu_eager_baseline": eager,
             "native_ops": native,
         }

@@ -486,8 +486,13 @@ ln_patchify2_kernel(const float* __restrict__ x, const float* __restrict__ ln_w,
   for (int k = 0; k < NV; ++k) {
     const int c = (k * 32 + lane) * VW;
     float gw[VW], gb[VW];
-#pragma unroll
-    for (int e = 0; e < VW; ++e) { gw[e] = __ldg(ln_w + c + e); gb[e] = __ldg(ln_b + c + e); }
+    if constexpr (VW == 4) {
+      const float4 w4 = *reinterpret_cast<const float4*>(ln_w + c), b4 = *reinterpret_cast<const float4*>(ln_b + c);
+      gw[0] = w4.x; gw[1] = w4.y; gw[2] = w4.z; gw[3] = w4.w; gb[0] = b4.x; gb[1] = b4.y; gb[2] = b4.z; gb[3] = b4.w;
+    } else {
+      const float2 w2 = *reinterpret_cast<const float2*>(ln_w + c), b2 = *reinterpret_cast<const float2*>(ln_b + c);
+      gw[0] = w2.x; gw[1] = w2.y; gb[0] = b2.x; gb[1] = b2.y;
+    }
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       // each zero pad channel added mean^2 to q (exact no-op when c_real == C)
@@ -495,14 +500,22 @@ ln_patchify2_kernel(const float* __restrict__ x, const float* __restrict__ ln_w,
       float o[VW];
 #pragma unroll
       for (int e = 0; e < VW; ++e) o[e] = fmaf((v[p][k][e] - s[p]) * r, gw[e], gb[e]);
+      uint32_t hw[VW / 2], lw[VW / 2];
 #pragma unroll
       for (int e = 0; e < VW; e += 2) {
         const __nv_bfloat162 h2 = __floats2bfloat162_rn(o[e], o[e + 1]);
-        *reinterpret_cast<__nv_bfloat162*>(dst + p * C + c + e) = h2;
-        if (split) {
-          const float2 f = __bfloat1622float2(h2);
-          *reinterpret_cast<uint32_t*>(dst + 4LL * C + p * C + c + e) = pack_bf16(o[e] - f.x, o[e + 1] - f.y);   // lo half of [hi 4C | lo 4C]
-        }
+        const float2 f = __bfloat1622float2(h2);
+        hw[e / 2] = *reinterpret_cast<const uint32_t*>(&h2);
+        lw[e / 2] = pack_bf16(o[e] - f.x, o[e + 1] - f.y);
+      }
+      __nv_bfloat16* dh = dst + p * C + c;
+      __nv_bfloat16* dl = dst + 4LL * C + p * C + c;      // lo half of the [hi 4C | lo 4C] row
+      if constexpr (VW == 4) {
+        *reinterpret_cast<uint2*>(dh) = make_uint2(hw[0], hw[1]);
+        if (split) *reinterpret_cast<uint2*>(dl) = make_uint2(lw[0], lw[1]);
+      } else {
+        *reinterpret_cast<uint32_t*>(dh) = hw[0];
+        if (split) *reinterpret_cast<uint32_t*>(dl) = lw[0];
       }
     }
   }

@@ -41,8 +41,9 @@ assert len(st) >= 2, "need at least one full step in the capture"
 step = [per[k] for k in ids[st[0]:st[1]]]
 agg = collections.defaultdict(lambda: {"launches": 0, "dram_read": 0.0, "dram_write": 0.0, "us": 0.0})
 for k in step:
-    fam = ("gemm (gemm_tc_kernel + gemm_pair_kernel + gemm_pair_x3_kernel + mlp_fused_kernel, all tcgen05 launches)"
-           if k["name"].startswith(("gemm_tc_kernel", "gemm_pair_kernel", "gemm_pair_x3_kernel", "mlp_fused_kernel")) else k["name"])
+    fam = ("gemm (gemm_tc_kernel + gemm_pair_kernel + gemm_pair_x3_kernel + mlp_fused_kernel + mlp_fused_x3_kernel, all tcgen05 launches)"
+           if k["name"].startswith(("gemm_tc_kernel", "gemm_pair_kernel", "gemm_pair_x3_kernel", "mlp_fused_kernel",
+                                    "mlp_fused_x3_kernel")) else k["name"])
     a = agg[fam]
     a["launches"] += 1
     a["dram_read"] += k.get("dram__bytes_read.sum", 0)
@@ -54,6 +55,6 @@ for f, a in agg.items():
     out["families"][f] = {"launches": a["launches"],
                           "dram_bytes_per_launch": (a["dram_read"] + a["dram_write"]) / a["launches"],
                           "dram_read_total": a["dram_read"], "dram_write_total": a["dram_write"], "us_total": a["us"]}
-path = os.path.join(ROOT, "profiles", f"{tag}_traffic.json")
+path = os.path.join(ROOT, "profiles", tag if tag.endswith(".json") else f"{tag}_traffic.json")
 json.dump(out, open(path, "w"), indent=1)
 print("wrote", path, {f: round(v["dram_bytes_per_launch"] / 1e6, 1) for f, v in out["families"].items()})
