@@ -145,14 +145,25 @@ gemm_pair_x3_kernel(const __grid_constant__ GemmPlan p) {
         const uint64_t a_lo = ptx::make_sw128_kmajor_desc(sa + A_STAGE_BYTES);
         const uint64_t b_hi = ptx::make_sw128_kmajor_desc(sa + 2 * A_STAGE_BYTES);
         const uint64_t b_lo = ptx::make_sw128_kmajor_desc(sa + 2 * A_STAGE_BYTES + C::B_BYTES);
-        // small terms first within the stage
+        if (p.x3_collect) {
+          // per 16-wide k-step: A_lo.W_hi, then A_hi.W_lo keeping A_hi in the collector, then A_hi.W_hi re-using it -- one
+          // shared-memory read of A less per k-step (the short-K shapes run at ~98 % of the 128 B/clk shared-memory port)
 #pragma unroll
-        for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
-          ptx::tc_mma_bf16_pair(d_tmem, a_lo + 2u * kk, b_hi + 2u * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+            ptx::tc_mma_bf16_pair(d_tmem, a_lo + 2u * kk, b_hi + 2u * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+            ptx::tc_mma_bf16_pair_a_keep(d_tmem, a_hi + 2u * kk, b_lo + 2u * kk, idesc, 1u);
+            ptx::tc_mma_bf16_pair_a_reuse(d_tmem, a_hi + 2u * kk, b_hi + 2u * kk, idesc, 1u);
+          }
+        } else {
+          // small terms first within the stage
 #pragma unroll
-        for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) ptx::tc_mma_bf16_pair(d_tmem, a_hi + 2u * kk, b_lo + 2u * kk, idesc, 1u);
+          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk)
+            ptx::tc_mma_bf16_pair(d_tmem, a_lo + 2u * kk, b_hi + 2u * kk, idesc, (k | kk) != 0 ? 1u : 0u);
 #pragma unroll
-        for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) ptx::tc_mma_bf16_pair(d_tmem, a_hi + 2u * kk, b_hi + 2u * kk, idesc, 1u);
+          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) ptx::tc_mma_bf16_pair(d_tmem, a_hi + 2u * kk, b_lo + 2u * kk, idesc, 1u);
+#pragma unroll
+          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) ptx::tc_mma_bf16_pair(d_tmem, a_hi + 2u * kk, b_hi + 2u * kk, idesc, 1u);
+        }
         ptx::tc_commit_pair(empty_bar(stage), 0x3);   // slot reusable in BOTH CTAs
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -234,7 +245,13 @@ int gemm_pair_x3_supported(const GemmPlan& plan, int block_n) {
   return total >= min_tiles;
 }
 
-int gemm_pair_x3_launch(const GemmPlan& plan, int block_n, cudaStream_t stream) {
+int gemm_pair_x3_launch(const GemmPlan& plan_in, int block_n, cudaStream_t stream) {
+  GemmPlan plan = plan_in;
+  {
+    static int collect = -1;   // GDRN_X3_COLLECT=1: A_hi through the A collector (measured: no change, 74.1 vs 74.3 us on stage-2 fc1)
+    if (collect < 0) { const char* e = getenv("GDRN_X3_COLLECT"); collect = e ? atoi(e) : 0; }
+    plan.x3_collect = collect;
+  }
   if (plan.epi == EPI_GELU) {
     // 16 epilogue warps for the short-K GELU GEMMs (stages 0 / 1: the epilogue, not the mainloop, sets their time)
     static int gelu16_max_k = -1;   // GDRN_X3_GELU16_MAX_KITERS: use the 16-warp variant up to this many k-iterations (0 = never)

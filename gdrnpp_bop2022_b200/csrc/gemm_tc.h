@@ -55,6 +55,7 @@ struct GemmPlan {
                         // [hi | lo] pairs (row width 2N, lo = bf16(v - hi))
   int x3_a_lo;          // split: offset of the lo half in A's coordinate 0 (channels / K); taps[] list the hi operands only
   int x3_b_lo;          // split: offset of the lo half inside a row of W (elements)
+  int x3_collect;       // pair kernel: A_hi read once per k-step through the A collector (set by gemm_pair_x3_launch; GDRN_X3_COLLECT)
   int x3_expanded;      // set by gemm_tc_launch once taps[] has been expanded to the three products (general kernel)
   void* out;            // [rows, ldo]
   CUtensorMap tmap_out; // rank-2 outputs: store map (filled by gemm_tc_launch when use_tma_store)
