@@ -294,6 +294,19 @@ int fps_launch(const float* pts, int* idxs, int pn, int sn, int batch, const int
     if (pn <= 4 * FPS_SMEM_D) return fps_launch_cluster<4>(pts, idxs, pn, sn, batch, start_idx, st);
     return fps_launch_cluster<8>(pts, idxs, pn, sn, batch, start_idx, st);
   }
+  {
+    // Few large clouds (a mesh being sampled, not a batch of ROI clouds): one CTA per cloud leaves most SMs idle and, beyond
+    // 14 000 points, re-reads the coordinates from L2 every step.  Spread each cloud over a cluster when the SMs are there:
+    // the per-step scan shrinks by the cluster size and the slices fit shared memory again.  Same arg-max order, same bits.
+    static int min_pn = -1;   // GDRN_FPS_CLUSTER_MIN_PN (0 = never)
+    if (min_pn < 0) { const char* e = getenv("GDRN_FPS_CLUSTER_MIN_PN"); min_pn = e ? atoi(e) : 16384; }
+    if (min_pn > 0 && pn >= min_pn) {
+      const int room = gdrn_num_sms() / batch;
+      if (room >= 8) return fps_launch_cluster<8>(pts, idxs, pn, sn, batch, start_idx, st);
+      if (room >= 4) return fps_launch_cluster<4>(pts, idxs, pn, sn, batch, start_idx, st);
+      if (room >= 2) return fps_launch_cluster<2>(pts, idxs, pn, sn, batch, start_idx, st);
+    }
+  }
   GDRN_OPT_IN_SMEM(fps_kernel<true>, 224000);
   GDRN_OPT_IN_SMEM(fps_kernel<false>, 224000);
   if (pn <= FPS_SMEM_ALL) {

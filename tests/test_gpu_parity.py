@@ -481,10 +481,11 @@ def test_fps_bit_exact(dev, pn, sn):
         assert (idx2[b] == OO.fps(pts[b], sn, start=int(start[b]))).all()
 
 
-@pytest.mark.parametrize("pn,sn", [(60000, 24), (150001, 16), (300000, 12)])
+@pytest.mark.parametrize("pn,sn", [(60000, 24), (150001, 16), (300000, 12), (20000, 40), (50000, 32)])
 def test_fps_large_clouds_cluster_bit_exact(dev, pn, sn):
     """pn > 56 000 (meshes reach 10^5 vertices): a cluster of 2 / 4 / 8 CTAs shares one cloud; same indices as the
-    reference algorithm (core/csrc/fps/src/farthest_point_sampling.cpp:118-160 handles any pn)."""
+    reference algorithm (core/csrc/fps/src/farthest_point_sampling.cpp:118-160 handles any pn).  The last two cases are
+    few mid-size clouds (16 384 <= pn <= 56 000), which also run on a cluster so that the SMs are not left idle."""
     from gdrnpp_bop2022_b200 import native_ops
 
     rs = np.random.RandomState(pn % 1000)
