@@ -609,7 +609,7 @@ __global__ void gn_finalize_kernel(const double* __restrict__ stats, float2* __r
 // computed once per thread, GELU uses the packed-half2 tanh.approx form (two elements per instruction).
 constexpr int GN_PPT = 4;
 __global__ void __launch_bounds__(256)
-gn_gelu_kernel(const void* __restrict__ raw, int raw_is_f32, const float2* __restrict__ mr,
+gn_gelu_kernel(const void* __restrict__ raw, int raw_is_f32, const double* __restrict__ stats, double count, float eps,
                const float* __restrict__ gn_w, const float* __restrict__ gn_b, __nv_bfloat16* __restrict__ out, int B,
                int hw, int C, int groups, int split) {
   ptx::griddep_launch();
@@ -617,6 +617,21 @@ gn_gelu_kernel(const void* __restrict__ raw, int raw_is_f32, const float2* __res
   const int cv = C >> 3;
   const unsigned total = (unsigned)B * (hw / GN_PPT) * cv;  // < 2^31 (checked by the launcher)
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  // per-(image, group) mean / rstd of the (at most two) images this block touches, from the double sums accumulated by the
+  // conv epilogue -- the arithmetic of gn_finalize_kernel, folded in here to save one launch per GroupNorm
+  __shared__ float2 mr_s[2][32];
+  const int b_first = (int)((blockIdx.x * blockDim.x / (unsigned)cv) / (unsigned)(hw / GN_PPT));
+  if ((int)threadIdx.x < 2 * groups) {
+    const int bi = (int)threadIdx.x / groups, g = (int)threadIdx.x % groups;
+    if (b_first + bi < B) {
+      const long long i = (long long)(b_first + bi) * groups + g;
+      const double mean = stats[2 * i] / count;
+      double var = stats[2 * i + 1] / count - mean * mean;
+      if (var < 0.0) var = 0.0;
+      mr_s[bi][g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+    }
+  }
+  __syncthreads();
   if (idx >= total) return;
   const int c8 = (int)(idx % (unsigned)cv) * 8;
   const unsigned pg = idx / (unsigned)cv;                  // pixel group over all images
@@ -629,12 +644,13 @@ gn_gelu_kernel(const void* __restrict__ raw, int raw_is_f32, const float2* __res
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(gn_b + c8)), b1 = __ldg(reinterpret_cast<const float4*>(gn_b + c8 + 4));
     const float gw[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
     const float gb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    float2 m = __ldg(mr + (long long)b * groups + c8 / cpg);
+    const float2* mrow = mr_s[b - b_first];
+    float2 m = mrow[c8 / cpg];
     int gcur = c8 / cpg;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int g = (c8 + k) / cpg;
-      if (g != gcur) { m = __ldg(mr + (long long)b * groups + g); gcur = g; }
+      if (g != gcur) { m = mrow[g]; gcur = g; }
       a[k] = m.y * gw[k];
       s[k] = fmaf(-m.x, a[k], gb[k]);
     }
@@ -679,27 +695,61 @@ __global__ void gn_gelu_f32_kernel(const float* __restrict__ raw, const float2* 
   }
 }
 
-// y[b, n] = act(sum_k x[b,k] * W[n,k] + bias[n]) in fp32 on the CUDA cores (Patch-PnP FC stack in split-bf16 mode:
-// 8.7 MMAC per ROI, irrelevant for throughput).  One warp per output element.
-__global__ void fc_f32_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
-                              float* __restrict__ y, int B, int N, int K, int ldy, int gelu) {
+// y[b, n] = act(sum_k x[b,k] * W[n,k] + bias[n]) in fp32 on the CUDA cores (Patch-PnP FC stack in split-bf16 mode).
+// One warp per FC_NT neurons x FC_BT batch rows: per 128-wide k-step a lane loads FC_NT + FC_BT float4 for FC_NT * FC_BT * 4
+// FMAs (the one-output-per-warp form moved 8 bytes of L1 traffic per FMA and ran fc1 at the L1 bandwidth: 150 us at B = 64).
+// Per output the summation order is unchanged: lane-partial sums over k = 4 * lane + 128 * i, then the xor butterfly.
+constexpr int FC_NT = 4, FC_BT = 16;
+__global__ void __launch_bounds__(256)
+fc_f32_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
+              float* __restrict__ y, int B, int N, int K, int ldy, int gelu) {
   ptx::griddep_launch();
   ptx::griddep_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= B * N) return;
-  const int b = warp / N, n = warp % N;
-  const float* xr = x + (long long)b * K;
-  const float* wr = W + (long long)n * K;
-  float acc = 0.f;
+  const int n_groups = N / FC_NT, b_groups = (B + FC_BT - 1) / FC_BT;
+  if (warp >= n_groups * b_groups) return;
+  const int n0 = (warp % n_groups) * FC_NT, b0 = (warp / n_groups) * FC_BT;
+  float acc[FC_BT][FC_NT];
+#pragma unroll
+  for (int i = 0; i < FC_BT; ++i)
+#pragma unroll
+    for (int j = 0; j < FC_NT; ++j) acc[i][j] = 0.f;
   for (int k = lane * 4; k < K; k += 128) {
-    const float4 xv = *reinterpret_cast<const float4*>(xr + k), wv = __ldg(reinterpret_cast<const float4*>(wr + k));
-    acc = fmaf(xv.x, wv.x, acc); acc = fmaf(xv.y, wv.y, acc); acc = fmaf(xv.z, wv.z, acc); acc = fmaf(xv.w, wv.w, acc);
+    float4 wv[FC_NT];
+#pragma unroll
+    for (int j = 0; j < FC_NT; ++j) wv[j] = __ldg(reinterpret_cast<const float4*>(W + (long long)(n0 + j) * K + k));
+#pragma unroll
+    for (int i = 0; i < FC_BT; ++i) {
+      const int b = min(b0 + i, B - 1);   // rows past the batch repeat the last one (never stored)
+      const float4 xv = *reinterpret_cast<const float4*>(x + (long long)b * K + k);
+#pragma unroll
+      for (int j = 0; j < FC_NT; ++j) {
+        float a = acc[i][j];
+        a = fmaf(xv.x, wv[j].x, a); a = fmaf(xv.y, wv[j].y, a); a = fmaf(xv.z, wv[j].z, a); a = fmaf(xv.w, wv[j].w, a);
+        acc[i][j] = a;
+      }
+    }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) {
-    acc += bias[n];
-    y[(long long)b * ldy + n] = gelu ? gelu_erf(acc) : acc;
+  for (int i = 0; i < FC_BT; ++i)
+#pragma unroll
+    for (int j = 0; j < FC_NT; ++j) {
+      float a = acc[i][j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      acc[i][j] = a;
+    }
+  if (lane < FC_BT && b0 + lane < B) {   // lane i stores row b0 + i
+#pragma unroll
+    for (int i = 0; i < FC_BT; ++i) {
+      if (i == lane) {
+#pragma unroll
+        for (int j = 0; j < FC_NT; ++j) {
+          const float v = acc[i][j] + bias[n0 + j];
+          y[(long long)(b0 + i) * ldy + n0 + j] = gelu ? gelu_erf(v) : v;
+        }
+      }
+    }
   }
 }
 
@@ -999,15 +1049,15 @@ int launch_gn_gelu(const void* raw, int raw_is_f32, const double* stats, float* 
                    const float* gn_b, __nv_bfloat16* out, int B, int h, int w, int C, int groups, float eps, int split,
                    cudaStream_t st) {
   GDRN_REQUIRE(C % 8 == 0 && (h * w) % GN_PPT == 0, "gn_gelu: unsupported shape");
-  const int n_bg = B * groups;
-  GDRN_CHECK_CUDA(gdrn_launch_dep(gn_finalize_kernel, dim3((n_bg + 127) / 128), dim3(128), 0, st, stats, reinterpret_cast<float2*>(mean_rstd_scratch), n_bg,
-                                                        (double)h * w * (C / groups), eps));
+  // a 256-thread block covers 256 / (C/8) pixel groups: it must not span more than two images, and 2 * groups <= 256 threads
+  GDRN_REQUIRE(groups <= 32 && (long long)(h * w / GN_PPT) * (C / 8) >= 256, "gn_gelu: image too small for the block-level statistics");
+  (void)mean_rstd_scratch;
   long long total = (long long)B * (h * w / GN_PPT) * (C / 8);
   GDRN_REQUIRE(total < (1LL << 31), "gn_gelu: tensor too large for 32-bit indexing");
-  GDRN_CHECK_CUDA(gdrn_launch_dep(gn_gelu_kernel, dim3((int)((total + 255) / 256)), dim3(256), 0, st, raw, raw_is_f32, reinterpret_cast<const float2*>(mean_rstd_scratch),
-                                                            gn_w, gn_b, out, B, h * w, C, groups, split));
+  GDRN_CHECK_CUDA(gdrn_launch_dep(gn_gelu_kernel, dim3((int)((total + 255) / 256)), dim3(256), 0, st, raw, raw_is_f32, stats,
+                                  (double)h * w * (C / groups), eps, gn_w, gn_b, out, B, h * w, C, groups, split));
   GDRN_CHECK_CUDA(cudaGetLastError());
-  gdrn_count_launch(2);
+  gdrn_count_launch(1);
   return GDRN_OK;
 }
 
@@ -1026,8 +1076,8 @@ int launch_gn_gelu_f32(const float* raw, const double* stats, float* mean_rstd_s
 
 int launch_fc_f32(const float* x, const float* W, const float* bias, float* y, int B, int N, int K, int ldy, int gelu,
                   cudaStream_t st) {
-  GDRN_REQUIRE(K % 128 == 0, "fc_f32: K must be a multiple of 128");
-  const long long warps = (long long)B * N;
+  GDRN_REQUIRE(K % 128 == 0 && N % FC_NT == 0, "fc_f32: K must be a multiple of 128 and N of 4");
+  const long long warps = (long long)(N / FC_NT) * ((B + FC_BT - 1) / FC_BT);
   GDRN_CHECK_CUDA(gdrn_launch_dep(fc_f32_kernel, dim3((int)((warps * 32 + 255) / 256)), dim3(256), 0, st, x, W, bias, y, B, N, K, ldy, gelu));
   GDRN_CHECK_CUDA(cudaGetLastError());
   gdrn_count_launch(1);
