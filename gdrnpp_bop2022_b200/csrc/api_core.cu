@@ -85,8 +85,22 @@ extern "C" int gdrn_mlp_fused_x3(const void* A, const void* W1, const float* b1,
   return mlp_fused_x3_launch(A, W1, b1, W2, b2, gamma, x, M, C, (cudaStream_t)stream);
 }
 
+static int gemm_x3_impl(const void* A, const void* W, const float* bias, const float* gamma, const float* resid, void* out,
+                       int M, int N, int K, int epi, int block_n, unsigned* sk_flags, int sk_flag_words, void* stream);
+
 extern "C" int gdrn_gemm_x3(const void* A, const void* W, const float* bias, const float* gamma, const float* resid,
                             void* out, int M, int N, int K, int epi, int block_n, void* stream) {
+  return gemm_x3_impl(A, W, bias, gamma, resid, out, M, N, K, epi, block_n, nullptr, 0, stream);
+}
+
+extern "C" int gdrn_gemm_x3_ksplit(const void* A, const void* W, const float* bias, const float* gamma, float* x, int M, int N,
+                                   int K, int block_n, unsigned* flags, int flag_words, void* stream) {
+  GDRN_REQUIRE(flags != nullptr && flag_words > 0, "gemm_x3_ksplit: flags must be a zeroed device buffer");
+  return gemm_x3_impl(A, W, bias, gamma, x, x, M, N, K, EPI_RESID, block_n, flags, flag_words, stream);
+}
+
+static int gemm_x3_impl(const void* A, const void* W, const float* bias, const float* gamma, const float* resid, void* out,
+                       int M, int N, int K, int epi, int block_n, unsigned* sk_flags, int sk_flag_words, void* stream) {
   GDRN_REQUIRE(M > 0 && N > 0 && K > 0, "gemm_x3: empty problem");
   GDRN_REQUIRE(K % 64 == 0, "gemm_x3: K must be a multiple of 64 (the lo half starts at a k-chunk boundary)");
   GDRN_REQUIRE(epi >= 0 && epi <= 2, "gemm_x3: epi must be 0 (store fp32), 1 (gelu -> split bf16) or 2 (resid)");
@@ -123,6 +137,7 @@ extern "C" int gdrn_gemm_x3(const void* A, const void* W, const float* bias, con
   p.bias = bias;
   p.gamma = gamma;
   p.resid = resid;
+  p.sk_flags = sk_flags; p.sk_flag_words = sk_flag_words;
   static int trace_on = -1;
   if (trace_on < 0) trace_on = getenv("GDRN_GEMM_TRACE") ? 1 : 0;
   if (trace_on) {

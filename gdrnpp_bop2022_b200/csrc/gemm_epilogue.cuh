@@ -603,7 +603,9 @@ __device__ __forceinline__ void epilogue_tile_staged_t(const GemmPlan& p, int m_
 // half, register-prefetched one half ahead).
 template <int BLOCK_N, int EPI, bool F32, int NEW = NUM_EPI_WARPS>
 __device__ __forceinline__ void epilogue_tile_tma(const GemmPlan& p, int m_tile, int n_tile, uint32_t tmem_acc, int ew,
-                                                  int lane, uint8_t* stg, int g_begin = 0, int g_end = 1 << 30) {
+                                                  int lane, uint8_t* stg, int g_begin = 0, int g_end = 1 << 30,
+                                                  bool use_bias = true) {
+  // use_bias = false: a k-split PART of a tile that does not contain k = 0 (the bias travels with the k = 0 part)
   // [g_begin, g_end): sub-range of this warp's columns (multiples of GW) -- lets a caller interleave the 128-byte groups
   // of a tile with other work so that the wait for the previous TMA store never blocks (fused MLP kernel)
   static_assert(BLOCK_N >= 128, "TMA-store epilogue needs BLOCK_N >= 128");
@@ -652,7 +654,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmPlan& p, int m_tile,
       // bias is read four columns at a time right where it is consumed (keeps the live register set small
       // enough for the 16-warp epilogue variant); the loads are warp-uniform L1 hits
       auto bias4 = [&](int j) {
-        return p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        return (p.bias && use_bias) ? __ldg(reinterpret_cast<const float4*>(p.bias + col + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
       };
       float x[EPI == EPI_RESID ? CH : 1], gm[EPI == EPI_RESID ? CH : 1];
       if constexpr (EPI == EPI_RESID) {

@@ -36,6 +36,61 @@ struct X3Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NEW * EPI_STAGE_BYTES + 256 + 1024;
 };
 
+// Work sequence of one CTA pair.  Default: whole tiles, strided over the pairs.  Balanced k-split (p.streamk, in-place
+// EPI_RESID only): the total_tiles * k_iters (tile, k-iteration) units are cut into num_pairs contiguous ranges of equal
+// length (+-1), so a launch whose tile count is not a multiple of the pair count (stage-2 fc2: 128 tiles on 74 pairs =
+// 0.86 wave efficiency) keeps every pair busy to the end.  A pair's first and last work items may be PART of a tile's K
+// range; the parts meet in the L2 reduce-add (x += gamma * partial; the bias goes with the k = 0 part).
+struct X3Work { int tile, kb, ke; };
+struct X3Sched {
+  int streamk, k_iters, total_tiles, num_pairs, tile, u, u_end;
+  __device__ X3Sched(int streamk_, int k_iters_, int total_tiles_, int pair_id, int num_pairs_)
+      : streamk(streamk_), k_iters(k_iters_), total_tiles(total_tiles_), num_pairs(num_pairs_), tile(pair_id) {
+    const long long units = (long long)total_tiles * k_iters;
+    u = (int)(units * pair_id / num_pairs);
+    u_end = (int)(units * (pair_id + 1) / num_pairs);
+  }
+  __device__ bool next(X3Work& w) {
+    if (!streamk) {
+      if (tile >= total_tiles) return false;
+      w.tile = tile; w.kb = 0; w.ke = k_iters;
+      tile += num_pairs;
+      return true;
+    }
+    if (u >= u_end) return false;
+    w.tile = u / k_iters;
+    w.kb = u - w.tile * k_iters;
+    w.ke = min(k_iters, w.kb + (u_end - u));
+    u += w.ke - w.kb;
+    return true;
+  }
+  // k-split: how many parts of this tile are written BEFORE the part [kb, ke) in the fixed order "highest k range first"
+  // (= the parts owned by the pairs after this one, up to the owner of the tile's last unit)
+  __device__ int parts_before(const X3Work& w, int pair_id) const {
+    const long long units = (long long)total_tiles * k_iters;
+    const int last = (w.tile + 1) * k_iters - 1;     // the tile's last unit
+    int q = pair_id;
+    while (q + 1 < num_pairs && (int)(units * (q + 1) / num_pairs) <= last) ++q;
+    return q - pair_id;
+  }
+};
+
+// Bounded acquire spin on a global word (k-split ordering of partial reduce-adds); a protocol bug traps instead of hanging.
+__device__ __forceinline__ void sk_wait_flag(const unsigned* f, unsigned want) {
+  long long t0 = 0;
+  int spins = 0;
+  while (true) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    if (v == want) break;
+    if (++spins == 64) t0 = clock64();
+    if (spins > 64 && (clock64() - t0) > 4000000000LL) {
+      printf("gdrn: k-split flag wait timeout (block %d thread %d want %u have %u)\n", blockIdx.x, threadIdx.x, want, v);
+      __trap();
+    }
+  }
+}
+
 template <int BLOCK_N, int EPI, int NEWARPS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(X3Cfg<BLOCK_N, NEWARPS>::THREADS, 1)
 gemm_pair_x3_kernel(const __grid_constant__ GemmPlan p) {
@@ -91,7 +146,10 @@ gemm_pair_x3_kernel(const __grid_constant__ GemmPlan p) {
     // ================= TMA producer (both CTAs): {A hi, A lo, W hi, W lo} per (tap, k-chunk) =================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = pair_id; tile < total_tiles; tile += num_pairs) {
+    X3Sched sched(p.streamk, k_iters, total_tiles, pair_id, num_pairs);
+    X3Work wk;
+    while (sched.next(wk)) {
+      const int tile = wk.tile;
       const int n_tile = tile % p.n_tiles, m_pair = tile / p.n_tiles;
       const int m_tile = m_pair * 2 + (int)rank;
       int x0 = 0, y0 = 0, b0 = 0;
@@ -103,25 +161,25 @@ gemm_pair_x3_kernel(const __grid_constant__ GemmPlan p) {
         b0 = (t2 / p.tiles_y) << p.lg_bb;     // an odd tile count leaves the last peer tile out of bounds: zero fill
       }
       const int brow = n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2);
-      for (int tap = 0; tap < p.num_taps; ++tap) {
-        const GemmTap tp = p.taps[tap];
-        for (int kc = 0; kc < p.k_chunks; ++kc) {
-          { const long long t0 = tr ? clock64() : 0; ptx::mbar_wait(empty_bar(stage), phase ^ 1); if (tr) tr_acc0 += clock64() - t0; }
-          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-          const uint32_t sb = sa + 2 * A_STAGE_BYTES;
-          const uint32_t lead_full = ptx::mapa_shared(full_bar(stage), 0);
-          if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
-          const int k0 = kc * BLOCK_K;
+      int tap = wk.kb / p.k_chunks, kc = wk.kb - tap * p.k_chunks;
+      GemmTap tp = p.taps[tap];
+      for (int k = wk.kb; k < wk.ke; ++k) {   // k = tap * k_chunks + kc
+        { const long long t0 = tr ? clock64() : 0; ptx::mbar_wait(empty_bar(stage), phase ^ 1); if (tr) tr_acc0 += clock64() - t0; }
+        const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+        const uint32_t sb = sa + 2 * A_STAGE_BYTES;
+        const uint32_t lead_full = ptx::mapa_shared(full_bar(stage), 0);
+        if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+        const int k0 = kc * BLOCK_K;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {      // h = 0: hi halves, 1: lo halves
-            const int ca = k0 + tp.c0 + h * p.x3_a_lo;
-            if (p.a_rank == 2) ptx::tma_load_2d_pair(sa + h * A_STAGE_BYTES, &p.tmap_a, lead_full, ca, m_tile * BLOCK_M + tp.d1);
-            else if (p.a_rank == 4) ptx::tma_load_4d_pair(sa + h * A_STAGE_BYTES, &p.tmap_a, lead_full, ca, x0 + tp.d1, y0 + tp.d2, b0);
-            else ptx::tma_load_5d_pair(sa + h * A_STAGE_BYTES, &p.tmap_a, lead_full, ca, x0 + tp.d1, tp.d2, y0 + tp.d3, b0);
-            ptx::tma_load_2d_pair(sb + h * C::B_BYTES, &p.tmap_b, lead_full, tp.b_off + k0 + h * p.x3_b_lo, brow);
-          }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        for (int h = 0; h < 2; ++h) {      // h = 0: hi halves, 1: lo halves
+          const int ca = k0 + tp.c0 + h * p.x3_a_lo;
+          if (p.a_rank == 2) ptx::tma_load_2d_pair(sa + h * A_STAGE_BYTES, &p.tmap_a, lead_full, ca, m_tile * BLOCK_M + tp.d1);
+          else if (p.a_rank == 4) ptx::tma_load_4d_pair(sa + h * A_STAGE_BYTES, &p.tmap_a, lead_full, ca, x0 + tp.d1, y0 + tp.d2, b0);
+          else ptx::tma_load_5d_pair(sa + h * A_STAGE_BYTES, &p.tmap_a, lead_full, ca, x0 + tp.d1, tp.d2, y0 + tp.d3, b0);
+          ptx::tma_load_2d_pair(sb + h * C::B_BYTES, &p.tmap_b, lead_full, tp.b_off + k0 + h * p.x3_b_lo, brow);
         }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++kc == p.k_chunks) { kc = 0; if (++tap < p.num_taps) tp = p.taps[tap]; }
       }
     }
     if (tr) { p.trace[0] = tr_acc0; p.trace[6] = clock64() - tr_start; p.trace[7] = (total_tiles - 1 - pair_id) / num_pairs + 1; }
@@ -131,13 +189,15 @@ gemm_pair_x3_kernel(const __grid_constant__ GemmPlan p) {
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = pair_id; tile < total_tiles; tile += num_pairs, ++it) {
+    X3Sched sched(p.streamk, k_iters, total_tiles, pair_id, num_pairs);
+    X3Work wk;
+    for (; sched.next(wk); ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       { const long long t0 = tr ? clock64() : 0; ptx::mbar_wait(tempty_bar(as), aphase ^ 1); if (tr) tr_acc1 += clock64() - t0; }
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-      for (int k = 0; k < k_iters; ++k) {
+      for (int k = 0; k < wk.ke - wk.kb; ++k) {   // k counts from the start of this part: the first MMA overwrites
         { const long long t0 = tr ? clock64() : 0; ptx::mbar_wait(full_bar(stage), phase); if (tr) tr_acc0 += clock64() - t0; }
         ptx::tc_fence_after();
         const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
@@ -175,7 +235,10 @@ gemm_pair_x3_kernel(const __grid_constant__ GemmPlan p) {
     const int ew = warp - 4;
     uint8_t* stg = stage_base + ew * EPI_STAGE_BYTES;
     int it = 0;
-    for (int tile = pair_id; tile < total_tiles; tile += num_pairs, ++it) {
+    X3Sched sched(p.streamk, k_iters, total_tiles, pair_id, num_pairs);
+    X3Work wk;
+    for (; sched.next(wk); ++it) {
+      const int tile = wk.tile;
       const int n_tile = tile % p.n_tiles, m_pair = tile / p.n_tiles;
       const int m_tile = m_pair * 2 + (int)rank;
       const int as = it & 1;
@@ -190,7 +253,30 @@ gemm_pair_x3_kernel(const __grid_constant__ GemmPlan p) {
           epilogue_tile_tma_split<BLOCK_N, EPI_GELU, NEW>(p, m_tile, n_tile, acc, ew, lane, stg);
         } else if constexpr (EPI == EPI_GNSTATS) {
           epilogue_tile_staged_t<BLOCK_N, EPI_GNSTATS, true>(p, m_tile, n_tile, acc, ew, lane, stg);
-        } else {   // EPI_RESID / EPI_STORE, fp32 out through TMA stores (reduce-add for the in-place residual)
+        } else if constexpr (EPI == EPI_RESID) {
+          // k-split: a PART of the tile's K range adds gamma * partial (bias with the k = 0 part).  The parts of one tile
+          // are reduce-added in a fixed order (highest k range first; flag word per (tile, CTA, warp) = parts written so
+          // far), so x does not depend on which pair happened to finish first.
+          const bool part = p.streamk && (wk.kb != 0 || wk.ke != k_iters);
+          unsigned* flag = nullptr;
+          if (part) {
+            flag = p.sk_flags + ((size_t)tile * 2 + rank) * NEW + ew;
+            const int before = sched.parts_before(wk, pair_id);
+            if (before > 0) {
+              if (lane == 0) sk_wait_flag(flag, (unsigned)before);
+              __syncwarp();
+            }
+          }
+          epilogue_tile_tma<BLOCK_N, EPI, true, NEW>(p, m_tile, n_tile, acc, ew, lane, stg, 0, 1 << 30, wk.kb == 0);
+          if (part && lane == 0) {
+            if (wk.kb == 0) {
+              *reinterpret_cast<volatile unsigned*>(flag) = 0u;   // last part of the tile: leave the word clean for the next launch
+            } else {
+              ptx::bulk_wait0();   // this part's reduce-adds have been performed (not only read from the staging tile)
+              asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(flag) : "memory");
+            }
+          }
+        } else {   // EPI_STORE, fp32 out through TMA stores
           epilogue_tile_tma<BLOCK_N, EPI, true, NEW>(p, m_tile, n_tile, acc, ew, lane, stg);
         }
       }
@@ -221,7 +307,7 @@ int launch_x3(const GemmPlan& plan, cudaStream_t stream) {
   const int total = m_pairs * plan.n_tiles;
   if (total <= 0) return GDRN_OK;
   int pairs = gdrn_num_sms() / 2;
-  if (pairs > total) pairs = total;
+  if (pairs > total && !plan.streamk) pairs = total;   // the k-split schedule feeds every pair even with fewer tiles than pairs
   GDRN_CHECK_CUDA(gdrn_launch_dep(kfn, dim3(2 * pairs), dim3(C::THREADS), C::SMEM_BYTES, stream, plan));
   gdrn_count_launch(1);
   return GDRN_OK;
@@ -251,6 +337,19 @@ int gemm_pair_x3_launch(const GemmPlan& plan_in, int block_n, cudaStream_t strea
     static int collect = -1;   // GDRN_X3_COLLECT=1: A_hi through the A collector (measured: no change, 74.1 vs 74.3 us on stage-2 fc1)
     if (collect < 0) { const char* e = getenv("GDRN_X3_COLLECT"); collect = e ? atoi(e) : 0; }
     plan.x3_collect = collect;
+  }
+  plan.streamk = 0;
+  if (plan.epi == EPI_RESID && plan.resid_reduce && plan.sk_flags != nullptr) {
+    // balanced k-split for the in-place residual GEMMs whose tile count leaves the last wave partly empty (stage-1/2/3 fc2
+    // at B = 64: 256 / 128 / 64 tiles on 74 pairs = 0.86 wave efficiency)
+    static int sk = -1;   // GDRN_X3_KSPLIT=0: whole tiles only (A/B experiments)
+    if (sk < 0) { const char* e = getenv("GDRN_X3_KSPLIT"); sk = e ? atoi(e) : 0; }
+    const int pairs = gdrn_num_sms() / 2;
+    const long long total = (long long)((plan.m_tiles + 1) / 2) * plan.n_tiles;
+    const long long k_iters = (long long)plan.num_taps * plan.k_chunks;
+    const long long waves = (total + pairs - 1) / pairs;
+    if (sk && total * 100 < waves * pairs * 93 && total * k_iters >= 8LL * pairs && total * 2 * 8 <= plan.sk_flag_words)
+      plan.streamk = 1;
   }
   if (plan.epi == EPI_GELU) {
     // 16 epilogue warps for the short-K GELU GEMMs (stages 0 / 1: the epilogue, not the mainloop, sets their time)

@@ -62,6 +62,13 @@ struct GemmPlan {
   int use_tma_store;    // set by gemm_tc_launch
   int resid_reduce;     // set by gemm_tc_launch: EPI_RESID in place -> TMA reduce-add (x += gamma*(acc+bias)), x is never read by the SM
   long long ldo;        // output row stride (elements)
+  // pair-x3 kernel, in-place EPI_RESID only: balanced k-split schedule (every CTA pair gets one contiguous, equally long
+  // range of (tile, k-iteration) units instead of whole tiles; partial tiles meet in the L2 reduce-add).  sk_flags =
+  // zeroed device words, one per (tile, CTA of the pair, epilogue warp): order the partial reduce-adds of a tile (highest
+  // k range first) so that the result does not depend on timing; the last writer leaves its word at zero again.
+  unsigned* sk_flags;   // null: whole tiles only
+  int sk_flag_words;    // capacity of sk_flags
+  int streamk;          // set by gemm_pair_x3_launch
   int OH, OW, osy, osx, ooy, oox;  // rank 4/5: out row = (b*OH + y*osy+ooy)*OW + x*osx+oox
   const float* bias;    // [N] or null
   const float* gamma;   // EPI_RESID [N]

@@ -293,11 +293,14 @@ struct Workspace {
   float *pF, *f1f, *f2f;  // precise mode: fp32 Patch-PnP feature [B,8192] and FC activations
   float* fout;      // [B][16]
   double* gn_stats; // [10][B][32][2]
+  unsigned* sk_flags;   // [SK_FLAG_WORDS] k-split ordering words of the pair-x3 residual GEMMs (gemm_tc.h), directly behind gn_stats
+  size_t zero_bytes;    // gn_stats .. end of sk_flags: cleared at the start of every forward
   float* gn_mr;     // [B][32][2] mean / rstd scratch of the layer being applied
   size_t total;
 };
 
 size_t align_up(size_t v) { return (v + 1023) & ~(size_t)1023; }
+constexpr int SK_FLAG_WORDS = 8192;   // >= tiles * 2 CTAs * 8 epilogue warps of the largest k-split GEMM (256 tiles at B = 64, stage 1)
 
 Workspace carve(const GdrnModel* m, int B, void* base) {
   const Arch& a = m->arch;
@@ -331,6 +334,8 @@ Workspace carve(const GdrnModel* m, int B, void* base) {
   w.f2 = reinterpret_cast<__nv_bfloat16*>(take((size_t)B * 256 * 2));
   w.fout = reinterpret_cast<float*>(take((size_t)B * 16 * 4));
   w.gn_stats = reinterpret_cast<double*>(take((size_t)10 * B * 32 * 2 * 8));
+  w.sk_flags = reinterpret_cast<unsigned*>(take((size_t)SK_FLAG_WORDS * 4));
+  w.zero_bytes = align_up((size_t)10 * B * 32 * 2 * 8) + (size_t)SK_FLAG_WORDS * 4;
   w.gn_mr = reinterpret_cast<float*>(take((size_t)B * 32 * 2 * 4));
   w.total = off;
   return w;
@@ -526,7 +531,7 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
   Workspace w = carve(m, B, wbase);
   m->prof_used = 0;
   m->prof_cat.clear();
-  GDRN_CHECK_CUDA(cudaMemsetAsync(w.gn_stats, 0, (size_t)10 * B * 32 * 2 * 8, st));
+  GDRN_CHECK_CUDA(cudaMemsetAsync(w.gn_stats, 0, w.zero_bytes, st));   // GroupNorm sums + k-split ordering words
 
   GemmPlan p;
   auto reset = [&]() { memset(&p, 0, sizeof(p)); p.ldo = 0; };
@@ -599,6 +604,7 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
       RC(plan_b(p, bw.fc2_w, C, H4, bn2, C, S));
       if (PR) set_x3(p, H4, H4);
       p.epi = EPI_RESID; p.out_f32 = 1; p.out = w.X; p.resid = w.X; p.ldo = C; p.bias = bw.fc2_b; p.gamma = bw.gamma;
+      p.sk_flags = w.sk_flags; p.sk_flag_words = SK_FLAG_WORDS;
       RCP(0, gemm_tc_launch(p, bn2, st));
     }
   }

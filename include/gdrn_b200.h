@@ -104,6 +104,14 @@ int gdrn_gemm_bf16(const void* A, const void* W, const float* bias, const float*
 int gdrn_gemm_x3(const void* A, const void* W, const float* bias, const float* gamma, const float* resid, void* out,
                  int M, int N, int K, int epi, int block_n, void* stream);
 
+/* In-place residual form (epi 2) of gdrn_gemm_x3 with the balanced k-split schedule of the CTA-pair kernel allowed:
+ * x [M,N] fp32 += gamma * (A @ W^T + bias).  `flags` = flag_words ZEROED device words (>= 16 per 256 x block_n tile); the
+ * kernel leaves them zeroed.  Tiles whose K range is split between two CTA pairs are reduce-added in a fixed order, so the
+ * result is run-to-run deterministic.  GDRN_X3_KSPLIT=0 keeps whole tiles.  Exported for tests and measurement (the model
+ * forward uses the same path for its fc2 GEMMs: timm ConvNeXtBlock.mlp.fc2 + layer scale + shortcut). */
+int gdrn_gemm_x3_ksplit(const void* A, const void* W, const float* bias, const float* gamma, float* x, int M, int N, int K,
+                        int block_n, unsigned* flags, int flag_words, void* stream);
+
 /* Fused ConvNeXt MLP half-block of the split-bf16 mode (stage 0, C = 128), exported for tests and measurement:
  * x [M,C] fp32 += gamma * (W2 . gelu(W1 . a + b1) + b2) with a [M,2C], W1 [4C,2C], W2 [C,8C] in [hi | lo] bf16 rows; the
  * 4C-wide hidden activation stays on chip.  Replaces two gdrn_gemm_x3 calls (epi 1 then epi 2); same arithmetic.

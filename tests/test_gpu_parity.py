@@ -142,6 +142,49 @@ def test_gemm_x3_vs_fp64(dev, lib, M, N, K, bn, epi):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K,bn", [
+    (16384, 512, 2048, 256),    # stage-2 fc2 at B = 64: 128 tiles x 32 k-iterations on 74 pairs (tiles cut in two)
+    (65536, 256, 1024, 256),    # stage-1 fc2: 256 tiles x 16
+    (4096, 1024, 4096, 256),    # stage-3 fc2: 64 tiles x 64 (fewer tiles than pairs: some tiles are cut in THREE)
+    (20000, 256, 1024, 256),    # ragged M, odd tile count (the peer CTA of the last pair has no rows)
+    (16384, 128, 512, 128),     # BLOCK_N 128
+])
+def test_gemm_x3_ksplit_residual(dev, lib, M, N, K, bn):
+    """Balanced k-split schedule of the CTA-pair split-bf16 kernel (in-place residual GEMMs whose tile count leaves the
+    last wave partly empty): same result as the fp64 reference, run-to-run bit-identical (partial tiles are reduce-added
+    in a fixed order), ordering words left at zero."""
+    L = _lib()
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(dev)
+    W = (torch.randn(N, K, generator=g) / np.sqrt(K)).to(dev)
+    bias, gamma = torch.randn(N, generator=g).to(dev), torch.rand(N, generator=g).to(dev)
+    x = torch.randn(M, N, generator=g).to(dev)
+    ref = x.double() + gamma.double() * (A.double() @ W.double().t() + bias.double())
+    A2, W2 = _split_bf16(A), _split_bf16(W)
+    flags = torch.zeros(8192, dtype=torch.int32, device=dev)
+    outs = []
+    for _ in range(3):
+        out = torch.full((M + 64, N), 7.0, dtype=torch.float32, device=dev)
+        out[:M] = x
+        L.check(lib.gdrn_gemm_x3_ksplit(L.ptr(A2), L.ptr(W2), L.ptr(bias), L.ptr(gamma), L.ptr(out), M, N, K, bn,
+                                        L.ptr(flags), flags.numel(), L.current_stream()), "gemm_x3_ksplit")
+        torch.cuda.synchronize()
+        assert int(flags.abs().max().item()) == 0
+        assert torch.equal(out[M:], torch.full((64, N), 7.0, device=dev))
+        outs.append(out[:M].clone())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    err = (outs[0].double() - ref).abs().max().item()
+    assert err < 4e-5 * max(1.0, ref.abs().max().item()), err
+    # whole-tile schedule (no flags): same sums up to the fp32 rounding of the partial adds
+    whole = torch.full((M + 64, N), 7.0, dtype=torch.float32, device=dev)
+    whole[:M] = x
+    L.check(lib.gdrn_gemm_x3(L.ptr(A2), L.ptr(W2), L.ptr(bias), L.ptr(gamma), L.ptr(whole), L.ptr(whole), M, N, K, 2, bn,
+                             L.current_stream()), "gemm_x3")
+    torch.cuda.synchronize()
+    assert (whole[:M] - outs[0]).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.gpu
 def test_mlp_fused_x3_vs_unfused_and_fp64(dev, lib):
     """Fused fc1 -> GELU -> fc2 -> residual of the split-bf16 mode (ConvNeXt stage 0, C = 128; the hidden activation stays on
     chip) against (a) the two-kernel path it replaces -- same products in the same accumulation order -- and (b) an fp64
@@ -319,6 +362,16 @@ def test_forward_vs_oracle_b64(dev, precision):
         assert (raw[:, :6] - ref["rot6d"]).abs().max().item() < 1e-4
         assert rerr < 1e-4, rerr
         assert terr < 1e-3, terr
+        # run-to-run determinism at the bench's batch size (the k-split fc2 GEMMs add partial tiles in a fixed order; the
+        # GroupNorm sums are double atomics whose order noise disappears in the float rounding of mean / rstd)
+        gb = {k: v.to(dev) for k, v in batch.items()}
+        out2 = model(gb["roi_img"], roi_classes=gb["roi_classes"], roi_coord_2d=gb["roi_coord_2d"], roi_cams=gb["roi_cams"],
+                     roi_centers=gb["roi_centers"], roi_whs=gb["roi_whs"], roi_extents=gb["roi_extents"],
+                     resize_ratios=gb["resize_ratios"], return_raw=True)
+        torch.cuda.synchronize()
+        x3b = model.debug_read("stage3_x", 64, 64 * 64 * 1024).reshape(64, 8, 8, 1024).permute(0, 3, 1, 2).cpu()
+        assert torch.equal(x3, x3b)
+        assert (out2["rot"] - out["rot"]).abs().max().item() < 1e-6
     else:
         for k in ("mask", "full_mask", "coor_x", "coor_y", "coor_z", "region"):
             assert (out[k].cpu() - ref[k]).abs().max().item() < 0.15, k

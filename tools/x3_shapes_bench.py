@@ -31,8 +31,13 @@ def main():
         W = (torch.randn(N, 2 * K, generator=g) / np.sqrt(K)).to(dev).bfloat16()
         bias, gamma = torch.randn(N).to(dev), torch.rand(N).to(dev)
         o = torch.zeros((M, 2 * N), dtype=torch.bfloat16, device=dev) if epi == 1 else torch.zeros((M, N), dtype=torch.float32, device=dev)
-        call = lambda: L.check(lib.gdrn_gemm_x3(L.ptr(A), L.ptr(W), L.ptr(bias), L.ptr(gamma), L.ptr(o), L.ptr(o), M, N, K, epi, bn,
-                                                L.current_stream()), "gemm_x3")
+        if epi == 2:   # in-place residual: the entry that may use the balanced k-split schedule (GDRN_X3_KSPLIT)
+            flags = torch.zeros(8192, dtype=torch.int32, device=dev)
+            call = lambda: L.check(lib.gdrn_gemm_x3_ksplit(L.ptr(A), L.ptr(W), L.ptr(bias), L.ptr(gamma), L.ptr(o), M, N, K, bn,
+                                                           L.ptr(flags), 8192, L.current_stream()), "gemm_x3_ksplit")
+        else:
+            call = lambda: L.check(lib.gdrn_gemm_x3(L.ptr(A), L.ptr(W), L.ptr(bias), L.ptr(gamma), L.ptr(o), L.ptr(o), M, N, K, epi, bn,
+                                                    L.current_stream()), "gemm_x3")
         for _ in range(3):
             call()
         torch.cuda.synchronize()
