@@ -695,62 +695,117 @@ __global__ void gn_gelu_f32_kernel(const float* __restrict__ raw, const float2* 
   }
 }
 
-// y[b, n] = act(sum_k x[b,k] * W[n,k] + bias[n]) in fp32 on the CUDA cores (Patch-PnP FC stack in split-bf16 mode).
-// One warp per FC_NT neurons x FC_BT batch rows: per 128-wide k-step a lane loads FC_NT + FC_BT float4 for FC_NT * FC_BT * 4
-// FMAs (the one-output-per-warp form moved 8 bytes of L1 traffic per FMA and ran fc1 at the L1 bandwidth: 150 us at B = 64).
-// Per output the summation order is unchanged: lane-partial sums over k = 4 * lane + 128 * i, then the xor butterfly.
-constexpr int FC_NT = 4, FC_BT = 16;
+// y[b, n] = act(sum_k x[b,k] * W[n,k] + bias[n]) in fp32 on the CUDA cores (Patch-PnP FC stack of the split-bf16 mode:
+// conv_pnp_net.py:150-183 fc1 8192 -> 1024, fc2 -> 256, fc_r | fc_t -> 16).  The op is bound by streaming W (fc1: 32 MB) once,
+// so it is split along K over the whole chip: block = FC_NB neurons x BT batch rows x one K slice; x and W tiles of FC_KT
+// k-values are staged through shared memory in [k][row] layout (the global loads of the next tile are in flight during the
+// FMAs of the current one), a thread owns 4 neurons x BT/16 rows.  The slices' partial sums go to part[ks][b][n];
+// fc_f32_reduce_kernel adds them in slice order, then bias and GELU: deterministic, no atomics.  (The previous forms -- one
+// output per warp, then 4 neurons x 16 rows per warp straight from global memory -- re-read x or W from L2 hundreds of times:
+// 150 / 480 us for fc1 at B = 64.)
+constexpr int FC_NB = 64, FC_KT = 32, FC_MAX_KS = 16;
+template <int BT>
 __global__ void __launch_bounds__(256)
-fc_f32_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ bias,
-              float* __restrict__ y, int B, int N, int K, int ldy, int gelu) {
+fc_f32_partial_kernel(const float* __restrict__ x, const float* __restrict__ W, float* __restrict__ part, int B, int N, int K,
+                      int kslice) {
+  constexpr int RB = BT / 16;                       // batch rows per thread
+  __shared__ __align__(16) float xs[FC_KT][BT];
+  __shared__ __align__(16) float ws[FC_KT][FC_NB];
+  ptx::griddep_launch();
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int n0 = blockIdx.x * FC_NB, ks = blockIdx.y, b0 = blockIdx.z * BT;
+  const int kbeg = ks * kslice;
+  // loader mapping: rows vary fastest inside a warp (conflict-free transposing stores), 8 k-quads per row
+  const int lrow = t & 31, lkq = t >> 5;
+  const bool w_ok0 = n0 + lrow < N, w_ok1 = n0 + lrow + 32 < N;
+  const float* wp0 = W + (long long)(n0 + lrow) * K + kbeg + lkq * 4;
+  const float* wp1 = wp0 + 32LL * K;
+  // x rows: BT = 64 -> two passes of 32 rows; BT = 16 -> threads 0..127 (16 rows x 8 k-quads)
+  const int xrow = BT == 64 ? lrow : (t & 15), xkq = BT == 64 ? lkq : ((t >> 4) & 7);
+  const bool x_act = BT == 64 || t < 128;
+  const bool x_ok0 = x_act && b0 + xrow < B, x_ok1 = BT == 64 && b0 + xrow + 32 < B;
+  const float* xp0 = x + (long long)(b0 + xrow) * K + kbeg + xkq * 4;
+  const float* xp1 = xp0 + 32LL * K;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  ptx::griddep_wait();
+  float4 rw0 = w_ok0 ? __ldg(reinterpret_cast<const float4*>(wp0)) : z4;
+  float4 rw1 = w_ok1 ? __ldg(reinterpret_cast<const float4*>(wp1)) : z4;
+  float4 rx0 = x_ok0 ? *reinterpret_cast<const float4*>(xp0) : z4;
+  float4 rx1 = x_ok1 ? *reinterpret_cast<const float4*>(xp1) : z4;
+  float acc[RB][4];
+#pragma unroll
+  for (int i = 0; i < RB; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int ntiles = kslice / FC_KT;
+  for (int kt = 0; kt < ntiles; ++kt) {
+    __syncthreads();   // the previous tile has been consumed
+    ws[lkq * 4 + 0][lrow] = rw0.x; ws[lkq * 4 + 1][lrow] = rw0.y; ws[lkq * 4 + 2][lrow] = rw0.z; ws[lkq * 4 + 3][lrow] = rw0.w;
+    ws[lkq * 4 + 0][lrow + 32] = rw1.x; ws[lkq * 4 + 1][lrow + 32] = rw1.y; ws[lkq * 4 + 2][lrow + 32] = rw1.z; ws[lkq * 4 + 3][lrow + 32] = rw1.w;
+    if (x_act) {
+      xs[xkq * 4 + 0][xrow] = rx0.x; xs[xkq * 4 + 1][xrow] = rx0.y; xs[xkq * 4 + 2][xrow] = rx0.z; xs[xkq * 4 + 3][xrow] = rx0.w;
+      if (BT == 64) {
+        xs[xkq * 4 + 0][(xrow + 32) % BT] = rx1.x; xs[xkq * 4 + 1][(xrow + 32) % BT] = rx1.y;
+        xs[xkq * 4 + 2][(xrow + 32) % BT] = rx1.z; xs[xkq * 4 + 3][(xrow + 32) % BT] = rx1.w;
+      }
+    }
+    __syncthreads();
+    if (kt + 1 < ntiles) {   // next tile: in flight during the FMAs below
+      const int o = (kt + 1) * FC_KT;
+      rw0 = w_ok0 ? __ldg(reinterpret_cast<const float4*>(wp0 + o)) : z4;
+      rw1 = w_ok1 ? __ldg(reinterpret_cast<const float4*>(wp1 + o)) : z4;
+      rx0 = x_ok0 ? *reinterpret_cast<const float4*>(xp0 + o) : z4;
+      rx1 = x_ok1 ? *reinterpret_cast<const float4*>(xp1 + o) : z4;
+    }
+#pragma unroll
+    for (int k = 0; k < FC_KT; ++k) {
+      const float4 wv = *reinterpret_cast<const float4*>(&ws[k][tx * 4]);
+      float a[RB];
+      if constexpr (RB == 4) {
+        const float4 av = *reinterpret_cast<const float4*>(&xs[k][ty * 4]);
+        a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < RB; ++i) a[i] = xs[k][ty * RB + i];
+      }
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        acc[i][0] = fmaf(a[i], wv.x, acc[i][0]); acc[i][1] = fmaf(a[i], wv.y, acc[i][1]);
+        acc[i][2] = fmaf(a[i], wv.z, acc[i][2]); acc[i][3] = fmaf(a[i], wv.w, acc[i][3]);
+      }
+    }
+  }
+  const int n = n0 + tx * 4;
+  if (n < N) {
+#pragma unroll
+    for (int i = 0; i < RB; ++i) {
+      const int b = b0 + ty * RB + i;
+      if (b < B)
+        *reinterpret_cast<float4*>(part + ((long long)ks * B + b) * N + n) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+  }
+}
+
+// y[b, n] = act(bias[n] + sum over the K slices, in slice order)
+__global__ void __launch_bounds__(256)
+fc_f32_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bias, float* __restrict__ y, int B, int N, int ks_n,
+                     int ldy, int gelu) {
   ptx::griddep_launch();
   ptx::griddep_wait();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int n_groups = N / FC_NT, b_groups = (B + FC_BT - 1) / FC_BT;
-  if (warp >= n_groups * b_groups) return;
-  const int n0 = (warp % n_groups) * FC_NT, b0 = (warp / n_groups) * FC_BT;
-  float acc[FC_BT][FC_NT];
-#pragma unroll
-  for (int i = 0; i < FC_BT; ++i)
-#pragma unroll
-    for (int j = 0; j < FC_NT; ++j) acc[i][j] = 0.f;
-  for (int k = lane * 4; k < K; k += 128) {
-    float4 wv[FC_NT];
-#pragma unroll
-    for (int j = 0; j < FC_NT; ++j) wv[j] = __ldg(reinterpret_cast<const float4*>(W + (long long)(n0 + j) * K + k));
-#pragma unroll
-    for (int i = 0; i < FC_BT; ++i) {
-      const int b = min(b0 + i, B - 1);   // rows past the batch repeat the last one (never stored)
-      const float4 xv = *reinterpret_cast<const float4*>(x + (long long)b * K + k);
-#pragma unroll
-      for (int j = 0; j < FC_NT; ++j) {
-        float a = acc[i][j];
-        a = fmaf(xv.x, wv[j].x, a); a = fmaf(xv.y, wv[j].y, a); a = fmaf(xv.z, wv[j].z, a); a = fmaf(xv.w, wv[j].w, a);
-        acc[i][j] = a;
-      }
-    }
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // one float4 of outputs
+  const int nq = N >> 2;
+  if (i >= B * nq) return;
+  const int b = i / nq, n = (i - b * nq) * 4;
+  float4 s = *reinterpret_cast<const float4*>(part + (long long)b * N + n);
+  for (int ks = 1; ks < ks_n; ++ks) {
+    const float4 v = *reinterpret_cast<const float4*>(part + ((long long)ks * B + b) * N + n);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
-#pragma unroll
-  for (int i = 0; i < FC_BT; ++i)
-#pragma unroll
-    for (int j = 0; j < FC_NT; ++j) {
-      float a = acc[i][j];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      acc[i][j] = a;
-    }
-  if (lane < FC_BT && b0 + lane < B) {   // lane i stores row b0 + i
-#pragma unroll
-    for (int i = 0; i < FC_BT; ++i) {
-      if (i == lane) {
-#pragma unroll
-        for (int j = 0; j < FC_NT; ++j) {
-          const float v = acc[i][j] + bias[n0 + j];
-          y[(long long)(b0 + i) * ldy + n0 + j] = gelu ? gelu_erf(v) : v;
-        }
-      }
-    }
-  }
+  const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + n));
+  s.x += bv.x; s.y += bv.y; s.z += bv.z; s.w += bv.w;
+  if (gelu) { s.x = gelu_erf(s.x); s.y = gelu_erf(s.y); s.z = gelu_erf(s.z); s.w = gelu_erf(s.w); }
+  float* yr = y + (long long)b * ldy + n;
+  yr[0] = s.x; yr[1] = s.y; yr[2] = s.z; yr[3] = s.w;
 }
 
 // nn.UpsamplingBilinear2d(scale_factor=2) (align_corners=True) on NHWC bf16: src = dst * (in-1)/(out-1)
@@ -1074,13 +1129,33 @@ int launch_gn_gelu_f32(const float* raw, const double* stats, float* mean_rstd_s
   return GDRN_OK;
 }
 
-int launch_fc_f32(const float* x, const float* W, const float* bias, float* y, int B, int N, int K, int ldy, int gelu,
+int fc_f32_slices(int B, int N, int K) {
+  // K slices: enough blocks to cover the chip about twice, slices of whole k tiles, at most FC_MAX_KS
+  const int bt = B <= 16 ? 16 : 64;
+  const long long blocks = (long long)((N + FC_NB - 1) / FC_NB) * ((B + bt - 1) / bt);
+  int ks = 1;
+  while (ks < FC_MAX_KS && blocks * ks < 2LL * gdrn_num_sms() && K % (2 * ks * FC_KT) == 0) ks *= 2;
+  return ks;
+}
+
+size_t fc_f32_part_bytes(int B, int N_max) { return (size_t)FC_MAX_KS * B * N_max * sizeof(float); }
+
+int launch_fc_f32(const float* x, const float* W, const float* bias, float* y, float* part, int B, int N, int K, int ldy, int gelu,
                   cudaStream_t st) {
-  GDRN_REQUIRE(K % 128 == 0 && N % FC_NT == 0, "fc_f32: K must be a multiple of 128 and N of 4");
-  const long long warps = (long long)(N / FC_NT) * ((B + FC_BT - 1) / FC_BT);
-  GDRN_CHECK_CUDA(gdrn_launch_dep(fc_f32_kernel, dim3((int)((warps * 32 + 255) / 256)), dim3(256), 0, st, x, W, bias, y, B, N, K, ldy, gelu));
+  GDRN_REQUIRE(K % FC_KT == 0 && N % 4 == 0 && B > 0 && part != nullptr, "fc_f32: K must be a multiple of 32 and N of 4");
+  const int ks = fc_f32_slices(B, N, K);
+  const int kslice = K / ks;
+  if (B <= 16) {
+    GDRN_CHECK_CUDA(gdrn_launch_dep(fc_f32_partial_kernel<16>, dim3((N + FC_NB - 1) / FC_NB, ks, (B + 15) / 16), dim3(256), 0, st, x, W,
+                                    part, B, N, K, kslice));
+  } else {
+    GDRN_CHECK_CUDA(gdrn_launch_dep(fc_f32_partial_kernel<64>, dim3((N + FC_NB - 1) / FC_NB, ks, (B + 63) / 64), dim3(256), 0, st, x, W,
+                                    part, B, N, K, kslice));
+  }
+  GDRN_CHECK_CUDA(gdrn_launch_dep(fc_f32_reduce_kernel, dim3((B * (N / 4) + 255) / 256), dim3(256), 0, st, (const float*)part, bias, y, B, N,
+                                  ks, ldy, gelu));
   GDRN_CHECK_CUDA(cudaGetLastError());
-  gdrn_count_launch(1);
+  gdrn_count_launch(2);
   return GDRN_OK;
 }
 

@@ -45,8 +45,10 @@ int launch_gn_gelu(const void* raw, int raw_is_f32, const double* stats, float* 
 int launch_gn_gelu_f32(const float* raw, const double* stats, float* mean_rstd_scratch, const float* gn_w,
                        const float* gn_b, float* out, int B, int h, int w, int C, int groups, float eps, cudaStream_t st);
 // fp32 CUDA-core fully connected layer (split-bf16 mode FC stack): y[b,n] = act(x[b,:] . W[n,:] + bias[n])
-int launch_fc_f32(const float* x, const float* W, const float* bias, float* y, int B, int N, int K, int ldy, int gelu,
+// part: scratch of fc_f32_part_bytes(B, N) bytes (partial sums of the K slices)
+int launch_fc_f32(const float* x, const float* W, const float* bias, float* y, float* part, int B, int N, int K, int ldy, int gelu,
                   cudaStream_t st);
+size_t fc_f32_part_bytes(int B, int N_max);
 // fp32 [rows,C] -> split bf16 [rows,2C]
 int launch_cast_split(const float* src, __nv_bfloat16* dst, long long rows, int C, cudaStream_t st);
 // bilinear x2 (align_corners=True) on NHWC bf16: [B,h,w,C] -> [B,2h,2w,C]

@@ -291,6 +291,7 @@ struct Workspace {
   __nv_bfloat16 *pR, *pP;
   __nv_bfloat16 *f1, *f2;
   float *pF, *f1f, *f2f;  // precise mode: fp32 Patch-PnP feature [B,8192] and FC activations
+  float* fc_part;         // precise mode: K-slice partial sums of the fp32 FC stack
   float* fout;      // [B][16]
   double* gn_stats; // [10][B][32][2]
   unsigned* sk_flags;   // [SK_FLAG_WORDS] k-split ordering words of the pair-x3 residual GEMMs (gemm_tc.h), directly behind gn_stats
@@ -330,6 +331,7 @@ Workspace carve(const GdrnModel* m, int B, void* base) {
   w.pF = reinterpret_cast<float*>(take(m->precise ? (size_t)B * 8192 * 4 : 0));
   w.f1f = reinterpret_cast<float*>(take(m->precise ? (size_t)B * 1024 * 4 : 0));
   w.f2f = reinterpret_cast<float*>(take(m->precise ? (size_t)B * 256 * 4 : 0));
+  w.fc_part = reinterpret_cast<float*>(take(m->precise ? fc_f32_part_bytes(B, 1024) : 0));
   w.f1 = reinterpret_cast<__nv_bfloat16*>(take((size_t)B * 1024 * 2));
   w.f2 = reinterpret_cast<__nv_bfloat16*>(take((size_t)B * 256 * 2));
   w.fout = reinterpret_cast<float*>(take((size_t)B * 16 * 4));
@@ -726,9 +728,9 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
     }
     // FC stack: [B,8192] -> 1024 -> 256 -> 9
     if (PR) {
-      RCP(2, launch_fc_f32(w.pF, m->pfc1_wf, m->pfc1_b, w.f1f, B, 1024, 8192, 1024, 1, st));
-      RCP(2, launch_fc_f32(w.f1f, m->pfc2_wf, m->pfc2_b, w.f2f, B, 256, 1024, 256, 1, st));
-      RCP(2, launch_fc_f32(w.f2f, m->pfcrt_wf, m->pfcrt_b, w.fout, B, 16, 256, 16, 0, st));
+      RCP(2, launch_fc_f32(w.pF, m->pfc1_wf, m->pfc1_b, w.f1f, w.fc_part, B, 1024, 8192, 1024, 1, st));
+      RCP(2, launch_fc_f32(w.f1f, m->pfc2_wf, m->pfc2_b, w.f2f, w.fc_part, B, 256, 1024, 256, 1, st));
+      RCP(2, launch_fc_f32(w.f2f, m->pfcrt_wf, m->pfcrt_b, w.fout, w.fc_part, B, 16, 256, 16, 0, st));
     } else {
     reset();
     RC(plan_a2d(p, w.pP, B, 8192));

@@ -375,13 +375,15 @@ def get_affine_transform(center, scale, rot, output_size, shift=(0.0, 0.0), inv=
     (out centre, out centre + (0, -out_w/2), third point).  The reference builds the three point pairs in float32
     and solves with cv2.getAffineTransform; here the same float32 point pairs are solved in closed form in float64
     (equal to 1e-12; the warp quantises coordinates to 1/32 pixel, so crops are identical)."""
-    center = np.asarray(center, np.float32)
+    # dtype handling as in the reference: tuples / lists and python scalars become float32, arrays keep their dtype, so that
+    # `center + src_dir + scale * shift` is evaluated at the caller's precision and rounded ONCE into the float32 points
+    center = np.array(center, np.float32) if isinstance(center, (tuple, list)) else np.asarray(center)
     if np.isscalar(scale):
         scale = np.array([scale, scale], np.float32)
-    scale = np.asarray(scale, np.float32)
+    scale = np.asarray(scale)
     if np.isscalar(output_size):
         output_size = (output_size, output_size)
-    shift = np.asarray(shift, np.float32)
+    shift = np.array(shift, np.float32) if isinstance(shift, (tuple, list)) else np.asarray(shift)
     src_w, dst_w, dst_h = scale[0], output_size[0], output_size[1]
     rot_rad = np.pi * rot / 180
     sn, cs = np.sin(rot_rad), np.cos(rot_rad)
