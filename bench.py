@@ -440,6 +440,21 @@ def main():
                 break
         except Exception:  # noqa: BLE001
             traffic = None
+    # tensor-pipe activity of the whole forward (BASELINE.json metric: "backbone tensor-pipe %") from the committed ncu
+    # launch list of this same workload (profiles/r02_step_tensor.json, tools/r02b_ncu_step.sh + step_tensor_share.py)
+    tensor_pipe = None
+    tp_path = os.path.join(ROOT, "profiles", "r02_step_tensor.json")
+    if x3 and os.path.exists(tp_path):
+        try:
+            tj = json.load(open(tp_path))
+            tensor_pipe = {"forward_pct_of_elapsed": tj["tensor_pipe_pct_of_elapsed_forward"],
+                           "tcgen05_kernels_pct_of_elapsed": tj["tensor_pipe_pct_of_elapsed_tcgen05_kernels"],
+                           "tcgen05_kernels_pct_of_active": tj["tensor_pipe_pct_of_active_tcgen05_kernels"],
+                           "tcgen05_time_share": tj["tcgen05_time_share"],
+                           "source": "profiles/r02_step_tensor.json (ncu sm__pipe_tensor_cycles_active, time-weighted over the %d "
+                                     "launches of one forward; build %s)" % (tj["launches"], tj.get("build"))}
+        except Exception:  # noqa: BLE001
+            tensor_pipe = None
     step_ms = ms_total / args.steps
     roofline = {
         "bound": "tensor",
@@ -453,6 +468,7 @@ def main():
         "whole_step_tflops_reference_flops": BATCH * GFLOP_PER_ROI_REFERENCE / step_ms,
         "whole_step_frac_reference_flops": BATCH * GFLOP_PER_ROI_REFERENCE / step_ms / peaks["bf16_tflops"],
         "whole_step_tflops_executed_flops": BATCH * GFLOP_PER_ROI_EXECUTED / step_ms,
+        "tensor_pipe": tensor_pipe,
     }
     if x3:
         # `achieved` / `frac` count every multiply-add of the reference's fp32 GEMMs ONCE (algorithmic work).  The

@@ -37,8 +37,9 @@ for d in data:
         e["us"] = v / 1e3 if d["Metric Unit"] == "ns" else v
 ids = list(per.keys())
 st = [i for i, k in enumerate(ids) if per[k]["name"].startswith("stem_patchify")]
-assert len(st) >= 2, "need at least one full step in the capture"
-step = [per[k] for k in ids[st[0]:st[1]]]
+assert len(st) >= 1, "need at least one full step in the capture"
+# two stems: the launches between them; one stem: the capture is exactly one forward (tools/r02b_ncu_step.sh)
+step = [per[k] for k in (ids[st[0]:st[1]] if len(st) >= 2 else ids[st[0]:])]
 agg = collections.defaultdict(lambda: {"launches": 0, "dram_read": 0.0, "dram_write": 0.0, "us": 0.0})
 for k in step:
     fam = ("gemm (gemm_tc_kernel + gemm_pair_kernel + gemm_pair_x3_kernel + mlp_fused_kernel + mlp_fused_x3_kernel, all tcgen05 launches)"

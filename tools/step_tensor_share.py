@@ -60,6 +60,17 @@ def main():
     print(txt)
     if len(sys.argv) > 2:
         open(sys.argv[2], "w").write("```\n" + txt + "\n```\n")
+    if len(sys.argv) > 3:   # machine-readable digest for bench.py's roofline record
+        import json
+        tc_t = sum(g[1] for g in agg.values() if g[2] > 0)
+        json.dump({"launches": len(launches), "window_us": tot_t,
+                   "tensor_pipe_pct_of_elapsed_forward": tot_w / tot_t,
+                   "tensor_pipe_pct_of_elapsed_tcgen05_kernels": sum(g[2] for g in agg.values()) / tc_t,
+                   "tensor_pipe_pct_of_active_tcgen05_kernels": sum(g[3] for g in agg.values()) / tc_t,
+                   "tcgen05_time_share": tc_t / tot_t, "dram_gb": tot_b / 1e9,
+                   "build": sys.argv[4] if len(sys.argv) > 4 else None,
+                   "how": "ncu --clock-control none, one parity-mode forward at B = 64 (tools/r02b_ncu_step.sh); per-launch "
+                          "times are cold-cache and serialised"}, open(sys.argv[3], "w"), indent=1)
 
 
 if __name__ == "__main__":
