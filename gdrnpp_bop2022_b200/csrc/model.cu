@@ -559,8 +559,16 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
       return GDRN_ERR_INVALID;
     }
   }
-  // largest tile width the N dimension divides into (the CTA-pair kernels need N % block_n == 0)
-  auto pick_bn = [](int N) { return N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64); };
+  // tile width: the largest one the N dimension divides into (the CTA-pair kernels need N % block_n == 0) that still yields
+  // at least half a wave of CTAs; small batches (the per-image case: 5 ROIs, BASELINE configs[4]) otherwise run their long-K
+  // GEMMs on a dozen SMs (stage-2 fc2 at B = 5: 20 CTAs of 96 k-iterations, 51 us -> 80 CTAs at width 64)
+  const int half_wave = gdrn_num_sms() / 2;
+  auto pick_bn = [half_wave](int N, long long M) {
+    const long long m_tiles = (M + 127) / 128;
+    int bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64);
+    while (bn > 64 && m_tiles * (N / bn) < half_wave) bn >>= 1;
+    return bn;
+  };
   // ---------------- stages ----------------
   int res = 64;
   for (int s = 0; s < 4; ++s) {
@@ -573,7 +581,7 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
       const long long M = (long long)B * res * res;
       reset();
       RC(plan_a2d(p, w.A, M, 4 * Ci, S));
-      const int bn = pick_bn(C);
+      const int bn = pick_bn(C, M);
       RC(plan_b(p, m->down[s].w, C, 4 * Ci, bn, C, S));
       if (PR) set_x3(p, 4 * Ci, 4 * Ci);
       p.epi = EPI_STORE; p.out_f32 = 1; p.out = w.X; p.ldo = C; p.bias = m->down[s].b;
@@ -595,14 +603,14 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
       }
       reset();
       RC(plan_a2d(p, w.A, M, C, S));
-      const int bn1 = pick_bn(H4);
+      const int bn1 = pick_bn(H4, M);
       RC(plan_b(p, bw.fc1_w, H4, C, bn1, H4, S));
       if (PR) set_x3(p, C, C);
       p.epi = EPI_GELU; p.gelu_mode = gelu_mode; p.out = w.Hb; p.ldo = S * H4; p.bias = bw.fc1_b;
       RCP(0, gemm_tc_launch(p, bn1, st));
       reset();
       RC(plan_a2d(p, w.Hb, M, H4, S));
-      const int bn2 = pick_bn(C);
+      const int bn2 = pick_bn(C, M);
       RC(plan_b(p, bw.fc2_w, C, H4, bn2, C, S));
       if (PR) set_x3(p, H4, H4);
       p.epi = EPI_RESID; p.out_f32 = 1; p.out = w.X; p.resid = w.X; p.ldo = C; p.bias = bw.fc2_b; p.gamma = bw.gamma;
@@ -651,12 +659,13 @@ extern "C" int gdrn_model_forward(GdrnModel* m, const float* roi_img, const int6
       RC(plan_a4d(p, cur, B, hres, hres, 256, S));
       for (int t = 0; t < 9; ++t) p.taps[t] = {0, t % 3 - 1, t / 3 - 1, 0, t * 256};
       p.num_taps = 9;
-      RC(plan_b(p, m->hconv_w[li], 256, 9 * 256, 256, 256, S));
+      const int hbn = pick_bn(256, (long long)B * hres * hres);   // narrower tiles when a small batch leaves most SMs without one
+      RC(plan_b(p, m->hconv_w[li], 256, 9 * 256, hbn, 256, S));
       if (PR) set_x3(p, 256, 9 * 256);
       p.epi = EPI_GNSTATS; p.out_f32 = PR; p.out = w.R; p.ldo = 256;
       p.OH = hres; p.OW = hres; p.osy = 1; p.osx = 1; p.ooy = 0; p.oox = 0;
       p.gn_stats = stat_slot(li + 1); p.gn_groups = 32; p.gn_cpg = 8;
-      RCP(0, gemm_tc_launch(p, 256, st));
+      RCP(0, gemm_tc_launch(p, hbn, st));
       const int up = (j == 1 && blk < 2) ? 2 : 1;
       if (up == 1) {
         RCP(2, launch_gn_gelu(w.R, PR, stat_slot(li + 1), w.gn_mr, m->gn_w[li + 1], m->gn_b[li + 1], nxt, B, hres, hres, 256, 32,

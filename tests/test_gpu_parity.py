@@ -106,6 +106,8 @@ def _split_bf16(t):
     (12300, 128, 128, 128, 1), (16384, 512, 2048, 256, 2),
     # general kernel with the 3x tap list (too few tiles for the pairs, or BLOCK_N 64)
     (300, 128, 64, 128, 0), (1000, 512, 128, 256, 1), (64, 1024, 8192, 64, 1), (4096, 256, 1024, 256, 2),
+    # narrow tiles the forward picks for small batches (B = 5: stage-2 / stage-3 fc2, stage-3 fc1)
+    (1280, 512, 2048, 64, 2), (320, 1024, 4096, 64, 2), (320, 4096, 1024, 128, 1), (1280, 256, 512, 64, 0),
 ])
 def test_gemm_x3_vs_fp64(dev, lib, M, N, K, bn, epi):
     """Split-bf16 ("bf16x3") GEMM -- the tensor-core path of the fp32-parity mode -- vs an fp64 torch reference of the
