@@ -238,7 +238,8 @@ def test_get_affine_transform_matches_reference_formula():
     from gdrnpp_bop2022_b200.native_ops import get_affine_transform
 
     def ref(center, scale, rot, out):
-        center = np.array(center, np.float32)
+        if isinstance(center, (tuple, list)):   # the reference converts sequences only; arrays keep their dtype (float64 bbox
+            center = np.array(center, np.float32)   # arithmetic is rounded ONCE, into the float32 point array)
         scale = np.array([scale, scale], np.float32)
         rot_rad = np.pi * rot / 180
         sn, cs = np.sin(rot_rad), np.cos(rot_rad)
@@ -257,7 +258,8 @@ def test_get_affine_transform_matches_reference_formula():
     for _ in range(100):
         c, s = rng.uniform(0, 640, 2), float(rng.uniform(20, 700))
         rot, out = float(rng.choice([0, 0, 15, -30])), int(rng.choice([64, 256]))
-        assert np.abs(get_affine_transform(c, s, rot, out) - ref(c, s, rot, out)).max() < 1e-9
+        for cc in (c, c.astype(np.float32), tuple(c.tolist())):   # float64 array, float32 array, python sequence
+            assert np.abs(get_affine_transform(cc, s, rot, out) - ref(cc, s, rot, out)).max() < 1e-9
 
 
 def test_baseline_config0_cpu_plumbing():
