@@ -703,7 +703,7 @@ __global__ void gn_gelu_f32_kernel(const float* __restrict__ raw, const float2* 
 // fc_f32_reduce_kernel adds them in slice order, then bias and GELU: deterministic, no atomics.  (The previous forms -- one
 // output per warp, then 4 neurons x 16 rows per warp straight from global memory -- re-read x or W from L2 hundreds of times:
 // 150 / 480 us for fc1 at B = 64.)
-constexpr int FC_NB = 64, FC_KT = 32, FC_MAX_KS = 16;
+constexpr int FC_NB = 64, FC_KT = 32, FC_MAX_KS = 32;
 template <int BT>
 __global__ void __launch_bounds__(256)
 fc_f32_partial_kernel(const float* __restrict__ x, const float* __restrict__ W, float* __restrict__ part, int B, int N, int K,

@@ -49,7 +49,11 @@ constexpr size_t PP_SMEM = (size_t)(2 * PP_SLOT_FLOATS + 49 * PP_CPC) * 4 + (siz
 // Everything that depends on (C, split) is a compile-time constant: the kernel is instruction-issue bound (the code around
 // the convolution was ~1.2 k dynamic instructions per thread and tile against 0.98 k for the convolution itself), so output
 // strides are immediates, the Chan combine is unrolled, and the normalisation runs in packed fp32.
-template <int NR, bool SPLIT, bool TRACE>
+// R2 = the convolution's thread tile: false = one output row x 16 pixels per thread (warp = output row: 22 halo + 7 tap
+// LDS.64 per filter row, 203 per tile), true = TWO output rows x 8 pixels (warp = row pair x half of the tile width): an
+// input row is loaded once for both output rows and a filter row's taps are kept for the second one, 161 LDS.64 per tile for
+// the same 784 FFMA2, same per-output accumulation order (bit-identical results).
+template <int NR, bool SPLIT, bool TRACE, bool R2 = false>
 __global__ void __launch_bounds__(2 * PP_WG_THREADS, 1)
 dwconv_ln_pp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                     const float* __restrict__ bias, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
@@ -81,6 +85,7 @@ dwconv_ln_pp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   const int wg = threadIdx.x >> 8;
   const int tidw = threadIdx.x & 255, lane = tidw & 31;
   const int row0 = tidw >> 5;          // output row of this warp
+  const int rp2 = (row0 >> 1) * 2, xh8 = (row0 & 1) * 8;   // R2: first output row / first output column of this warp
   const int cl = 2 * lane;             // first channel of the pair (CTA-local)
   const int n_w = (n_my - wg + 1) >> 1;                    // tiles of this warpgroup: k = wg, wg + 2, ...
   const int n_other = (n_my - (wg ^ 1) + 1) >> 1;
@@ -146,7 +151,36 @@ dwconv_ln_pp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     f32x2_t acc[TW];
 #pragma unroll
     for (int ox = 0; ox < TW; ++ox) acc[ox] = bv;
-    if (!(dbg & 4)) {
+    if constexpr (R2) {
+      // acc[r * 8 + q] = output (rp2 + r, xh8 + q).  Input row iy feeds output row 0 with filter row iy and output row 1 with
+      // filter row iy - 1 (the taps loaded one iteration earlier): per output the order is still ky = 0..6, kx = 0..6.
+      f32x2_t wprev[7];
+#pragma unroll
+      for (int iy = 0; iy < 8; ++iy) {
+        f32x2_t v[14], wk[7];
+        const float* rowp = tile + ((rp2 + iy) * IW + xh8) * CPC + cl;
+#pragma unroll
+        for (int j = 0; j < 14; ++j) v[j] = *reinterpret_cast<const f32x2_t*>(rowp + j * CPC);
+        if (iy < 7) {
+#pragma unroll
+          for (int kx = 0; kx < 7; ++kx) wk[kx] = *reinterpret_cast<const f32x2_t*>(wsm + (iy * 7 + kx) * CPC + cl);
+#pragma unroll
+          for (int kx = 0; kx < 7; ++kx)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] = f2_fma(v[q + kx], wk[kx], acc[q]);
+        }
+        if (iy >= 1) {
+#pragma unroll
+          for (int kx = 0; kx < 7; ++kx)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[8 + q] = f2_fma(v[q + kx], wprev[kx], acc[8 + q]);
+        }
+        if (iy < 7) {
+#pragma unroll
+          for (int kx = 0; kx < 7; ++kx) wprev[kx] = wk[kx];
+        }
+      }
+    } else if (!(dbg & 4)) {
 #pragma unroll
     for (int ky = 0; ky < 7; ++ky) {
       f32x2_t v[IW], wk[7];
@@ -177,7 +211,9 @@ dwconv_ln_pp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     PP_MARK(3);
     // ---- LayerNorm statistics of this warp's 64 channels (shuffles only) ----
     constexpr float INV_W = 1.0f / 64.0f;
-    const int pix = row0 * TW + lane / LPP;
+    // pixel (tile-local index) of value q of this thread: R2 maps q -> (row rp2 + q / 8, column xh8 + q % 8)
+    const int vi = lane / LPP;
+    const int pix = R2 ? (rp2 + (vi >> 3)) * TW + xh8 + (vi & 7) : row0 * TW + vi;
     float s_loc, m2_loc;
     {
       float a[NV];
@@ -234,12 +270,17 @@ dwconv_ln_pp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     // which is what a peer needs before it can push tile i + 2 (see the banner)
     if (tidw == 0 && i + 2 < n_w && !(dbg & 2)) ptx::mbar_arrive_expect_tx(bar_parts(buf), parts_bytes);
     // ---- normalise + affine in packed fp32, bf16x2 out (a warp writes 128 contiguous bytes per pixel) ----
-    __nv_bfloat16* orow = out + (((long long)b * H + (y0 + row0)) * W + x0) * LDC + c0 + cl;
-    const float2* srow = my_stats + row0 * TW;
+    __nv_bfloat16* orow = R2 ? out + (((long long)b * H + (y0 + rp2)) * W + x0 + xh8) * LDC + c0 + cl
+                             : out + (((long long)b * H + (y0 + row0)) * W + x0) * LDC + c0 + cl;
+    const float2* srow = R2 ? my_stats + rp2 * TW + xh8 : my_stats + row0 * TW;
+    __nv_bfloat16* const orow_next = orow + (long long)W * LDC;   // R2: second output row of this warp
 #pragma unroll
-    for (int ox = 0; ox < TW; ++ox) {
-      const float2 st = srow[ox];                                  // broadcast read: (mean, rstd) of pixel ox
-      const f32x2_t cen = f2_sub(acc[ox], f2_dup(st.x));
+    for (int ox_ = 0; ox_ < TW; ++ox_) {
+      // R2: values 8..15 are the second row (stats TW entries further, output W pixels further)
+      const int ox = R2 ? (ox_ & 7) : ox_;
+      if (R2 && ox_ == 8) { orow = orow_next; srow += TW; }
+      const float2 st = srow[ox];                                  // broadcast read: (mean, rstd) of this value's pixel
+      const f32x2_t cen = f2_sub(acc[ox_], f2_dup(st.x));
       const f32x2_t o2 = f2_fma(f2_mul(cen, f2_dup(st.y)), gw, gb);
       const float2 of = f2_unpack(o2);
       const uint32_t hb = pack_bf16(of.x, of.y);
@@ -260,10 +301,10 @@ dwconv_ln_pp_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 
 namespace {
 
-template <int NR, bool SPLIT, bool TRACE>
+template <int NR, bool SPLIT, bool TRACE, bool R2 = false>
 int pp_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_w, const float* bias, const float* ln_w, const float* ln_b,
               __nv_bfloat16* out, int B, int H, int W, int c_real, float eps, int token, cudaStream_t st) {
-  auto kfn = dwconv_ln_pp_kernel<NR, SPLIT, TRACE>;
+  auto kfn = dwconv_ln_pp_kernel<NR, SPLIT, TRACE, R2>;
   GDRN_OPT_IN_SMEM(kfn, PP_SMEM);
   const int n_tiles = B * (H / PP_TH) * (W / PP_TW);
   cudaLaunchConfig_t cfg = {};
@@ -280,7 +321,7 @@ int pp_launch(const CUtensorMap& tmap, const CUtensorMap& tmap_w, const float* b
   cfg.attrs = attr;
   cfg.numAttrs = gdrn_pdl_enabled() ? 2 : 1;
   // how many clusters of NR one-CTA-per-SM blocks the device can hold at once (GPC-granular), per device
-  static int max_clusters[GDRN_MAX_DEVICES] = {};
+  static int max_clusters[GDRN_MAX_DEVICES] = {};   // (per instantiation: R2 and R1 kernels query separately)
   const int dev = gdrn_cur_device();
   if (max_clusters[dev] == 0) {
     int n = 0;
@@ -341,9 +382,12 @@ int launch_dwconv_ln_pp(const float* x, const float* w49c, const float* bias, co
     if (const char* d = getenv("GDRN_DW_DBG")) token = (token & 1) | (atoi(d) & ~7);   // experiment bits, see the kernel
   }
 #define PP_ARGS tmap, tmap_w, bias, ln_w, ln_b, out, B, H, W, c_real, eps, token, st
+  static int r2 = -1;        // GDRN_DW_R2=0: one output row x 16 pixels per thread in the convolution (the earlier thread tile)
+  if (r2 < 0) { const char* e = getenv("GDRN_DW_R2"); r2 = e ? atoi(e) : 1; }
 #define PP_CASE(NR)                                                                                    \
   if (csize == NR) {                                                                                   \
     if (trace_on) return split ? pp_launch<NR, true, true>(PP_ARGS) : pp_launch<NR, false, true>(PP_ARGS);   \
+    if (r2) return split ? pp_launch<NR, true, false, true>(PP_ARGS) : pp_launch<NR, false, false, true>(PP_ARGS);   \
     return split ? pp_launch<NR, true, false>(PP_ARGS) : pp_launch<NR, false, false>(PP_ARGS);          \
   }
   PP_CASE(2) PP_CASE(3) PP_CASE(4) PP_CASE(6) PP_CASE(8)
