@@ -809,6 +809,43 @@ fc_f32_reduce_kernel(const float* __restrict__ part, const float* __restrict__ b
 }
 
 // nn.UpsamplingBilinear2d(scale_factor=2) (align_corners=True) on NHWC bf16: src = dst * (in-1)/(out-1)
+// (top_down_doublemask_xyz_region_head.py:99-104).  A thread produces a 2 x 2 block of output pixels x 8 channels: the four
+// outputs read from a window of (2 + DY) x (2 + DX) input pixels (the source step is < 0.5, so neighbouring outputs start at
+// the same or the next input pixel: DY, DX in {0, 1}, uniform over the warp), 4 - 9 pixel loads per block instead of 16.
+// Per output the arithmetic is the one-pixel-per-thread form's: o = w00*v00 + w01*v01 + w10*v10 + w11*v11.
+template <int DY, int DX>
+__device__ __forceinline__ void upsample_block(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int b, int h,
+                                               int w, int C, int split, int ldc, int c8, int oy0, int ox0, const int (&y0)[2],
+                                               const int (&x0)[2], const float (&ly)[2], const float (&lx)[2]) {
+  float win[2 + DY][2 + DX][8];
+#pragma unroll
+  for (int r = 0; r < 2 + DY; ++r)
+#pragma unroll
+    for (int c = 0; c < 2 + DX; ++c) {
+      const long long off = (((long long)b * h + min(y0[0] + r, h - 1)) * w + min(x0[0] + c, w - 1)) * ldc + c8;
+      load8(in, 0, off, win[r][c]);
+      if (split) {  // value = hi + lo
+        float t[8];
+        load8(in, 0, off + C, t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) win[r][c][k] += t[k];
+      }
+    }
+  const int oh = 2 * h, ow = 2 * w;
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int wr = r * DY, wc = c * DX;   // window position of this output's (y0, x0)
+      const float w00 = (1.f - ly[r]) * (1.f - lx[c]), w01 = (1.f - ly[r]) * lx[c], w10 = ly[r] * (1.f - lx[c]), w11 = ly[r] * lx[c];
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        o[k] = w00 * win[wr][wc][k] + w01 * win[wr][wc + 1][k] + w10 * win[wr + 1][wc][k] + w11 * win[wr + 1][wc + 1][k];
+      store8_split(out + (((long long)b * oh + oy0 + r) * ow + ox0 + c) * ldc + c8, o, split, C);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int h, int w, int C,
                   int split) {
@@ -816,46 +853,31 @@ upsample2x_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restric
   ptx::griddep_wait();
   const int cv = C >> 3;
   const int oh = 2 * h, ow = 2 * w;
-  const unsigned total = (unsigned)B * oh * ow * cv;
+  const unsigned total = (unsigned)B * h * w * cv;       // one thread per 2 x 2 output block and 8 channels
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int c8 = (int)(idx % (unsigned)cv) * 8;
   const unsigned p = idx / (unsigned)cv;
-  const int ox = (int)(p % (unsigned)ow);
-  const unsigned prow = p / (unsigned)ow;
-  const int oy = (int)(prow % (unsigned)oh);
-  const int b = (int)(prow / (unsigned)oh);
-  const float fy = (float)oy * ((float)(h - 1) / (float)(oh - 1));
-  const float fx = (float)ox * ((float)(w - 1) / (float)(ow - 1));
-  const int y0 = (int)fy, x0 = (int)fx;
-  const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
-  const float ly = fy - (float)y0, lx = fx - (float)x0;
-  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-  const int ldc = split ? 2 * C : C;
-  float v00[8], v01[8], v10[8], v11[8];
-  load8(in, 0, (((long long)b * h + y0) * w + x0) * ldc + c8, v00);
-  load8(in, 0, (((long long)b * h + y0) * w + x1) * ldc + c8, v01);
-  load8(in, 0, (((long long)b * h + y1) * w + x0) * ldc + c8, v10);
-  load8(in, 0, (((long long)b * h + y1) * w + x1) * ldc + c8, v11);
-  if (split) {  // value = hi + lo
-    float t[8];
-    load8(in, 0, (((long long)b * h + y0) * w + x0) * ldc + C + c8, t);
+  const int bx = (int)(p % (unsigned)w);
+  const unsigned prow = p / (unsigned)w;
+  const int by = (int)(prow % (unsigned)h);
+  const int b = (int)(prow / (unsigned)h);
+  const int oy0 = 2 * by, ox0 = 2 * bx;
+  int y0[2], x0[2];
+  float ly[2], lx[2];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v00[k] += t[k];
-    load8(in, 0, (((long long)b * h + y0) * w + x1) * ldc + C + c8, t);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v01[k] += t[k];
-    load8(in, 0, (((long long)b * h + y1) * w + x0) * ldc + C + c8, t);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v10[k] += t[k];
-    load8(in, 0, (((long long)b * h + y1) * w + x1) * ldc + C + c8, t);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v11[k] += t[k];
+  for (int r = 0; r < 2; ++r) {
+    const float fy = (float)(oy0 + r) * ((float)(h - 1) / (float)(oh - 1));
+    const float fx = (float)(ox0 + r) * ((float)(w - 1) / (float)(ow - 1));
+    y0[r] = (int)fy; x0[r] = (int)fx;
+    ly[r] = fy - (float)y0[r]; lx[r] = fx - (float)x0[r];
   }
-  float o[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) o[k] = w00 * v00[k] + w01 * v01[k] + w10 * v10[k] + w11 * v11[k];
-  store8_split(out + (((long long)b * oh + oy) * ow + ox) * ldc + c8, o, split, C);
+  const int ldc = split ? 2 * C : C;
+  const int dy = y0[1] - y0[0], dx = x0[1] - x0[0];   // 0 or 1 (source step < 0.5), the same for all threads of a block
+  if (dy == 0 && dx == 0) upsample_block<0, 0>(in, out, b, h, w, C, split, ldc, c8, oy0, ox0, y0, x0, ly, lx);
+  else if (dy == 0) upsample_block<0, 1>(in, out, b, h, w, C, split, ldc, c8, oy0, ox0, y0, x0, ly, lx);
+  else if (dx == 0) upsample_block<1, 0>(in, out, b, h, w, C, split, ldc, c8, oy0, ox0, y0, x0, ly, lx);
+  else upsample_block<1, 1>(in, out, b, h, w, C, split, ldc, c8, oy0, ox0, y0, x0, ly, lx);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1172,8 +1194,8 @@ int launch_cast_split(const float* src, __nv_bfloat16* dst, long long rows, int 
 
 int launch_upsample2x(const __nv_bfloat16* in, __nv_bfloat16* out, int B, int h, int w, int C, int split, cudaStream_t st) {
   GDRN_REQUIRE(C % 8 == 0 && h > 1 && w > 1, "upsample2x: unsupported shape");
-  long long total = (long long)B * 4 * h * w * (C / 8);
-  GDRN_REQUIRE(total < (1LL << 31), "upsample2x: tensor too large for 32-bit indexing");
+  long long total = (long long)B * h * w * (C / 8);   // threads: one per 2 x 2 output block and 8 channels
+  GDRN_REQUIRE(total * 4 < (1LL << 31), "upsample2x: tensor too large for 32-bit indexing");
   GDRN_CHECK_CUDA(gdrn_launch_dep(upsample2x_kernel, dim3((int)((total + 255) / 256)), dim3(256), 0, st, in, out, B, h, w, C, split));
   GDRN_CHECK_CUDA(cudaGetLastError());
   gdrn_count_launch(1);

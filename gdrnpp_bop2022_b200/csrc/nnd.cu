@@ -5,52 +5,77 @@
 // Result definition (what the reference computes): for every point of set A the minimum over set B of
 //   d = fma(dz,dz, fma(dx,dx, dy*dy))      (the contraction nvcc applies to x2*x2+y2*y2+z2*z2)
 // with dx = bx - ax etc., and the LOWEST index attaining it (strict '<' scan in index order).
-// This op is FP32-ALU bound (~8 instructions per point pair, no HBM traffic once tiles are in smem):
-// 256 query points per CTA in registers, set B streamed through shared memory in tiles of 1024 points
-// read as warp-wide broadcasts.
+// This op is FP32-ALU bound (no HBM traffic once tiles are in smem).  A thread owns FOUR query points as two packed-fp32 pairs
+// (sub / mul / fma.rn.f32x2: the same IEEE operations per lane, half the FP instructions), set B streams through shared memory
+// in tiles of 1024 float4 points read as warp-wide LDS.128 broadcasts (one load per four point pairs instead of three per pair).
 #include "common.cuh"
 
 namespace {
 
-constexpr int NND_THREADS = 256;
+constexpr int NND_THREADS = 128;
+constexpr int NND_Q = 4;          // query points per thread (two f32x2 pairs)
 constexpr int NND_TILE = 1024;
 
 __global__ void __launch_bounds__(NND_THREADS)
 nnd_fwd_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ dist,
                int* __restrict__ idx, int n, int m) {
-  __shared__ float sb[NND_TILE * 3];
+  __shared__ float4 sb[NND_TILE];
   const int b = blockIdx.y;
   const float* a = A + (size_t)b * n * 3;
   const float* bb = B + (size_t)b * m * 3;
-  const int j = blockIdx.x * NND_THREADS + threadIdx.x;
-  float ax = 0.f, ay = 0.f, az = 0.f;
-  if (j < n) { ax = a[j * 3]; ay = a[j * 3 + 1]; az = a[j * 3 + 2]; }
-  float best = 0.f;
-  int best_i = 0;
+  const int j0 = blockIdx.x * (NND_THREADS * NND_Q) + threadIdx.x;   // queries j0 + q * NND_THREADS
+  float ax[NND_Q], ay[NND_Q], az[NND_Q];
+#pragma unroll
+  for (int q = 0; q < NND_Q; ++q) {
+    const int j = j0 + q * NND_THREADS;
+    ax[q] = ay[q] = az[q] = 0.f;
+    if (j < n) { ax[q] = a[j * 3]; ay[q] = a[j * 3 + 1]; az[q] = a[j * 3 + 2]; }
+  }
+  const f32x2_t axp[2] = {f2_pack(ax[0], ax[1]), f2_pack(ax[2], ax[3])};
+  const f32x2_t ayp[2] = {f2_pack(ay[0], ay[1]), f2_pack(ay[2], ay[3])};
+  const f32x2_t azp[2] = {f2_pack(az[0], az[1]), f2_pack(az[2], az[3])};
+  float best[NND_Q] = {0.f, 0.f, 0.f, 0.f};
+  int best_i[NND_Q] = {0, 0, 0, 0};
+  // d = fma(dz,dz, fma(dx,dx, dy*dy)) for the two queries of a pair
+  auto dist2 = [&](const float4 p, int h) {
+    const f32x2_t dx = f2_sub(f2_dup(p.x), axp[h]), dy = f2_sub(f2_dup(p.y), ayp[h]), dz = f2_sub(f2_dup(p.z), azp[h]);
+    return f2_unpack(f2_fma(dz, dz, f2_fma(dx, dx, f2_mul(dy, dy))));
+  };
   for (int k0 = 0; k0 < m; k0 += NND_TILE) {
     const int cnt = min(NND_TILE, m - k0);
     __syncthreads();
-    for (int i = threadIdx.x; i < cnt * 3; i += NND_THREADS) sb[i] = bb[(size_t)k0 * 3 + i];
+    for (int i = threadIdx.x; i < cnt; i += NND_THREADS) {
+      const float* s = bb + (size_t)(k0 + i) * 3;
+      sb[i] = make_float4(s[0], s[1], s[2], 0.f);
+    }
     __syncthreads();
-    if (j < n) {
-      int k = 0;
-      if (k0 == 0) {  // reference: `k==0 || d<best`
-        float dx = __fsub_rn(sb[0], ax), dy = __fsub_rn(sb[1], ay), dz = __fsub_rn(sb[2], az);
-        best = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-        best_i = 0;
-        k = 1;
+    int k = 0;
+    if (k0 == 0) {  // reference: `k==0 || d<best`
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float2 d = dist2(sb[0], h);
+        best[2 * h] = d.x; best[2 * h + 1] = d.y;
       }
+      k = 1;
+    }
 #pragma unroll 4
-      for (; k < cnt; ++k) {
-        float dx = __fsub_rn(sb[k * 3], ax), dy = __fsub_rn(sb[k * 3 + 1], ay), dz = __fsub_rn(sb[k * 3 + 2], az);
-        float d = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-        if (d < best) { best = d; best_i = k0 + k; }
+    for (; k < cnt; ++k) {
+      const float4 p = sb[k];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float2 d = dist2(p, h);
+        if (d.x < best[2 * h]) { best[2 * h] = d.x; best_i[2 * h] = k0 + k; }
+        if (d.y < best[2 * h + 1]) { best[2 * h + 1] = d.y; best_i[2 * h + 1] = k0 + k; }
       }
     }
   }
-  if (j < n) {
-    dist[(size_t)b * n + j] = best;
-    idx[(size_t)b * n + j] = best_i;
+#pragma unroll
+  for (int q = 0; q < NND_Q; ++q) {
+    const int j = j0 + q * NND_THREADS;
+    if (j < n) {
+      dist[(size_t)b * n + j] = best[q];
+      idx[(size_t)b * n + j] = best_i[q];
+    }
   }
 }
 
@@ -81,8 +106,8 @@ extern "C" int nnd_forward_cuda(const float* xyz1, const float* xyz2, float* dis
     return 0;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  nnd_fwd_kernel<<<dim3((n + NND_THREADS - 1) / NND_THREADS, b), NND_THREADS, 0, st>>>(xyz1, xyz2, dist1, idx1, n, m);
-  nnd_fwd_kernel<<<dim3((m + NND_THREADS - 1) / NND_THREADS, b), NND_THREADS, 0, st>>>(xyz2, xyz1, dist2, idx2, m, n);
+  nnd_fwd_kernel<<<dim3((n + NND_THREADS * NND_Q - 1) / (NND_THREADS * NND_Q), b), NND_THREADS, 0, st>>>(xyz1, xyz2, dist1, idx1, n, m);
+  nnd_fwd_kernel<<<dim3((m + NND_THREADS * NND_Q - 1) / (NND_THREADS * NND_Q), b), NND_THREADS, 0, st>>>(xyz2, xyz1, dist2, idx2, m, n);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     gdrn_set_last_error(__FILE__, __LINE__, cudaGetErrorString(e));
