@@ -182,6 +182,16 @@ def ransac_voting_layer_v3(mask, vertex, round_hyp_num, inlier_thresh=0.999, con
 
 
 @_lib.on_device(1)
+def b_inv(b_mat):
+    """ransac_voting_gpu.py:107-120: batched matrix inverse used by the voting-distribution code; a singular batch falls back
+    to the identity like the reference (its torch.solve call predates torch.linalg)."""
+    eye = b_mat.new_ones(b_mat.size(-1)).diag().expand_as(b_mat)
+    try:
+        return torch.linalg.solve(b_mat, eye)
+    except RuntimeError:   # singular input (https://github.com/zju3dv/clean-pvnet/issues/8)
+        return eye
+
+
 def estimate_voting_distribution_with_mean(mask, vertex, mean, round_hyp_num=256, min_hyp_num=4096, topk=128,
                                            inlier_thresh=0.99, min_num=5, max_num=30000, output_hyp=False, seed=None):
     """ransac_voting_gpu.py:221-330: hypothesis cloud of `min_hyp_num` line intersections per keypoint, weighted by their
@@ -351,6 +361,35 @@ def uncertainty_pnp(points_2d, weights_2d, points_3d, camera_matrix):
         return np.concatenate([R, t], axis=-1)
     init_rt = np.concatenate([R_exp, t], 0)
     result_rt = uncertainty_pnp_refine(points_2d, weights_2d, points_3d, camera_matrix, init_rt)
+    R, _ = cv2.Rodrigues(result_rt[:3])
+    return np.concatenate([R, result_rt[3:, None]], axis=-1)
+
+
+def uncertainty_pnp_v2(points_2d, covars, points_3d, camera_matrix, type="single"):
+    """un_pnp_utils.py:81-158: the covariance form.  Every 2-D point carries a 2x2 covariance; its weight is the inverse of the
+    LARGEST eigenvalue (0 for a degenerate covariance, covars[i,0,0] < 1e-5), used isotropically ([w, 0, w] rows); EPnP on the
+    four highest-weight points, then the same weighted LM refine as uncertainty_pnp -> [3,4].  `type` is accepted and unused,
+    as in the reference."""
+    import cv2
+
+    pn = points_2d.shape[0]
+    assert points_3d.shape[0] == pn and pn >= 4 and covars.shape[0] == pn
+    points_3d = points_3d.astype(np.float64)
+    points_2d = points_2d.astype(np.float64)
+    camera_matrix = camera_matrix.astype(np.float64)
+    covars = np.asarray(covars)
+    lam = np.linalg.eigvals(covars.astype(np.float64)).real.max(axis=-1)        # [pn] largest eigenvalue of each covariance
+    ok = covars[:, 0, 0] >= 1e-5
+    w = np.where(ok, 1.0 / np.where(ok, lam, 1.0), 0.0)
+    idxs = np.argsort(w)[-4:]
+    dist_coeffs = np.zeros(shape=[8, 1], dtype=np.float64)
+    _, R_exp, t = cv2.solvePnP(np.expand_dims(points_3d[idxs, :], 0), np.expand_dims(points_2d[idxs, :], 0),
+                               camera_matrix, dist_coeffs, None, None, False, flags=cv2.SOLVEPNP_EPNP)
+    if pn == 4:
+        R, _ = cv2.Rodrigues(R_exp)
+        return np.concatenate([R, t], axis=-1)
+    weights_2d = np.stack([w, np.zeros(pn), w], axis=1)
+    result_rt = uncertainty_pnp_refine(points_2d, weights_2d, points_3d, camera_matrix, np.concatenate([R_exp, t], 0))
     R, _ = cv2.Rodrigues(result_rt[:3])
     return np.concatenate([R, result_rt[3:, None]], axis=-1)
 

@@ -1324,6 +1324,35 @@ def test_upnp_vs_vendored_ceres_and_epnp_wrapper(dev):
     assert pose4.shape == (3, 4) and np.abs(pose4[:, :3] @ pose4[:, :3].T - np.eye(3)).max() < 1e-6
 
 
+def test_uncertainty_pnp_v2_covariance_form(dev):
+    """un_pnp_utils.uncertainty_pnp_v2 (un_pnp_utils.py:81-158): per-point 2x2 covariances -> weight = 1 / largest eigenvalue
+    (0 for a degenerate covariance), EPnP on the four best points, weighted refine.  Must equal uncertainty_pnp called with
+    those weights as [w, 0, w] rows (the reference builds exactly that), and recover a noise-free pose."""
+    import cv2
+    from test_oracle_pinning import _upnp_problem
+
+    from gdrnpp_bop2022_b200 import native_ops
+
+    rs = np.random.RandomState(33)
+    K, rt, p2, p3, _, _ = _upnp_problem(rs, 12, 0.0)
+    sig = rs.uniform(0.5, 3.0, size=12)
+    rot = rs.uniform(0, np.pi, size=12)
+    covars = np.zeros((12, 2, 2))
+    for i in range(12):   # anisotropic covariances: eigenvalues sig^2 and (0.3 sig)^2, rotated
+        c, s_ = np.cos(rot[i]), np.sin(rot[i])
+        Rm = np.array([[c, -s_], [s_, c]])
+        covars[i] = Rm @ np.diag([sig[i] ** 2, (0.3 * sig[i]) ** 2]) @ Rm.T
+    covars[3] = 0.0            # degenerate covariance -> weight 0 (covars[i,0,0] < 1e-5)
+    w = np.where(covars[:, 0, 0] >= 1e-5, 1.0 / np.maximum(sig ** 2, 1e-30), 0.0)
+    pose = native_ops.uncertainty_pnp_v2(p2, covars, p3, K)
+    same = native_ops.uncertainty_pnp(p2, np.stack([w, np.zeros(12), w], 1), p3, K)
+    assert pose.shape == (3, 4) and np.abs(pose - same).max() < 1e-9
+    Rgt = cv2.Rodrigues(rt[:3])[0]
+    assert np.abs(pose[:, :3] - Rgt).max() < 1e-6 and np.abs(pose[:, 3] - rt[3:]).max() < 1e-6
+    pose4 = native_ops.uncertainty_pnp_v2(p2[:4], covars[[0, 1, 2, 4]], p3[:4], K)   # pn == 4: EPnP result only
+    assert pose4.shape == (3, 4) and np.abs(pose4[:, :3] @ pose4[:, :3].T - np.eye(3)).max() < 1e-6
+
+
 # --------------------------------------------------------------------- online training targets (SURVEY 8f-3)
 def _ref_calc_xyz_bp_batch(depth, R, T, K):
     """lib/pysixd/misc.py:412-446 (fmt="BHWC"), restated verbatim in torch (pure-torch reference code)."""

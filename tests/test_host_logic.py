@@ -188,3 +188,14 @@ def test_reference_style_config_loader(tmp_path):
     assert pn.GEO_HEAD.XYZ_CLASS_AWARE is True and cfg.TEST.DEPTH_REFINE_ITER == 2 and cfg.MODEL.PIXEL_STD[0] == 255.0
     m = GDRN_DoubleMask(cfg)          # the loaded config drives the model surface like the reference's mmcv Config
     assert m.num_classes == 21 and m.precision == "bf16x3"
+
+
+def test_b_inv_matches_the_reference_contract():
+    """ransac_voting_gpu.py:107-120: batched inverse; a singular batch yields the identity instead of raising."""
+    import torch
+
+    from gdrnpp_bop2022_b200.native_ops import b_inv
+
+    m = torch.randn(6, 3, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(0)) + 3 * torch.eye(3, dtype=torch.float64)
+    assert (b_inv(m) @ m - torch.eye(3, dtype=torch.float64)).abs().max().item() < 1e-12
+    assert torch.equal(b_inv(torch.zeros(2, 2, 2)), torch.eye(2).expand(2, 2, 2))
