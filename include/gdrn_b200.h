@@ -107,8 +107,9 @@ int gdrn_gemm_x3(const void* A, const void* W, const float* bias, const float* g
 /* In-place residual form (epi 2) of gdrn_gemm_x3 with the balanced k-split schedule of the CTA-pair kernel allowed:
  * x [M,N] fp32 += gamma * (A @ W^T + bias).  `flags` = flag_words ZEROED device words (>= 16 per 256 x block_n tile); the
  * kernel leaves them zeroed.  Tiles whose K range is split between two CTA pairs are reduce-added in a fixed order, so the
- * result is run-to-run deterministic.  GDRN_X3_KSPLIT=0 keeps whole tiles.  Exported for tests and measurement (the model
- * forward uses the same path for its fc2 GEMMs: timm ConvNeXtBlock.mlp.fc2 + layer scale + shortcut). */
+ * result is run-to-run deterministic.  The schedule is used when GDRN_X3_KSPLIT=1 (default 0 = whole tiles: measured no
+ * faster, the GEMMs are clock-limited by the power cap).  Exported for tests and measurement (the model forward
+ * passes the same flag words for its fc2 GEMMs: timm ConvNeXtBlock.mlp.fc2 + layer scale + shortcut). */
 int gdrn_gemm_x3_ksplit(const void* A, const void* W, const float* bias, const float* gamma, float* x, int M, int N, int K,
                         int block_n, unsigned* flags, int flag_words, void* stream);
 
