@@ -365,6 +365,15 @@ def uncertainty_pnp(points_2d, weights_2d, points_3d, camera_matrix):
     return np.concatenate([R, result_rt[3:, None]], axis=-1)
 
 
+def covariance_weights(covars):
+    """Per-point scalar weights of uncertainty_pnp_v2 (un_pnp_utils.py:96-104): 1 / (largest eigenvalue of the 2x2 covariance),
+    0 where the covariance is degenerate (covars[i, 0, 0] < 1e-5).  covars [pn,2,2] -> float64 [pn]."""
+    covars = np.asarray(covars)
+    lam = np.linalg.eigvals(covars.astype(np.float64)).real.max(axis=-1)        # [pn] largest eigenvalue of each covariance
+    ok = covars[:, 0, 0] >= 1e-5
+    return np.where(ok, 1.0 / np.where(ok, lam, 1.0), 0.0)
+
+
 def uncertainty_pnp_v2(points_2d, covars, points_3d, camera_matrix, type="single"):
     """un_pnp_utils.py:81-158: the covariance form.  Every 2-D point carries a 2x2 covariance; its weight is the inverse of the
     LARGEST eigenvalue (0 for a degenerate covariance, covars[i,0,0] < 1e-5), used isotropically ([w, 0, w] rows); EPnP on the
@@ -377,10 +386,7 @@ def uncertainty_pnp_v2(points_2d, covars, points_3d, camera_matrix, type="single
     points_3d = points_3d.astype(np.float64)
     points_2d = points_2d.astype(np.float64)
     camera_matrix = camera_matrix.astype(np.float64)
-    covars = np.asarray(covars)
-    lam = np.linalg.eigvals(covars.astype(np.float64)).real.max(axis=-1)        # [pn] largest eigenvalue of each covariance
-    ok = covars[:, 0, 0] >= 1e-5
-    w = np.where(ok, 1.0 / np.where(ok, lam, 1.0), 0.0)
+    w = covariance_weights(covars)
     idxs = np.argsort(w)[-4:]
     dist_coeffs = np.zeros(shape=[8, 1], dtype=np.float64)
     _, R_exp, t = cv2.solvePnP(np.expand_dims(points_3d[idxs, :], 0), np.expand_dims(points_2d[idxs, :], 0),

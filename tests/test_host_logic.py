@@ -199,3 +199,25 @@ def test_b_inv_matches_the_reference_contract():
     m = torch.randn(6, 3, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(0)) + 3 * torch.eye(3, dtype=torch.float64)
     assert (b_inv(m) @ m - torch.eye(3, dtype=torch.float64)).abs().max().item() < 1e-12
     assert torch.equal(b_inv(torch.zeros(2, 2, 2)), torch.eye(2).expand(2, 2, 2))
+
+
+def test_covariance_weights_follow_the_reference_loop():
+    """un_pnp_utils.py:96-104 restated as the reference's per-point loop (np.max(np.linalg.eigvals(C)), 0 for C[0,0] < 1e-5)."""
+    import numpy as np
+
+    from gdrnpp_bop2022_b200.native_ops import covariance_weights
+
+    rs = np.random.RandomState(4)
+    A = rs.randn(40, 2, 2)
+    covars = A @ A.transpose(0, 2, 1) * rs.uniform(0.01, 4.0, size=(40, 1, 1))
+    covars[5] = 0.0
+    covars[17, 0, 0] = 1e-6
+    ref = []
+    for pi in range(40):
+        if covars[pi, 0, 0] < 1e-5:
+            ref.append(0.0)
+        else:
+            ref.append(1.0 / np.max(np.linalg.eigvals(covars[pi])))
+    got = covariance_weights(covars)
+    assert got.dtype == np.float64 and np.allclose(got, np.asarray(ref), rtol=1e-13, atol=0)
+    assert got[5] == 0.0 and got[17] == 0.0
